@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py — Mpixels/s of the feature-detection hot path (Harris + Canny + FHOG) on 4K frames.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+  torchrun --nproc-per-node N bench.py --gpus N ...        (one rank per GPU, frames sharded, no
+                                                            data-path collective: weak scaling)
+
+A step = one pass of the three detectors over one batch of B synthetic 3840x2160 frames per GPU
+(grey plane -> Harris corners and Canny edge map, RGB planes -> FHOG).  The JSON line reports
+  value   : whole-job Mpixels/s with the frames already resident in HBM (device-timed, CUDA events)
+  e2e     : the same through the public host API (pinned host buffers, H2D + D2H inside the timing)
+  roofline: the fused Harris gradient+response kernel, algorithmic 5 B/pixel (u8 in, f32 R out),
+            achieved GB/s from CUDA events around back-to-back launches, against MEASURED_PEAKS.json
+  cpu_baseline: the reference's own C/C++ (oracle/_ref) on this box's host cores, bounded sample.
+`--impl reference` times only the reference CPU implementation (all host threads).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NX, NY = 3840, 2160
+HARRIS_KW = dict(k=0.06, sigma_d=1.0, sigma_i=2.5, threshold=130.0, gaussian=0, gradient=0, measure=0)
+CANNY_KW = dict(s=2.0, low_thr=3.0, high_thr=10.0, accGrad=True)
+FHOG_KW = dict(cell=8, frp=1, fcp=1)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons}
+
+
+def available_detectors():
+    import image_b200
+    d = ["harris"]
+    try:
+        from image_b200 import canny  # noqa: F401
+        d.append("canny")
+    except ImportError:
+        pass
+    try:
+        from image_b200 import dlib  # noqa: F401
+        d.append("fhog")
+    except ImportError:
+        pass
+    return d
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, dets):
+    """The reference's own CPU implementation (oracle/_ref when built, else the oracle port) on the
+    box's host cores.  Harris is OpenMP-parallel inside one frame (reference behaviour); Canny and
+    FHOG are single-threaded in the reference, so independent frames run one per core."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import pyoracle as po
+    from image_b200 import synth
+    cores = os.cpu_count() or 1
+    if po.lib("oracle") is None:
+        po.build(ref=False)
+        po._cache.clear()
+    kind = "reference" if all(po.have_ref(w) for w in ("harris", "canny", "dlib")) else "port"
+    impl = "ref" if kind == "reference" else "oracle"
+    nf = max(1, args.ref_frames)
+    rgb = [synth.frame_rgb(2000 + i, NY, NX) for i in range(nf)]
+    grey = [np.ascontiguousarray(f[..., 1]) for f in rgb]
+
+    def step():
+        if "harris" in dets:
+            for g in grey:
+                po.harris_detect(g, precision=0, impl=impl, **{k: v for k, v in HARRIS_KW.items()})
+        with ThreadPoolExecutor(max_workers=cores) as ex:
+            jobs = []
+            if "canny" in dets:
+                jobs += [ex.submit(po.canny, g, impl=impl, **CANNY_KW) for g in grey]
+            if "fhog" in dets:
+                jobs += [ex.submit(po.fhog, f, impl=impl, **FHOG_KW) for f in rgb]
+            for j in jobs:
+                j.result()
+
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    mpix = nf * NX * NY / dt / 1e6
+    line = {
+        "impl": "reference", "metric": "Mpixels/sec (Harris+Canny+HOG) at 4K frames", "value": mpix, "unit": "Mpixels/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64/f32 (CPU reference)",
+        "data": "synthetic",
+        "config": {"workload": "+".join(dets) + " @3840x2160", "frames_per_step": nf, "detectors": dets},
+        "cpu_baseline": {"value": mpix, "unit": "Mpixels/s", "cores": cores, "kind": kind,
+                         "sample": "%d synthetic 4K frame(s) per step, %d steps; Harris OpenMP, Canny/FHOG one frame per core%s"
+                                   % (nf, args.steps, "; Canny FFT through the oracle DFT shim (FFTW3 absent)" if kind == "reference" else "")},
+        "e2e": {"value": mpix, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=16, help="4K frames per GPU per step")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ref-frames", type=int, default=2)
+    ap.add_argument("--detectors", default="")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank == 0:
+            dets = args.detectors.split(",") if args.detectors else ["harris", "canny", "fhog"]
+            from oracle import pyoracle as po
+            if po.lib("oracle") is None:
+                po.build(ref=False); po._cache.clear()
+            dets = [d for d in dets if (d != "fhog" or hasattr(po.lib("oracle"), "orc_fhog") or po.have_ref("dlib"))]
+            run_reference(args, dets)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from image_b200 import _lib, synth
+    from image_b200 import harris as H
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback "
+                         "(use --impl reference for the CPU reference arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _lib.load()
+    ctx = _lib.context(local)
+    dets = args.detectors.split(",") if args.detectors else available_detectors()
+    B = args.batch
+    W = max(args.warmup, 3)
+    K = args.steps
+
+    # ---- synthetic frames (seeded per rank: frames are independent units, sharded across ranks)
+    rgb = synth.batch(synth.frame_rgb, 2000 + 1000 * rank, B, NY, NX, distinct=2)      # [B, NY, NX, 3] u8
+    grey = np.ascontiguousarray(rgb[..., 1])
+    h_rgb = torch.from_numpy(rgb).pin_memory()
+    h_grey = torch.from_numpy(grey).pin_memory()
+    d_rgb = h_rgb.cuda()
+    d_grey = h_grey.cuda()
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+
+    # ---- device-resident outputs
+    d_R = torch.empty((B, NY, NX), dtype=torch.float32, device="cuda")
+    cap = 65536
+    d_xy = torch.empty((B, cap), dtype=torch.int32, device="cuda")
+    d_st = torch.empty((B, cap), dtype=torch.float32, device="cuda")
+    d_cnt = torch.empty(B, dtype=torch.int32, device="cuda")
+    radius = int(2 * HARRIS_KW["sigma_i"] + 0.5)
+    if "canny" in dets:
+        from image_b200 import canny as Cn
+        d_edges = torch.empty((B, NY, NX), dtype=torch.uint8, device="cuda")
+        d_nz = torch.empty(B, dtype=torch.int32, device="cuda")
+    if "fhog" in dets:
+        from image_b200 import dlib as Dl
+        hnr, hnc = Dl.fhog_size(NY, NX, **FHOG_KW)
+        d_hog = torch.empty((B, hnr, hnc, 31), dtype=torch.float32, device="cuda")
+
+    def step_dev():
+        H.harris_response_dev(d_grey, True, B, NX, NY, d_R, stream=sp, **HARRIS_KW)
+        H.harris_nms_dev(d_R, B, NX, NY, HARRIS_KW["threshold"], radius, cap, d_xy, d_st, d_cnt, stream=sp)
+        if "canny" in dets:
+            Cn.canny_dev(d_grey, B, NX, NY, d_edges, d_nz, stream=sp, **CANNY_KW)
+        if "fhog" in dets:
+            Dl.fhog_dev(d_rgb, B, NY, NX, d_hog, stream=sp, **FHOG_KW)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(k):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- warm-up, then the device-resident timed region (inputs 16 x 8.3 MB grey + 16 x 24.9 MB
+    #      RGB per step >> 126 MB L2, so every step streams from HBM)
+    for _ in range(W):
+        step_dev()
+    l0 = lib.b2f_launch_count(ctx)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(step_dev, K)
+    launches = int(lib.b2f_launch_count(ctx) - l0)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / K
+    value = world * B * NX * NY / (ms_step * 1e-3) / 1e6
+
+    # ---- per-detector device times (explain the headline)
+    detail = {}
+
+    def t_of(fn, k=5):
+        return timed(fn, k) / k
+    th = t_of(lambda: H.harris_response_dev(d_grey, True, B, NX, NY, d_R, stream=sp, **HARRIS_KW))
+    tn = t_of(lambda: H.harris_nms_dev(d_R, B, NX, NY, HARRIS_KW["threshold"], radius, cap, d_xy, d_st, d_cnt, stream=sp))
+    detail["harris_response_ms"] = th
+    detail["harris_nms_ms"] = tn
+    if "canny" in dets:
+        detail["canny_ms"] = t_of(lambda: Cn.canny_dev(d_grey, B, NX, NY, d_edges, d_nz, stream=sp, **CANNY_KW))
+    if "fhog" in dets:
+        detail["fhog_ms"] = t_of(lambda: Dl.fhog_dev(d_rgb, B, NY, NX, d_hog, stream=sp, **FHOG_KW))
+
+    # ---- roofline of the dominant target kernel: fused Harris gradient+response, 5 B/px algorithmic
+    peak, peak_src = peaks()
+    alg_bytes = 5.0 * B * NX * NY
+    achieved = alg_bytes / (th * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "harris_fused_kernel<3,7,u8>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": alg_bytes,
+            "note": "fp32-issue bound, not HBM bound: ~170 fp32 instructions per pixel (DESIGN.md §4)"}
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            roof["traffic"] = json.load(open(tp)).get("harris_fused_bytes_per_launch_b%d" % B)
+        except Exception:
+            pass
+
+    # ---- end to end through the public host API (pinned host in, results back on the host)
+    e2e = None
+    h2d = d2h = 0
+    try:
+        np_grey = h_grey.numpy()
+        np_rgb = h_rgb.numpy()
+
+        def step_e2e():
+            nonlocal h2d, d2h
+            outs = H.harris_batch_u8(np_grey, cap=cap, precision=0, **HARRIS_KW)
+            h2d = np_grey.nbytes
+            d2h = sum(o["x"].nbytes * 3 for o in outs) + 4 * B
+            if "canny" in dets:
+                e, nz = Cn.canny_batch(np_grey, **CANNY_KW)
+                h2d += np_grey.nbytes
+                d2h += e.nbytes + 4 * B
+            if "fhog" in dets:
+                hog = Dl.fhog_batch(np_rgb, **FHOG_KW)
+                h2d += np_rgb.nbytes
+                d2h += hog.nbytes
+        for _ in range(2):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        ke = max(2, K // 2)
+        for _ in range(ke):
+            step_e2e()
+        torch.cuda.synchronize()
+        dt = torch.tensor([(time.perf_counter() - t0) / ke], device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * B * NX * NY / float(dt.item()) / 1e6, "unit": "Mpixels/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "api": "harris_batch_u8 / canny_batch / fhog_batch (C ABI *_batch entry points, pinned host buffers)"}
+    except Exception as ex:   # keep the device-timed line even if the host path fails
+        e2e = {"value": None, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": str(ex)}
+
+    # ---- CPU baseline (rank 0, N=1 only): the reference's own code on a bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle import pyoracle as po
+            if po.lib("oracle") is None:
+                po.build(ref=False); po._cache.clear()
+            kind = "reference" if all(po.have_ref(w) for w in ("harris", "canny", "dlib")) else "port"
+            impl = "ref" if kind == "reference" else "oracle"
+            g1, f1 = grey[0], rgb[0]
+            t0 = time.perf_counter()
+            po.harris_detect(g1, precision=0, impl=impl, **HARRIS_KW)
+            t_h = time.perf_counter() - t0
+            parts = {"harris_s": t_h}
+            tot = t_h
+            if "canny" in dets:
+                t0 = time.perf_counter(); po.canny(g1, impl=impl, **CANNY_KW); parts["canny_s"] = time.perf_counter() - t0
+                tot += parts["canny_s"]
+            if "fhog" in dets:
+                t0 = time.perf_counter(); po.fhog(f1, impl=impl, **FHOG_KW); parts["fhog_s"] = time.perf_counter() - t0
+                tot += parts["fhog_s"]
+            cpu = {"value": NX * NY / tot / 1e6, "unit": "Mpixels/s", "cores": os.cpu_count(), "kind": kind,
+                   "sample": "1 synthetic 4K frame through %s (Harris OpenMP on all cores; Canny, FHOG single thread as in the reference)" % "+".join(dets),
+                   "parts": parts}
+        except Exception as ex:
+            cpu = {"value": None, "unit": "Mpixels/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %s" % ex}
+
+    if rank == 0:
+        line = {
+            "metric": "Mpixels/sec (Harris+Canny+HOG) at 4K frames", "value": value, "unit": "Mpixels/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (Harris, FHOG) / f64 (Canny)", "data": "synthetic",
+            "config": {"workload": "+".join(dets) + " @3840x2160, batch=%d frames per GPU per step" % B,
+                       "detectors": dets, "frames_per_gpu": B, "l2": "inputs larger than L2 (%.0f MB per step)" % ((grey.nbytes + rgb.nbytes) / 1e6),
+                       "parallelism": "frames sharded over %d GPU(s), no data-path collective" % world},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+            "detail_ms_per_step": detail,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,81 @@
+// common.cuh — context, scratch arena and error plumbing shared by the libb200feat kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/b2f.h"
+
+namespace b2f {
+
+void set_error(const char *fmt, ...);
+
+#define B2F_CUDA(expr)                                                                     \
+  do {                                                                                     \
+    cudaError_t e__ = (expr);                                                              \
+    if (e__ != cudaSuccess) {                                                              \
+      b2f::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return B2F_ECUDA;                                                                    \
+    }                                                                                      \
+  } while (0)
+
+#define B2F_LAUNCH_CHECK(ctx)                                                              \
+  do {                                                                                     \
+    (ctx)->launches++;                                                                     \
+    cudaError_t e__ = cudaGetLastError();                                                  \
+    if (e__ != cudaSuccess) {                                                              \
+      b2f::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return B2F_ECUDA;                                                                    \
+    }                                                                                      \
+  } while (0)
+
+// Bump allocator over one cudaMalloc'ed slab that grows (by reallocation, only between
+// calls) to the high-water mark.  Every public entry point does arena.reset() first.
+struct Arena {
+  char *base = nullptr;
+  size_t cap = 0, off = 0, need = 0;
+  bool overflow = false;
+  void reset() { off = 0; need = 0; overflow = false; }
+  template <typename T> T *get(size_t n) {
+    size_t bytes = (n * sizeof(T) + 255) & ~size_t(255);
+    need += bytes;
+    if (off + bytes > cap) { overflow = true; return nullptr; }
+    T *p = reinterpret_cast<T *>(base + off);
+    off += bytes;
+    return p;
+  }
+};
+
+}  // namespace b2f
+
+struct b2f_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  b2f::Arena arena;       // device scratch
+  void *pinned = nullptr; // pinned host staging
+  size_t pinned_cap = 0;
+  long long launches = 0;
+};
+
+namespace b2f {
+// Make sure the device scratch arena holds at least `bytes` (grows by reallocation; synchronises
+// the context stream first) and rewind it.  Every public entry point calls this once with an
+// upper bound of its scratch need, then carves buffers with ctx->arena.get<T>(n).
+int arena_reserve(b2f_ctx *ctx, size_t bytes);
+int pinned_reserve(b2f_ctx *ctx, size_t bytes);
+#define B2F_ARENA_CHECK(ctx)                                                                \
+  do {                                                                                     \
+    if ((ctx)->arena.overflow) {                                                           \
+      b2f::set_error("internal: scratch arena under-reserved (%zu needed, %zu held) at %s:%d", \
+                     (ctx)->arena.need, (ctx)->arena.cap, __FILE__, __LINE__);            \
+      return B2F_ENOMEM;                                                                   \
+    }                                                                                      \
+  } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align256(size_t b) { return (b + 255) & ~size_t(255); }
+}  // namespace b2f

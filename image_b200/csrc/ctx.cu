@@ -1,0 +1,108 @@
+// ctx.cu — lifecycle of a libb200feat context: CUDA device selection, the launch stream, the
+// device scratch arena and the pinned staging buffer.  No CPU fallback exists anywhere in this
+// library: b2f_init fails when no usable sm_100 device is present.
+#include "common.cuh"
+#include <cstdarg>
+
+namespace b2f {
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int arena_reserve(b2f_ctx *ctx, size_t bytes) {
+  ctx->arena.reset();
+  if (bytes <= ctx->arena.cap) return B2F_OK;
+  size_t want = bytes + (bytes >> 4) + (1u << 20);
+  B2F_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ctx->arena.base) B2F_CUDA(cudaFree(ctx->arena.base));
+  ctx->arena.base = nullptr;
+  ctx->arena.cap = 0;
+  void *p = nullptr;
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("cudaMalloc(%zu bytes of scratch) failed: %s", want, cudaGetErrorString(e));
+    return B2F_ENOMEM;
+  }
+  ctx->arena.base = static_cast<char *>(p);
+  ctx->arena.cap = want;
+  return B2F_OK;
+}
+
+int pinned_reserve(b2f_ctx *ctx, size_t bytes) {
+  if (bytes <= ctx->pinned_cap) return B2F_OK;
+  B2F_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ctx->pinned) B2F_CUDA(cudaFreeHost(ctx->pinned));
+  ctx->pinned = nullptr;
+  ctx->pinned_cap = 0;
+  void *p = nullptr;
+  cudaError_t e = cudaMallocHost(&p, bytes);
+  if (e != cudaSuccess) {
+    set_error("cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    return B2F_ENOMEM;
+  }
+  ctx->pinned = p;
+  ctx->pinned_cap = bytes;
+  return B2F_OK;
+}
+}  // namespace b2f
+
+extern "C" {
+
+const char *b2f_last_error(void) { return b2f::g_err; }
+const char *b2f_version(void) { return "b200feat 0.1 (sm_100a)"; }
+
+int b2f_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int b2f_init(int device, b2f_ctx **out) {
+  if (!out) { b2f::set_error("b2f_init: ctx pointer is NULL"); return B2F_EINVAL; }
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    b2f::set_error("b2f_init: no CUDA device available (%s); this library has no CPU path",
+                   e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    cudaGetLastError();
+    return B2F_ECUDA;
+  }
+  if (device < 0 || device >= n) { b2f::set_error("b2f_init: device %d out of range [0,%d)", device, n); return B2F_EINVAL; }
+  B2F_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  B2F_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    b2f::set_error("b2f_init: device %d is sm_%d%d; this build contains sm_100a code only", device, prop.major, prop.minor);
+    return B2F_EUNSUP;
+  }
+  b2f_ctx *c = new b2f_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { b2f::set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); delete c; return B2F_ECUDA; }
+  *out = c;
+  return B2F_OK;
+}
+
+void b2f_shutdown(b2f_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->arena.base) cudaFree(c->arena.base);
+  if (c->pinned) cudaFreeHost(c->pinned);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+void b2f_free(void *p) { free(p); }
+void *b2f_stream(b2f_ctx *c) { return c ? (void *)c->stream : nullptr; }
+long long b2f_launch_count(b2f_ctx *c) { return c ? c->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,439 @@
+// harris.cu — host orchestration + remaining kernels of the Harris corner path
+// (image.CornerDetectionHarris).
+//
+//   response map    harris_fused_kernel (harris_kernels.cuh) or the bit-exact staged kernels here
+//   NMS             nms_bitmask_kernel: window predicate of harris.cpp:141-255 -> 1 bit / pixel
+//   compaction      row_count / row_scan / emit kernels -> corners in raster order (harris.cpp:250-252)
+//   selection, sub-pixel, scale check (H7, <1 % of the time): host code in harris_host.cpp
+#include "harris_kernels.cuh"
+#include "harris_host.h"
+#include <cmath>
+#include <algorithm>
+
+namespace b2f {
+
+// ------------------------------------------------------------------------------------------
+// bit-exact staged kernels (reference operation order, no FMA contraction)
+// ------------------------------------------------------------------------------------------
+struct ExactTaps { double B[HARRIS_MAX_TAPS]; int size; };
+
+__device__ __forceinline__ int pad_index(int p, int n) {   // gaussian.cpp:345-349
+  if (p < 0) return -p;
+  if (p >= n) return 2 * n - 1 - p;
+  return p;
+}
+
+// one pass of discrete_gaussian (gaussian.cpp:332-361 rows / :363-392 columns)
+template <bool COLS>
+__global__ void exact_gauss_pass(const float *__restrict__ src, float *__restrict__ dst, int nx, int ny,
+                                 const __grid_constant__ ExactTaps tp) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= nx) return;
+  size_t plane = (size_t)nx * ny * blockIdx.z;
+  const float *s = src + plane;
+  const int n = COLS ? ny : nx, i = COLS ? y : x;
+  auto at = [&](int q) -> double {
+    int p = pad_index(q, n);
+    return (double)(COLS ? s[(size_t)p * nx + x] : s[(size_t)y * nx + p]);
+  };
+  double sum = __dmul_rn(tp.B[0], at(i));
+  for (int j = 1; j < tp.size; j++) sum = __dadd_rn(sum, __dmul_rn(tp.B[j], __dadd_rn(at(i - j), at(i + j))));
+  dst[plane + (size_t)y * nx + x] = __double2float_rn(sum);
+}
+
+// SII 1-D pass, one thread per line, sequential float running sum (gaussian.cpp:179-215)
+struct SiiCoef { float w[3]; int r[3]; };
+__global__ void exact_sii_pass(const float *__restrict__ src, float *__restrict__ dst, float *__restrict__ scratch,
+                               int nx, int ny, int cols, SiiCoef c) {
+  int line = blockIdx.x * blockDim.x + threadIdx.x;
+  int nlines = cols ? nx : ny;
+  if (line >= nlines) return;
+  size_t plane = (size_t)nx * ny * blockIdx.y;
+  const int n = cols ? ny : nx;
+  const size_t stride = cols ? nx : 1;
+  const float *s = src + plane + (cols ? (size_t)line : (size_t)line * nx);
+  float *d = dst + plane + (cols ? (size_t)line : (size_t)line * nx);
+  const int pad = c.r[0] + 1;
+  const int nmax = nx > ny ? nx : ny;
+  float *b = scratch + ((size_t)blockIdx.y * nmax + line) * (size_t)(nmax + 2 * pad) + pad;
+  float acc = 0.f;
+  for (int i = -pad; i < n + pad; i++) {
+    int q = i < 0 ? 0 : (i >= n ? n - 1 : i);
+    acc = __fadd_rn(acc, s[stride * q]);
+    b[i] = acc;
+  }
+  for (int i = 0; i < n; i++) {
+    float a = __fmul_rn(c.w[0], __fsub_rn(b[i + c.r[0]], b[i - c.r[0] - 1]));
+    a = __fadd_rn(a, __fmul_rn(c.w[1], __fsub_rn(b[i + c.r[1]], b[i - c.r[1] - 1])));
+    a = __fadd_rn(a, __fmul_rn(c.w[2], __fsub_rn(b[i + c.r[2]], b[i - c.r[2] - 1])));
+    d[stride * i] = a;
+  }
+}
+
+// gradient (gradient.cpp:17-128) + products (harris.cpp:57-62), exact float roundings
+__global__ void exact_grad_products(const float *__restrict__ Is, float *__restrict__ A, float *__restrict__ B,
+                                    float *__restrict__ C, int nx, int ny, int grad) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= nx) return;
+  size_t plane = (size_t)nx * ny * blockIdx.z;
+  const float *I = Is + plane;
+  int cx = min(max(x, 1), nx - 2), cy = min(max(y, 1), ny - 2);   // replicate rule, gradient.cpp:40-55
+  size_t p = (size_t)cy * nx + cx;
+  float ix, iy;
+  if (grad == 1) {
+    float hx = __fsub_rn(I[p + 1], I[p - 1]);
+    float dx = __fsub_rn(__fsub_rn(__fadd_rn(I[p - nx + 1], I[p + nx + 1]), I[p - nx - 1]), I[p + nx - 1]);
+    ix = __double2float_rn(__dadd_rn(__dmul_rn(0.25, (double)hx), __dmul_rn(0.125, (double)dx)));
+    float hy = __fsub_rn(I[p + nx], I[p - nx]);
+    float dy = __fsub_rn(__fsub_rn(__fadd_rn(I[p + nx + 1], I[p + nx - 1]), I[p - nx + 1]), I[p - nx - 1]);
+    iy = __double2float_rn(__dadd_rn(__dmul_rn(0.25, (double)hy), __dmul_rn(0.125, (double)dy)));
+  } else {
+    ix = __fmul_rn(0.5f, __fsub_rn(I[p + 1], I[p - 1]));
+    iy = __fmul_rn(0.5f, __fsub_rn(I[p + nx], I[p - nx]));
+  }
+  size_t o = plane + (size_t)y * nx + x;
+  A[o] = __fmul_rn(ix, ix); B[o] = __fmul_rn(ix, iy); C[o] = __fmul_rn(iy, iy);
+}
+
+__global__ void exact_response(const float *__restrict__ A, const float *__restrict__ B, const float *__restrict__ C,
+                               float *__restrict__ R, size_t n, float k, int measure) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) R[i] = corner_measure(A[i], B[i], C[i], k, measure);
+}
+
+__global__ void u8_to_float(const unsigned char *__restrict__ s, float *__restrict__ d, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) d[i] = (float)s[i];
+}
+
+// zoom_out (zoom.cpp:121-139): bicubic sampled at even integer positions == decimation
+__global__ void decimate2(const float *__restrict__ s, float *__restrict__ d, int nx, int ny) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  int nxx = nx / 2, nyy = ny / 2;
+  if (x < nxx && y < nyy) d[(size_t)y * nxx + x] = s[(size_t)(2 * y) * nx + 2 * x];
+}
+
+// ------------------------------------------------------------------------------------------
+// NMS: window predicate -> bitmask
+//   (x,y) in [r,n-r), R>=Th, strictly greater than every window value in rows above and
+//   same-row values to the right, >= same-row values to the left and rows below
+//   (harris.cpp:170-243 restated order-free).
+// ------------------------------------------------------------------------------------------
+constexpr int NMS_TW = 128, NMS_TH = 16, NMS_NT = 256;
+
+__global__ void __launch_bounds__(NMS_NT)
+nms_bitmask_kernel(const float *__restrict__ R, unsigned *__restrict__ mask, int nx, int ny, int words_per_row,
+                   float Th, int radius) {
+  extern __shared__ float tile[];
+  const int P = NMS_TW + 2 * radius;           // tile pitch
+  const int TH2 = NMS_TH + 2 * radius;
+  const int x0 = blockIdx.x * NMS_TW, y0 = blockIdx.y * NMS_TH;
+  const float *Rf = R + (size_t)nx * ny * blockIdx.z;
+  for (int i = threadIdx.x; i < P * TH2; i += NMS_NT) {
+    int r = i / P, c = i - r * P;
+    int gx = x0 - radius + c, gy = y0 - radius + r;
+    float v = -INFINITY;
+    if (gx >= 0 && gx < nx && gy >= 0 && gy < ny) v = __ldg(Rf + (size_t)gy * nx + gx);
+    tile[i] = v;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;    // 8 warps
+#pragma unroll 1
+  for (int s = warp; s < NMS_TH * (NMS_TW / 32); s += NMS_NT / 32) {
+    int row = s / (NMS_TW / 32), seg = s - row * (NMS_TW / 32);
+    int lx = seg * 32 + lane, gx = x0 + lx, gy = y0 + row;
+    const float *c = tile + (row + radius) * P + lx + radius;
+    float v = *c;
+    bool ok = gx >= radius && gx < nx - radius && gy >= radius && gy < ny - radius && !(v < Th);
+    if (ok) {   // cheap 3x3 pre-test, then the full window
+      ok = v > c[-P - 1] && v > c[-P] && v > c[-P + 1] && v > c[1] && v >= c[-1] && v >= c[P - 1] && v >= c[P] && v >= c[P + 1];
+    }
+    if (ok) {
+      for (int dy = -radius; dy <= radius && ok; dy++) {
+        const float *q = c + dy * P;
+        if (dy < 0) { for (int dx = -radius; dx <= radius; dx++) ok = ok && (v > q[dx]); }
+        else if (dy > 0) { for (int dx = -radius; dx <= radius; dx++) ok = ok && (v >= q[dx]); }
+        else {
+          for (int dx = -radius; dx < 0; dx++) ok = ok && (v >= q[dx]);
+          for (int dx = 1; dx <= radius; dx++) ok = ok && (v > q[dx]);
+        }
+      }
+    }
+    unsigned bits = __ballot_sync(0xffffffffu, ok);
+    int word = (x0 >> 5) + seg;
+    if (lane == 0 && gy < ny && word < words_per_row)
+      mask[((size_t)blockIdx.z * ny + gy) * words_per_row + word] = bits;
+  }
+}
+
+// per-frame: count set bits per row, exclusive scan over rows (one CTA per frame)
+__global__ void __launch_bounds__(1024)
+row_count_scan_kernel(const unsigned *__restrict__ mask, int *__restrict__ row_off, int *__restrict__ counts,
+                      int ny, int words_per_row) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry;
+  const unsigned *m = mask + (size_t)blockIdx.x * ny * words_per_row;
+  int *off = row_off + (size_t)blockIdx.x * ny;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < ny; base += blockDim.x) {
+    // each warp counts rows base + warp*32 .. +31 cooperatively: lane l sums words l, l+32, ...
+    int mycount = 0;   // count of row (base + threadIdx.x), produced via shuffles below
+    for (int rr = 0; rr < 32; rr++) {
+      int row = base + warp * 32 + rr;
+      int c = 0;
+      if (row < ny)
+        for (int w = lane; w < words_per_row; w += 32) c += __popc(m[(size_t)row * words_per_row + w]);
+      for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+      if (lane == rr) mycount = c;
+    }
+    // block-wide exclusive scan of mycount
+    int incl = mycount;
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int t = lane < nwarp ? warp_tot[lane] : 0;
+      int ti = t;
+      for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, ti, o); if (lane >= o) ti += u; }
+      warp_tot[lane] = ti - t;   // exclusive
+    }
+    __syncthreads();
+    int row = base + threadIdx.x;
+    int excl = carry + warp_tot[warp] + incl - mycount;
+    if (row < ny) off[row] = excl;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = excl + mycount;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) counts[blockIdx.x] = carry;
+}
+
+// one warp per row: expand the bitmask into (y*nx+x, R) records at the scanned offsets
+__global__ void emit_corners_kernel(const unsigned *__restrict__ mask, const int *__restrict__ row_off,
+                                    const float *__restrict__ R, int *__restrict__ xy, float *__restrict__ strength,
+                                    int nx, int ny, int words_per_row, int cap) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31, f = blockIdx.y;
+  if (row >= ny) return;
+  const unsigned *m = mask + ((size_t)f * ny + row) * words_per_row;
+  int base = row_off[(size_t)f * ny + row];
+  for (int w0 = 0; w0 < words_per_row; w0 += 32) {
+    int w = w0 + lane;
+    unsigned bits = w < words_per_row ? m[w] : 0u;
+    int c = __popc(bits), incl = c;
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    int pos = base + incl - c;
+    while (bits) {
+      int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      int x = w * 32 + b;
+      if (pos < cap) {
+        xy[(size_t)f * cap + pos] = row * nx + x;
+        strength[(size_t)f * cap + pos] = R[((size_t)f * ny + row) * nx + x];
+      }
+      pos++;
+    }
+    base += __shfl_sync(0xffffffffu, incl, 31);
+  }
+}
+
+// gather the 3x3 neighbourhood of selected corners (input of compute_subpixel_precision, harris.cpp:360-369)
+__global__ void gather3x3_kernel(const float *__restrict__ R, const int *__restrict__ xy, float *__restrict__ M,
+                                 int n, int nx) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int p = xy[i];
+  int k = 0;
+  for (int dy = -1; dy <= 1; dy++)
+    for (int dx = -1; dx <= 1; dx++) M[(size_t)i * 9 + k++] = R[(long long)p + (long long)dy * nx + dx];
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static int taps_double(float sigma, double *B) {     // gaussian.cpp:306-329
+  int size = (int)(3 * sigma) + 1;
+  if (size > HARRIS_MAX_TAPS) return -1;
+  float den_f = 2 * sigma * sigma;
+  double den = den_f, s = sigma;
+  for (int i = 0; i < size; i++) B[i] = 1 / (s * sqrt(2.0 * 3.1415926)) * exp(-i * i / den);
+  double norm = 0;
+  for (int i = 0; i < size; i++) norm += B[i];
+  norm *= 2;
+  norm -= B[0];
+  for (int i = 0; i < size; i++) B[i] /= norm;
+  return size;
+}
+
+template <int RD, int RI, bool U8, int GRAD>
+static int launch_fused_t(b2f_ctx *ctx, const void *d_frames, int n_frames, int nx, int ny, float *d_R,
+                          const HarrisConsts &kc, cudaStream_t st) {
+  using C = FusedCfg<RD, RI>;
+  auto kern = harris_fused_kernel<RD, RI, U8, GRAD>;
+  static bool configured = false;   // per instantiation
+  if (!configured) {
+    B2F_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    configured = true;
+  }
+  dim3 grid(ceil_div(nx, C::TW), ceil_div(ny, C::TH), n_frames);
+  kern<<<grid, C::NT, C::SMEM, st>>>(d_frames, d_R, nx, ny, kc);
+  B2F_LAUNCH_CHECK(ctx);
+  return B2F_OK;
+}
+
+template <int RD, int RI>
+static int launch_fused(b2f_ctx *ctx, const void *d_frames, bool u8, int grad, int n_frames, int nx, int ny,
+                        float *d_R, const HarrisConsts &kc, cudaStream_t st) {
+  if (u8) return grad ? launch_fused_t<RD, RI, true, 1>(ctx, d_frames, n_frames, nx, ny, d_R, kc, st)
+                      : launch_fused_t<RD, RI, true, 0>(ctx, d_frames, n_frames, nx, ny, d_R, kc, st);
+  return grad ? launch_fused_t<RD, RI, false, 1>(ctx, d_frames, n_frames, nx, ny, d_R, kc, st)
+              : launch_fused_t<RD, RI, false, 0>(ctx, d_frames, n_frames, nx, ny, d_R, kc, st);
+}
+
+bool harris_fused_supported(int nx, int ny, float sigma_d, float sigma_i, int gaussian) {
+  if (gaussian != 0) return false;
+  if (sigma_d <= 0 || sigma_i <= 0) return false;
+  int rd = (int)(3 * sigma_d), ri = (int)(3 * sigma_i);
+  if (!(rd == 3 && (ri == 7 || ri == 3))) return false;
+  // frames must be large enough that every reflection stays inside its own tile window
+  return nx >= 32 && ny >= 32 && (long long)nx * ny < (1ll << 31);
+}
+
+// exact staged path: d_I (float planes) is blurred IN PLACE like harris.cpp:511, R written to d_R.
+// Scratch: 4 float planes per frame (+ SII line buffers) from the arena.
+static int response_exact(b2f_ctx *ctx, float *d_I, int n_frames, int nx, int ny, const b2f_harris_params *p,
+                          float *d_R, cudaStream_t st) {
+  size_t plane = (size_t)nx * ny, tot = plane * n_frames;
+  float *T = ctx->arena.get<float>(tot), *A = ctx->arena.get<float>(tot), *B = ctx->arena.get<float>(tot),
+        *Cc = ctx->arena.get<float>(tot);
+  int g1 = p->gaussian, g2 = (p->gaussian == 2) ? 1 : p->gaussian;   // harris.cpp:64-65
+  const int nmax = nx > ny ? nx : ny;
+  float *sii_scratch = nullptr;
+  if (g1 == 1 || g2 == 1) {
+    // largest pad among the two sigmas
+    double sg = std::max(p->sigma_d, p->sigma_i);
+    int pad = (int)(76 * (sg / (100.0 / 3.14159265358979323846264338327950288)) + 0.5) + 1;
+    sii_scratch = ctx->arena.get<float>((size_t)n_frames * nmax * (nmax + 2 * pad));
+  }
+  B2F_ARENA_CHECK(ctx);
+
+  auto blur = [&](float *buf, float sigma, int type) -> int {   // gaussian(): gaussian.cpp:403-430, in place
+    if (type == 0) {
+      if (sigma <= 0) return B2F_OK;                               // copy of itself
+      ExactTaps tp;
+      tp.size = taps_double(sigma, tp.B);
+      if (tp.size < 0) { set_error("harris: sigma %.3f needs more than %d taps", sigma, HARRIS_MAX_TAPS); return B2F_EUNSUP; }
+      if (tp.size > nx) return B2F_OK;                             // gaussian.cpp:312 early-out
+      if (tp.size > ny) { set_error("harris: image height %d below the Gaussian half-width %d (undefined in the reference)", ny, tp.size); return B2F_EUNSUP; }
+      dim3 grid(ceil_div(nx, 128), ny, n_frames);
+      exact_gauss_pass<false><<<grid, 128, 0, st>>>(buf, T, nx, ny, tp);
+      B2F_LAUNCH_CHECK(ctx);
+      exact_gauss_pass<true><<<grid, 128, 0, st>>>(T, buf, nx, ny, tp);
+      B2F_LAUNCH_CHECK(ctx);
+      return B2F_OK;
+    }
+    if (type == 1) {
+      SiiCoef c;                                                   // gaussian.cpp:61-90, K=3
+      const double sigma0 = 100.0 / 3.14159265358979323846264338327950288;
+      static const short radii0[3] = {76, 46, 23};
+      static const float weights0[3] = {0.1618f, 0.5502f, 0.9495f};
+      double sum = 0;
+      for (int k = 0; k < 3; k++) {
+        c.r[k] = (int)(long)(radii0[k] * ((double)sigma / sigma0) + 0.5);
+        sum += weights0[k] * (2 * (long)c.r[k] + 1);
+      }
+      for (int k = 0; k < 3; k++) c.w[k] = (float)(weights0[k] / sum);
+      exact_sii_pass<<<dim3(ceil_div(ny, 64), n_frames), 64, 0, st>>>(buf, T, sii_scratch, nx, ny, 0, c);
+      B2F_LAUNCH_CHECK(ctx);
+      exact_sii_pass<<<dim3(ceil_div(nx, 64), n_frames), 64, 0, st>>>(T, buf, sii_scratch, nx, ny, 1, c);
+      B2F_LAUNCH_CHECK(ctx);
+      return B2F_OK;
+    }
+    return B2F_OK;   // NO_GAUSSIAN: copy of itself
+  };
+  int rc;
+  if ((rc = blur(d_I, p->sigma_d, g1)) != B2F_OK) return rc;
+  dim3 grid(ceil_div(nx, 128), ny, n_frames);
+  exact_grad_products<<<grid, 128, 0, st>>>(d_I, A, B, Cc, nx, ny, p->gradient == 1 ? 1 : 0);
+  B2F_LAUNCH_CHECK(ctx);
+  if ((rc = blur(A, p->sigma_i, g2)) != B2F_OK) return rc;
+  if ((rc = blur(B, p->sigma_i, g2)) != B2F_OK) return rc;
+  if ((rc = blur(Cc, p->sigma_i, g2)) != B2F_OK) return rc;
+  exact_response<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(A, B, Cc, d_R, tot, p->k, p->measure);
+  B2F_LAUNCH_CHECK(ctx);
+  return B2F_OK;
+}
+
+// response map for frames already on the device.  exact!=0 forces the staged bit-exact path.
+// For the exact path with u8 input (or when the caller's float planes must stay untouched) the
+// frames are first copied into arena scratch.
+int harris_response_device(b2f_ctx *ctx, const void *d_frames, bool u8, int n_frames, int nx, int ny,
+                           const b2f_harris_params *p, int exact, float *d_R, cudaStream_t st) {
+  if (!exact && harris_fused_supported(nx, ny, p->sigma_d, p->sigma_i, p->gaussian)) {
+    HarrisConsts kc;
+    memset(&kc, 0, sizeof(kc));
+    double Bd[HARRIS_MAX_TAPS], Bi[HARRIS_MAX_TAPS];
+    int sd = taps_double(p->sigma_d, Bd), si = taps_double(p->sigma_i, Bi);
+    const float gscale = (p->gradient == 1) ? 1.f : 0.25f;
+    for (int i = 0; i < sd; i++) kc.wd[i] = (float)Bd[i];
+    for (int i = 0; i < si; i++) { kc.wic[i] = (float)Bi[i]; kc.wir[i] = gscale * (float)Bi[i]; }
+    kc.k = p->k;
+    kc.measure = p->measure;
+    int ri = si - 1;
+    if (ri == 7) return launch_fused<3, 7>(ctx, d_frames, u8, p->gradient == 1, n_frames, nx, ny, d_R, kc, st);
+    return launch_fused<3, 3>(ctx, d_frames, u8, p->gradient == 1, n_frames, nx, ny, d_R, kc, st);
+  }
+  size_t tot = (size_t)nx * ny * n_frames;
+  float *I = ctx->arena.get<float>(tot);
+  B2F_ARENA_CHECK(ctx);
+  if (u8) {
+    u8_to_float<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(static_cast<const unsigned char *>(d_frames), I, tot);
+    B2F_LAUNCH_CHECK(ctx);
+  } else {
+    B2F_CUDA(cudaMemcpyAsync(I, d_frames, tot * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  return response_exact(ctx, I, n_frames, nx, ny, p, d_R, st);
+}
+
+int harris_nms_device(b2f_ctx *ctx, const float *d_R, int n_frames, int nx, int ny, float Th, int radius, int cap,
+                      int *d_xy, float *d_strength, int *d_counts, cudaStream_t st) {
+  if (radius < 1) radius = 1;                                   // harris.cpp:152 (after the size check :151)
+  const int wpr = ceil_div(nx, 32);
+  unsigned *mask = ctx->arena.get<unsigned>((size_t)n_frames * ny * wpr);
+  int *row_off = ctx->arena.get<int>((size_t)n_frames * ny);
+  B2F_ARENA_CHECK(ctx);
+  size_t smem = sizeof(float) * (size_t)(NMS_TW + 2 * radius) * (NMS_TH + 2 * radius);
+  if (smem > 200 * 1024) { set_error("harris: NMS radius %d too large", radius); return B2F_EUNSUP; }
+  if (smem > 48 * 1024) B2F_CUDA(cudaFuncSetAttribute(nms_bitmask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(ceil_div(nx, NMS_TW), ceil_div(ny, NMS_TH), n_frames);
+  nms_bitmask_kernel<<<grid, NMS_NT, smem, st>>>(d_R, mask, nx, ny, wpr, Th, radius);
+  B2F_LAUNCH_CHECK(ctx);
+  row_count_scan_kernel<<<n_frames, 1024, 0, st>>>(mask, row_off, d_counts, ny, wpr);
+  B2F_LAUNCH_CHECK(ctx);
+  emit_corners_kernel<<<dim3(ceil_div(ny, 8), n_frames), 256, 0, st>>>(mask, row_off, d_R, d_xy, d_strength, nx, ny, wpr, cap);
+  B2F_LAUNCH_CHECK(ctx);
+  return B2F_OK;
+}
+
+int harris_gather3x3(b2f_ctx *ctx, const float *d_R, const int *d_xy, float *d_M, int n, int nx, cudaStream_t st) {
+  if (n <= 0) return B2F_OK;
+  gather3x3_kernel<<<ceil_div(n, 256), 256, 0, st>>>(d_R, d_xy, d_M, n, nx);
+  B2F_LAUNCH_CHECK(ctx);
+  return B2F_OK;
+}
+
+int harris_decimate2(b2f_ctx *ctx, const float *d_src, float *d_dst, int nx, int ny, cudaStream_t st) {
+  decimate2<<<dim3(ceil_div(nx / 2, 128), ny / 2), 128, 0, st>>>(d_src, d_dst, nx, ny);
+  B2F_LAUNCH_CHECK(ctx);
+  return B2F_OK;
+}
+
+int harris_u8_to_float(b2f_ctx *ctx, const unsigned char *s, float *d, size_t n, cudaStream_t st) {
+  u8_to_float<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s, d, n);
+  B2F_LAUNCH_CHECK(ctx);
+  return B2F_OK;
+}
+
+}  // namespace b2f

@@ -1,0 +1,15 @@
+// harris_host.h — internal interface between the Harris kernels (harris.cu) and the C ABI
+// (harris_api.cu).
+#pragma once
+#include "common.cuh"
+namespace b2f {
+bool harris_fused_supported(int nx, int ny, float sigma_d, float sigma_i, int gaussian);
+int harris_response_device(b2f_ctx *ctx, const void *d_frames, bool u8, int n_frames, int nx, int ny,
+                           const b2f_harris_params *p, int exact, float *d_R, cudaStream_t st);
+int harris_nms_device(b2f_ctx *ctx, const float *d_R, int n_frames, int nx, int ny, float Th, int radius, int cap,
+                      int *d_xy, float *d_strength, int *d_counts, cudaStream_t st);
+int harris_gather3x3(b2f_ctx *ctx, const float *d_R, const int *d_xy, float *d_M, int n, int nx, cudaStream_t st);
+int harris_decimate2(b2f_ctx *ctx, const float *d_src, float *d_dst, int nx, int ny, cudaStream_t st);
+int harris_u8_to_float(b2f_ctx *ctx, const unsigned char *s, float *d, size_t n, cudaStream_t st);
+size_t harris_scratch_bytes(int n_frames, int nx, int ny, const b2f_harris_params *p, int cap);
+}  // namespace b2f

@@ -1,0 +1,134 @@
+/* b2f.h — C ABI of libb200feat.so, the B200-native (sm_100a) replacement for the per-pixel
+ * hot path of bnosac/image's image.CornerDetectionHarris, image.CannyEdges and image.dlib
+ * (FHOG / SURF).  Plain C: pointers and sizes only, no C++ / torch / R types.
+ *
+ * Each `*_host` entry point is what the body of one reference Rcpp export reduces to
+ * (INTEGRATION.md shows the four replacement bodies):
+ *   b2f_harris_host  <- detect_corners        image.CornerDetectionHarris/src/rcpp_harris.cpp:19-59
+ *   b2f_canny_host   <- canny_edge_detector   image.CannyEdges/src/rcpp_canny.cpp:122-245
+ *   b2f_fhog_host    <- dlib_fhog             image.dlib/src/rcpp_fhog.cpp:10-46
+ *   b2f_surf_host    <- dlib_surf_points      image.dlib/src/rcpp_surf.cpp:10-54
+ * The `*_batch` forms take n_frames equally-sized frames in HOST memory (new surface: the
+ * reference has no batch API; a single call is batch = 1) and the `*_dev` forms take frames
+ * already resident in HBM plus a CUDA stream (benchmark / pipeline use).
+ *
+ * Conventions
+ *   - images are row-major with x fastest: pixel (x,y) at [y*nx + x]  (nx = R's nrow)
+ *   - every function returns B2F_OK (0) or a negative B2F_E* code; b2f_last_error() gives the
+ *     thread-local message.  Nothing longjmps or throws across this boundary.
+ *   - buffers returned through `float **` / `double **` are malloc'ed by the library and are
+ *     released with b2f_free(); no pointer is retained after a call returns.
+ *   - the library never falls back to a CPU path: if no CUDA device is usable b2f_init fails.
+ */
+#ifndef B2F_H
+#define B2F_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2F_OK 0
+#define B2F_EINVAL (-1)   /* bad argument */
+#define B2F_ECUDA (-2)    /* CUDA runtime error (message has the cudaError string) */
+#define B2F_ENOMEM (-3)
+#define B2F_ECAP (-4)     /* caller-provided capacity too small (counts still reported) */
+#define B2F_EUNSUP (-5)   /* parameter combination not supported on the GPU path */
+
+typedef struct b2f_ctx b2f_ctx;   /* one per (host thread, device): stream + scratch arena */
+
+/* lifecycle — called from R_init_<pkg> / .onUnload in the R packages */
+int b2f_init(int device, b2f_ctx **ctx);
+void b2f_shutdown(b2f_ctx *ctx);
+const char *b2f_last_error(void);
+const char *b2f_version(void);
+int b2f_device_count(void);
+void b2f_free(void *p);
+/* the CUDA stream (cudaStream_t) this context launches on, for callers that time with events */
+void *b2f_stream(b2f_ctx *ctx);
+/* kernels launched by this context since creation (bench.py reports it as gpu_launches) */
+long long b2f_launch_count(b2f_ctx *ctx);
+
+/* ------------------------------------------------------------------------------ Harris ----
+ * Integer fields carry the C++ meaning seen at the .Call boundary (gaussian.h:14-16,
+ * gradient.h:14-15, harris.h:16-24, interpolation.h:13-15):
+ *   gaussian 0=STD 1=SII("fast") 2=none; gradient 0=central 1=Sobel; measure 0=Harris
+ *   1=Shi-Tomasi 2=harmonic mean; strategy 0=all 1=sorted 2=N best 3=N distributed;
+ *   precision 0=none 1=quadratic 2=quartic.                                                  */
+typedef struct {
+  float k, sigma_d, sigma_i, threshold;
+  int gaussian, gradient, strategy, Nselect, measure, Nscales, precision, cells, verbose;
+  /* not a reference argument: 0 = fused fp32 kernel (R within 1e-4 of the reference, corner lists
+   * identical except at float near-ties); 1 = staged kernels that repeat the reference's
+   * double-accumulate arithmetic operation by operation (R bit-identical, ~6x slower). */
+  int exact;
+} b2f_harris_params;
+void b2f_harris_default_params(b2f_harris_params *p);   /* defaults of rcpp_harris.cpp:19-32 */
+
+/* detect_corners: img = nx*ny floats (the reference narrows R's doubles to float first,
+ * rcpp_harris.cpp:35).  Outputs three malloc'ed arrays of *n floats (x, y, strength). */
+int b2f_harris_host(b2f_ctx *ctx, const float *img, int nx, int ny, const b2f_harris_params *p,
+                    float **x, float **y, float **strength, int *n);
+
+/* batch of u8 frames in host memory; per frame at most `cap` corners are written at
+ * x[f*cap + i] ...; counts[f] is the true count (B2F_ECAP if any exceeds cap). */
+int b2f_harris_batch_u8(b2f_ctx *ctx, const uint8_t *frames, int n_frames, int nx, int ny,
+                        const b2f_harris_params *p, int cap, float *x, float *y, float *strength,
+                        int *counts);
+
+/* device-resident stages.  d_frames: n_frames planes of nx*ny u8 (is_u8=1) or float (0) in HBM.
+ * d_R: n_frames*nx*ny floats.  Asynchronous on `stream` (cudaStream_t; NULL = ctx stream). */
+int b2f_harris_response_dev(b2f_ctx *ctx, const void *d_frames, int is_u8, int n_frames, int nx, int ny,
+                            const b2f_harris_params *p, float *d_R, void *stream);
+/* NMS + raster-ordered compaction on device: d_xy receives y*nx+x (int32), d_strength the R
+ * value, d_counts[f] the number of corners of frame f (may exceed cap; only cap are stored). */
+int b2f_harris_nms_dev(b2f_ctx *ctx, const float *d_R, int n_frames, int nx, int ny, float threshold,
+                       int radius, int cap, int *d_xy, float *d_strength, int *d_counts, void *stream);
+
+/* ------------------------------------------------------------------------------- Canny ----
+ * canny_edge_detector: img = nx*ny u8 (R's ints are narrowed to unsigned char,
+ * rcpp_canny.cpp:137); low/high thresholds are truncated to int exactly like the reference
+ * (rcpp_canny.cpp:88,180).  edges = nx*ny bytes, 0 or 255; *nonzero = number of 255s. */
+int b2f_canny_host(b2f_ctx *ctx, const uint8_t *img, int nx, int ny, double s, double low_thr,
+                   double high_thr, int acc_grad, uint8_t *edges, int *nonzero);
+int b2f_canny_batch(b2f_ctx *ctx, const uint8_t *frames, int n_frames, int nx, int ny, double s,
+                    double low_thr, double high_thr, int acc_grad, uint8_t *edges, int *nonzero);
+int b2f_canny_dev(b2f_ctx *ctx, const uint8_t *d_frames, int n_frames, int nx, int ny, double s,
+                  double low_thr, double high_thr, int acc_grad, uint8_t *d_edges, int *d_nonzero,
+                  void *stream);
+
+/* -------------------------------------------------------------------------------- FHOG ----
+ * dlib_fhog: rgb = rows*cols*3 interleaved u8 (x[3*c + 3*cols*r + ch], rcpp_fhog.cpp:19-23).
+ * Output `hog` is [hog_nr][hog_nc][31] floats (row, col, feature) — the element order of
+ * dlib's array2d<matrix<float,31,1>>; the Rcpp shim transposes to R's y + nr*(x + nc*feat).
+ * b2f_fhog_size gives the output shape for given inputs (fhog.h:790-813, init_hog :448-471). */
+int b2f_fhog_size(int rows, int cols, int cell_size, int filter_rows_padding, int filter_cols_padding,
+                  int *hog_nr, int *hog_nc);
+int b2f_fhog_host(b2f_ctx *ctx, const uint8_t *rgb, int rows, int cols, int cell_size,
+                  int filter_rows_padding, int filter_cols_padding, float *hog);
+int b2f_fhog_batch(b2f_ctx *ctx, const uint8_t *frames, int n_frames, int rows, int cols, int cell_size,
+                   int filter_rows_padding, int filter_cols_padding, float *hog);
+int b2f_fhog_dev(b2f_ctx *ctx, const uint8_t *d_frames, int n_frames, int rows, int cols, int cell_size,
+                 int filter_rows_padding, int filter_cols_padding, float *d_hog, void *stream);
+
+/* -------------------------------------------------------------------------------- SURF ----
+ * dlib_surf_points: same input layout as FHOG.  One record per key point, in the order the
+ * reference returns them (score descending, surf.h:268-285). */
+typedef struct {
+  double x, y;          /* interest_point::center */
+  double angle;         /* surf_point::angle */
+  double scale;         /* interest_point::scale   (R: pyramid_scale) */
+  double score;         /* interest_point::score */
+  double laplacian;     /* +1 / -1 */
+  double des[64];       /* surf_point::des */
+} b2f_surf_point;
+int b2f_surf_host(b2f_ctx *ctx, const uint8_t *rgb, int rows, int cols, long max_points,
+                  double detection_threshold, b2f_surf_point **points, int *n);
+int b2f_surf_batch(b2f_ctx *ctx, const uint8_t *frames, int n_frames, int rows, int cols, long max_points,
+                   double detection_threshold, int cap, b2f_surf_point *points, int *counts);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2F_H */
