@@ -197,7 +197,8 @@ def main():
     h_grey = torch.from_numpy(grey).pin_memory()
     d_rgb = h_rgb.cuda()
     d_grey = h_grey.cuda()
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # a real (non-default) stream: the C ABI launches on it and
+    torch.cuda.set_stream(stream)         # the CUDA events below are recorded on the same stream
     sp = stream.cuda_stream
 
     # ---- device-resident outputs
@@ -251,6 +252,7 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        time.sleep(0.25)
     ms_total = timed(step_dev, K)
     launches = int(lib.b2f_launch_count(ctx) - l0)
     clocks = sampler.stop() if rank == 0 else None

@@ -1,0 +1,432 @@
+// canny.cu — the Canny edge path (image.CannyEdges).
+//
+//   canny_blur_kernel      circular Gaussian blur, u8 -> float-rounded plane.  The reference runs a
+//                          2-D FFT (tools.c:89-202); this is the same circular convolution evaluated
+//                          directly: separable, double accumulation in a FIXED order (centre tap, then
+//                          symmetric pairs by increasing distance), narrowed to float exactly like
+//                          tools.c:129.  One CTA = 32x128 output tile, row pass into shared memory,
+//                          column pass out of it; wrap-around addressing (tools.c:151-155).
+//   canny_grad_nms_kernel  gradient (rcpp_canny.cpp:153-175) with glibc's hypot reproduced operation
+//                          by operation, then the interpolated non-maximum suppression of
+//                          maxima()/bilin() (rcpp_canny.cpp:65-106) -> class 0/1/2 per pixel.
+//   hysteresis             union-find over the 8-neighbourhood of class!=0 pixels (the reference's
+//                          adsf_* disjoint-set forest, adsf.c:17-50, rcpp_canny.cpp:184-215) done with
+//                          lock-free atomicMin links; a component survives iff it holds a class-2 pixel.
+//   All arithmetic that feeds a comparison is IEEE double with explicit rounding intrinsics, i.e. no
+//   FMA contraction, because the edge map has to come out bit-identical.
+#include "common.cuh"
+#include <cmath>
+#include <vector>
+
+namespace b2f {
+
+constexpr int CANNY_MAXR = 64;       // taps beyond this radius use the generic (unrolled-less) path
+struct CannyTaps {
+  double w[CANNY_MAXR + 1];          // w[k] for distance k (symmetric list)
+  int R;
+};
+
+// ------------------------------------------------------------------------------------------ blur
+constexpr int CB_TW = 32, CB_TH = 128, CB_NT = 256;
+
+__device__ __forceinline__ double u32_to_double(unsigned s) {
+  // exact int -> double without the conversion unit: (2^52 + s) - 2^52
+  return __dadd_rn(__hiloint2double(0x43300000, (int)s), -4503599627370496.0);
+}
+
+template <int RT>
+__global__ void __launch_bounds__(CB_NT)
+canny_blur_kernel(const unsigned char *__restrict__ frames, float *__restrict__ out, int nx, int ny,
+                  const __grid_constant__ CannyTaps tx, const __grid_constant__ CannyTaps ty) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int RX = RT ? RT : tx.R, RY = RT ? RT : ty.R;
+  const int TILE_H = CB_TH + 2 * RY, TILE_W = CB_TW + 2 * RX;
+  const int TP = (TILE_W + 3) & ~3;                       // u8 pitch
+  double *rowbuf = reinterpret_cast<double *>(smem_raw);  // [TILE_H][CB_TW]
+  unsigned char *tile = smem_raw + sizeof(double) * (size_t)TILE_H * CB_TW;
+  const int x0 = blockIdx.x * CB_TW, y0 = blockIdx.y * CB_TH;
+  const unsigned char *src = frames + (size_t)blockIdx.z * nx * ny;
+  // ---- load with wrap-around (circular convolution)
+  for (int i = threadIdx.x; i < TILE_H * TILE_W; i += CB_NT) {
+    int r = i / TILE_W, c = i - r * TILE_W;
+    int gx = (x0 - RX + c) % nx; if (gx < 0) gx += nx;
+    int gy = (y0 - RY + r) % ny; if (gy < 0) gy += ny;
+    tile[r * TP + c] = __ldg(src + (size_t)gy * nx + gx);
+  }
+  __syncthreads();
+  // ---- row pass: rowbuf[r][c] = w0*v0 + sum_k wk*(v[-k]+v[+k])   (pair sums are exact integers)
+  {
+    const int c = threadIdx.x & 31;
+    for (int r = threadIdx.x >> 5; r < TILE_H; r += CB_NT / 32) {
+      const unsigned char *p = tile + r * TP + c + RX;
+      double acc = __dmul_rn(tx.w[0], u32_to_double(p[0]));
+#pragma unroll
+      for (int k = 1; k <= (RT ? RT : CANNY_MAXR); k++) {
+        if (!RT && k > RX) break;
+        acc = __dadd_rn(acc, __dmul_rn(tx.w[k], u32_to_double((unsigned)p[-k] + (unsigned)p[k])));
+      }
+      rowbuf[r * CB_TW + c] = acc;
+    }
+  }
+  __syncthreads();
+  // ---- column pass, register-blocked 8 rows per thread, then narrow to float (tools.c:129)
+  {
+    const int c = threadIdx.x & 31;
+    const int gx = x0 + c;
+    float *dst = out + (size_t)blockIdx.z * nx * ny;
+    if (RT) {
+      constexpr int RB = 8;
+      constexpr int RR = RT ? RT : 1;
+      for (int rg = threadIdx.x >> 5; rg < CB_TH / RB; rg += CB_NT / 32) {
+        double v[RB + 2 * RR];
+#pragma unroll
+        for (int q = 0; q < RB + 2 * RR; q++) v[q] = rowbuf[(rg * RB + q) * CB_TW + c];
+#pragma unroll
+        for (int j = 0; j < RB; j++) {
+          double acc = __dmul_rn(ty.w[0], v[j + RR]);
+#pragma unroll
+          for (int k = 1; k <= RR; k++) acc = __dadd_rn(acc, __dmul_rn(ty.w[k], __dadd_rn(v[j + RR - k], v[j + RR + k])));
+          int gy = y0 + rg * RB + j;
+          if (gx < nx && gy < ny) dst[(size_t)gy * nx + gx] = __double2float_rn(acc);
+        }
+      }
+    } else {
+      for (int r = threadIdx.x >> 5; r < CB_TH; r += CB_NT / 32) {
+        const double *p = rowbuf + (r + RY) * CB_TW + c;
+        double acc = __dmul_rn(ty.w[0], p[0]);
+        for (int k = 1; k <= RY; k++) acc = __dadd_rn(acc, __dmul_rn(ty.w[k], __dadd_rn(p[-k * CB_TW], p[k * CB_TW])));
+        int gy = y0 + r;
+        if (gx < nx && gy < ny) dst[(size_t)gy * nx + gx] = __double2float_rn(acc);
+      }
+    }
+  }
+}
+
+// generic tap lists (tiny images where the wrapped kernel is not symmetric): one thread per pixel,
+// taps applied in ascending coordinate order — the order the oracle uses for that case.
+struct TapList { const int *coord; const double *weight; int n; };
+__global__ void canny_blur_generic_rows(const unsigned char *__restrict__ frames, double *__restrict__ tmp, int nx, int ny,
+                                        TapList t) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= nx) return;
+  const unsigned char *src = frames + (size_t)blockIdx.z * nx * ny + (size_t)y * nx;
+  double acc = 0;
+  for (int i = 0; i < t.n; i++) {
+    int q = (x - t.coord[i]) % nx; if (q < 0) q += nx;
+    acc = __dadd_rn(acc, __dmul_rn(t.weight[i], (double)src[q]));
+  }
+  tmp[(size_t)blockIdx.z * nx * ny + (size_t)y * nx + x] = acc;
+}
+__global__ void canny_blur_generic_cols(const double *__restrict__ tmp, float *__restrict__ out, int nx, int ny, TapList t) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= nx) return;
+  const double *src = tmp + (size_t)blockIdx.z * nx * ny;
+  double acc = 0;
+  for (int i = 0; i < t.n; i++) {
+    int q = (y - t.coord[i]) % ny; if (q < 0) q += ny;
+    acc = __dadd_rn(acc, __dmul_rn(t.weight[i], src[(size_t)q * nx + x]));
+  }
+  out[(size_t)blockIdx.z * nx * ny + (size_t)y * nx + x] = __double2float_rn(acc);
+}
+
+// ------------------------------------------------------------------------------------------ gradient + NMS
+// glibc 2.39 hypot for finite, moderate arguments (sysdeps/ieee754/dbl-64/e_hypot.c, non-FMA kernel),
+// reproduced operation by operation so that grad is bit-identical to the reference's libm call
+// (rcpp_canny.cpp:172).  Verified against libm on 5e6 random inputs.
+__device__ __forceinline__ double hypot_glibc(double x, double y) {
+  x = fabs(x); y = fabs(y);
+  double ax = x < y ? y : x, ay = x < y ? x : y;
+  if (ax >= __ddiv_rn(ay, 0x1p-54)) return __dadd_rn(ax, ay);
+  double h = __dsqrt_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)));
+  double t1, t2;
+  if (h <= __dmul_rn(2.0, ay)) {
+    double delta = __dsub_rn(h, ay);
+    t1 = __dmul_rn(ax, __dsub_rn(__dmul_rn(2.0, delta), ax));
+    t2 = __dmul_rn(__dsub_rn(delta, __dmul_rn(2.0, __dsub_rn(ax, ay))), delta);
+  } else {
+    double delta = __dsub_rn(h, ax);
+    t1 = __dmul_rn(__dmul_rn(2.0, delta), __dsub_rn(ax, __dmul_rn(2.0, ay)));
+    t2 = __dadd_rn(__dmul_rn(__dsub_rn(__dmul_rn(4.0, delta), ay), ay), __dmul_rn(delta, delta));
+  }
+  return __dsub_rn(h, __ddiv_rn(__dadd_rn(t1, t2), __dmul_rn(2.0, h)));
+}
+
+constexpr int CG_T = 32, CG_NT = 256;
+constexpr int CG_GH = 2;                 // halo of the grad tile (bilin can touch x+2 with weight 0)
+constexpr int CG_GW = CG_T + 2 * CG_GH;  // 36
+constexpr int CG_DW = CG_GW + 2;         // data tile 38
+
+__global__ void __launch_bounds__(CG_NT)
+canny_grad_nms_kernel(const float *__restrict__ data, unsigned char *__restrict__ cls, int nx, int ny, int accGrad,
+                      int low_thr, int high_thr) {
+  __shared__ float sd[CG_DW * CG_DW];
+  __shared__ double sg[CG_GW * CG_GW];
+  const int x0 = blockIdx.x * CG_T, y0 = blockIdx.y * CG_T;
+  const float *src = data + (size_t)blockIdx.z * nx * ny;
+  // data tile entry (i,j) <-> global (x0-3+i, y0-3+j), clamped to the image (rcpp_canny.cpp:38-62)
+  for (int t = threadIdx.x; t < CG_DW * CG_DW; t += CG_NT) {
+    int j = t / CG_DW, i = t - j * CG_DW;
+    int gx = min(max(x0 - 3 + i, 0), nx - 1), gy = min(max(y0 - 3 + j, 0), ny - 1);
+    sd[t] = __ldg(src + (size_t)gy * nx + gx);
+  }
+  __syncthreads();
+  // grad tile entry (i,j) <-> global (x0-2+i, y0-2+j) clamped; gradient evaluated AT the clamped pixel
+  for (int t = threadIdx.x; t < CG_GW * CG_GW; t += CG_NT) {
+    int j = t / CG_GW, i = t - j * CG_GW;
+    int cx = min(max(x0 - 2 + i, 0), nx - 1), cy = min(max(y0 - 2 + j, 0), ny - 1);
+    // neighbours of the clamped pixel are themselves clamped: index the data tile by clamped coords
+    int xm = min(max(cx - 1, 0), nx - 1) - (x0 - 3), xp = min(max(cx + 1, 0), nx - 1) - (x0 - 3), xc = cx - (x0 - 3);
+    int ym = min(max(cy - 1, 0), ny - 1) - (y0 - 3), yp = min(max(cy + 1, 0), ny - 1) - (y0 - 3), yc = cy - (y0 - 3);
+#define DD(a, b) ((double)sd[(b) * CG_DW + (a)])
+    double h, v;
+    if (accGrad) {
+      h = __dmul_rn(2.0, __dsub_rn(DD(xp, yc), DD(xm, yc)));
+      h = __dadd_rn(h, DD(xp, yp)); h = __dsub_rn(h, DD(xm, yp)); h = __dadd_rn(h, DD(xp, ym)); h = __dsub_rn(h, DD(xm, ym));
+      v = __dmul_rn(2.0, __dsub_rn(DD(xc, yp), DD(xc, ym)));
+      v = __dadd_rn(v, DD(xp, yp)); v = __dsub_rn(v, DD(xp, ym)); v = __dadd_rn(v, DD(xm, yp)); v = __dsub_rn(v, DD(xm, ym));
+    } else {
+      h = __dsub_rn(DD(xp, yc), DD(xm, yc));
+      v = __dsub_rn(DD(xc, yp), DD(xc, ym));
+    }
+    sg[t] = hypot_glibc(h, v);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < CG_T * CG_T; t += CG_NT) {
+    int ly = t / CG_T, lx = t - ly * CG_T;
+    int gx = x0 + lx, gy = y0 + ly;
+    if (gx >= nx || gy >= ny) continue;
+    const double now = sg[(ly + CG_GH) * CG_GW + lx + CG_GH];
+    unsigned char c = 0;
+    if (!(now <= (double)low_thr)) {
+      // recompute h, v of this pixel (cheaper than keeping two more planes in shared memory)
+      int xm = min(max(gx - 1, 0), nx - 1) - (x0 - 3), xp = min(max(gx + 1, 0), nx - 1) - (x0 - 3), xc = gx - (x0 - 3);
+      int ym = min(max(gy - 1, 0), ny - 1) - (y0 - 3), yp = min(max(gy + 1, 0), ny - 1) - (y0 - 3), yc = gy - (y0 - 3);
+      double h, v;
+      if (accGrad) {
+        h = __dmul_rn(2.0, __dsub_rn(DD(xp, yc), DD(xm, yc)));
+        h = __dadd_rn(h, DD(xp, yp)); h = __dsub_rn(h, DD(xm, yp)); h = __dadd_rn(h, DD(xp, ym)); h = __dsub_rn(h, DD(xm, ym));
+        v = __dmul_rn(2.0, __dsub_rn(DD(xc, yp), DD(xc, ym)));
+        v = __dadd_rn(v, DD(xp, yp)); v = __dsub_rn(v, DD(xp, ym)); v = __dadd_rn(v, DD(xm, yp)); v = __dsub_rn(v, DD(xm, ym));
+      } else {
+        h = __dsub_rn(DD(xp, yc), DD(xm, yc));
+        v = __dsub_rn(DD(xc, yp), DD(xc, ym));
+      }
+#undef DD
+      const double th = atan2(v, h);
+      double sn, cs;
+      sincos(th, &sn, &cs);
+      double nb[2];
+#pragma unroll
+      for (int s = 0; s < 2; s++) {                      // dir = -1 (prev), +1 (next): rcpp_canny.cpp:65-85
+        const double dir = s ? 1.0 : -1.0;
+        double xt = __dmul_rn(dir, cs), yt = __dmul_rn(dir, sn);
+        double x1 = floor(xt), x2 = __dadd_rn(x1, 1.0), y1 = floor(yt), y2 = __dadd_rn(y1, 1.0);
+        // value(x + x1, ...): clamp in image coordinates, then index the grad tile
+        int ix1 = min(max(gx + (int)x1, 0), nx - 1) - (x0 - CG_GH), ix2 = min(max(gx + (int)x2, 0), nx - 1) - (x0 - CG_GH);
+        int iy1 = min(max(gy + (int)y1, 0), ny - 1) - (y0 - CG_GH), iy2 = min(max(gy + (int)y2, 0), ny - 1) - (y0 - CG_GH);
+        double wa = __dsub_rn(x2, xt), wb = __dsub_rn(xt, x1);
+        double g1 = __dadd_rn(__dmul_rn(wa, sg[iy1 * CG_GW + ix1]), __dmul_rn(wb, sg[iy1 * CG_GW + ix2]));
+        double g2 = __dadd_rn(__dmul_rn(wa, sg[iy2 * CG_GW + ix1]), __dmul_rn(wb, sg[iy2 * CG_GW + ix2]));
+        nb[s] = __dadd_rn(__dmul_rn(__dsub_rn(y2, yt), g1), __dmul_rn(__dsub_rn(yt, y1), g2));
+      }
+      if (now <= nb[0] || now <= nb[1]) c = 0;
+      else if (now >= (double)high_thr) c = 2;
+      else c = 1;
+    }
+    cls[(size_t)blockIdx.z * nx * ny + (size_t)gy * nx + gx] = c;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ hysteresis
+__device__ __forceinline__ int uf_find(volatile int *L, int a) {
+  int p = L[a];
+  while (p != a) { a = p; p = L[a]; }
+  return a;
+}
+__device__ __forceinline__ void uf_union(int *L, int a, int b) {
+  // smaller index becomes the root (adsf.c:31-40); lock-free variant with atomicMin
+  while (true) {
+    a = uf_find(L, a); b = uf_find(L, b);
+    if (a == b) return;
+    if (a < b) { int t = a; a = b; b = t; }     // a > b : link a under b
+    int old = atomicMin(&L[a], b);
+    if (old == a) return;
+    a = old;                                     // somebody linked a elsewhere meanwhile: merge that too
+  }
+}
+
+__global__ void hyst_init(const unsigned char *__restrict__ cls, int *__restrict__ L, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) L[i] = (int)i;
+}
+// unions with the 4 "forward" neighbours (E, SW, S, SE): every 8-adjacency is covered once
+__global__ void hyst_merge(const unsigned char *__restrict__ cls, int *__restrict__ L, int nx, int ny) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= nx) return;
+  size_t base = (size_t)blockIdx.z * nx * ny;
+  size_t p = base + (size_t)y * nx + x;
+  if (!cls[p]) return;
+  if (x + 1 < nx && cls[p + 1]) uf_union(L, (int)p, (int)(p + 1));
+  if (y + 1 < ny) {
+    if (x > 0 && cls[p + nx - 1]) uf_union(L, (int)p, (int)(p + nx - 1));
+    if (cls[p + nx]) uf_union(L, (int)p, (int)(p + nx));
+    if (x + 1 < nx && cls[p + nx + 1]) uf_union(L, (int)p, (int)(p + nx + 1));
+  }
+}
+__global__ void hyst_mark(const unsigned char *__restrict__ cls, int *__restrict__ L, unsigned char *__restrict__ strong, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && cls[i] == 2) strong[uf_find(L, (int)i)] = 1;
+}
+__global__ void hyst_emit(const unsigned char *__restrict__ cls, int *__restrict__ L, const unsigned char *__restrict__ strong,
+                          unsigned char *__restrict__ edges, int *__restrict__ nonzero, size_t plane) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t f = blockIdx.y;
+  bool on = false;
+  if (i < plane) {
+    size_t p = f * plane + i;
+    on = cls[p] && strong[uf_find(L, (int)p)];
+    edges[p] = on ? 255 : 0;
+  }
+  unsigned b = __ballot_sync(0xffffffffu, on);
+  __shared__ int cnt;
+  if (threadIdx.x == 0) cnt = 0;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0 && b) atomicAdd(&cnt, __popc(b));
+  __syncthreads();
+  if (threadIdx.x == 0 && cnt) atomicAdd(&nonzero[f], cnt);
+}
+
+// ------------------------------------------------------------------------------------------ host
+// tap list of one axis: orc_canny_taps restated (tools.c:146-163): wrap coordinates, exp(-c^2/s^2),
+// unit sum over the full period, taps below 2^-64 dropped.
+static void make_taps(int w, double s, std::vector<int> &coord, std::vector<double> &weight) {
+  double inv_s = 1 / s, total = 0;
+  for (int i = 0; i < w; i++) { double c = i < w / 2 ? i : i - w; total += exp(-c * c * inv_s * inv_s); }
+  int lo = -(w - w / 2), hi = w / 2 - 1;
+  coord.clear(); weight.clear();
+  for (int c = lo; c <= hi; c++) {
+    double g = exp(-(double)c * c * inv_s * inv_s);
+    if (g < 0x1p-64) continue;
+    coord.push_back(c); weight.push_back(g / total);
+  }
+}
+static bool symmetric_taps(const std::vector<int> &c, const std::vector<double> &w, CannyTaps &out) {
+  int n = (int)c.size();
+  if (n % 2 == 0) return false;
+  int R = n / 2;
+  if (R > CANNY_MAXR) return false;
+  for (int k = 0; k <= R; k++) {
+    if (c[R - k] != -k || c[R + k] != k || w[R - k] != w[R + k]) return false;
+    out.w[k] = w[R + k];
+  }
+  out.R = R;
+  return true;
+}
+
+size_t canny_scratch_bytes(int n_frames, int nx, int ny) {
+  size_t n = (size_t)n_frames * nx * ny;
+  return align256(n * 4) /*blur*/ + align256(n) /*cls*/ + align256(n * 4) /*labels*/ + align256(n) /*strong*/ +
+         align256(n * 8) /*generic path rows*/ + (1 << 16);
+}
+
+int canny_device(b2f_ctx *ctx, const unsigned char *d_frames, int n_frames, int nx, int ny, double s, double low_thr,
+                 double high_thr, int acc_grad, unsigned char *d_edges, int *d_nonzero, cudaStream_t st) {
+  size_t plane = (size_t)nx * ny, n = plane * n_frames;
+  if (n >= (size_t)1 << 31) { set_error("canny: batch of %d frames %dx%d exceeds 2^31 pixels; split the batch", n_frames, nx, ny); return B2F_EUNSUP; }
+  if (!(s > 0)) { set_error("canny: s must be > 0"); return B2F_EINVAL; }
+  float *blur = ctx->arena.get<float>(n);
+  unsigned char *cls = ctx->arena.get<unsigned char>(n);
+  int *L = ctx->arena.get<int>(n);
+  unsigned char *strong = ctx->arena.get<unsigned char>(n);
+  std::vector<int> cx, cy; std::vector<double> wx, wy;
+  make_taps(nx, s, cx, wx); make_taps(ny, s, cy, wy);
+  CannyTaps tx, ty;
+  bool sym = symmetric_taps(cx, wx, tx) && symmetric_taps(cy, wy, ty);
+  if (sym) {
+    B2F_ARENA_CHECK(ctx);
+    dim3 grid(ceil_div(nx, CB_TW), ceil_div(ny, CB_TH), n_frames);
+    size_t smem = sizeof(double) * (size_t)(CB_TH + 2 * ty.R) * CB_TW + (size_t)(CB_TH + 2 * ty.R) * ((CB_TW + 2 * tx.R + 3) & ~3);
+    if (tx.R == 13 && ty.R == 13) {
+      static bool cfg = false;
+      if (!cfg) { B2F_CUDA(cudaFuncSetAttribute(canny_blur_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = true; }
+      canny_blur_kernel<13><<<grid, CB_NT, smem, st>>>(d_frames, blur, nx, ny, tx, ty);
+    } else {
+      if (smem > 200 * 1024) { set_error("canny: s=%g needs %zu bytes of shared memory", s, smem); return B2F_EUNSUP; }
+      B2F_CUDA(cudaFuncSetAttribute(canny_blur_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      canny_blur_kernel<0><<<grid, CB_NT, smem, st>>>(d_frames, blur, nx, ny, tx, ty);
+    }
+    B2F_LAUNCH_CHECK(ctx);
+  } else {
+    double *tmp = ctx->arena.get<double>(n);
+    int *dcx = ctx->arena.get<int>(cx.size() + cy.size());
+    double *dwx = ctx->arena.get<double>(wx.size() + wy.size());
+    B2F_ARENA_CHECK(ctx);
+    B2F_CUDA(cudaMemcpyAsync(dcx, cx.data(), cx.size() * 4, cudaMemcpyHostToDevice, st));
+    B2F_CUDA(cudaMemcpyAsync(dcx + cx.size(), cy.data(), cy.size() * 4, cudaMemcpyHostToDevice, st));
+    B2F_CUDA(cudaMemcpyAsync(dwx, wx.data(), wx.size() * 8, cudaMemcpyHostToDevice, st));
+    B2F_CUDA(cudaMemcpyAsync(dwx + wx.size(), wy.data(), wy.size() * 8, cudaMemcpyHostToDevice, st));
+    B2F_CUDA(cudaStreamSynchronize(st));   // host vectors go out of scope below
+    dim3 grid(ceil_div(nx, 128), ny, n_frames);
+    canny_blur_generic_rows<<<grid, 128, 0, st>>>(d_frames, tmp, nx, ny, TapList{dcx, dwx, (int)cx.size()});
+    B2F_LAUNCH_CHECK(ctx);
+    canny_blur_generic_cols<<<grid, 128, 0, st>>>(tmp, blur, nx, ny, TapList{dcx + cx.size(), dwx + wx.size(), (int)cy.size()});
+    B2F_LAUNCH_CHECK(ctx);
+  }
+  canny_grad_nms_kernel<<<dim3(ceil_div(nx, CG_T), ceil_div(ny, CG_T), n_frames), CG_NT, 0, st>>>(
+      blur, cls, nx, ny, acc_grad ? 1 : 0, (int)low_thr, (int)high_thr);   // thresholds truncate like rcpp_canny.cpp:180
+  B2F_LAUNCH_CHECK(ctx);
+  unsigned nb = (unsigned)((n + 255) / 256);
+  hyst_init<<<nb, 256, 0, st>>>(cls, L, n);
+  B2F_LAUNCH_CHECK(ctx);
+  B2F_CUDA(cudaMemsetAsync(strong, 0, n, st));
+  B2F_CUDA(cudaMemsetAsync(d_nonzero, 0, sizeof(int) * n_frames, st));
+  hyst_merge<<<dim3(ceil_div(nx, 128), ny, n_frames), 128, 0, st>>>(cls, L, nx, ny);
+  B2F_LAUNCH_CHECK(ctx);
+  hyst_mark<<<nb, 256, 0, st>>>(cls, L, strong, n);
+  B2F_LAUNCH_CHECK(ctx);
+  hyst_emit<<<dim3((unsigned)((plane + 255) / 256), n_frames), 256, 0, st>>>(cls, L, strong, d_edges, d_nonzero, plane);
+  B2F_LAUNCH_CHECK(ctx);
+  return B2F_OK;
+}
+
+}  // namespace b2f
+
+using namespace b2f;
+
+extern "C" {
+
+int b2f_canny_dev(b2f_ctx *ctx, const uint8_t *d_frames, int n_frames, int nx, int ny, double s, double low_thr,
+                  double high_thr, int acc_grad, uint8_t *d_edges, int *d_nonzero, void *stream) {
+  if (!ctx || !d_frames || !d_edges || !d_nonzero || n_frames <= 0 || nx <= 0 || ny <= 0) { set_error("b2f_canny_dev: bad argument"); return B2F_EINVAL; }
+  B2F_CUDA(cudaSetDevice(ctx->device));
+  int rc = arena_reserve(ctx, canny_scratch_bytes(n_frames, nx, ny));
+  if (rc != B2F_OK) return rc;
+  return canny_device(ctx, d_frames, n_frames, nx, ny, s, low_thr, high_thr, acc_grad, d_edges, d_nonzero,
+                      stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+int b2f_canny_batch(b2f_ctx *ctx, const uint8_t *frames, int n_frames, int nx, int ny, double s, double low_thr,
+                    double high_thr, int acc_grad, uint8_t *edges, int *nonzero) {
+  if (!ctx || !frames || !edges || !nonzero || n_frames <= 0 || nx <= 0 || ny <= 0) { set_error("b2f_canny_batch: bad argument"); return B2F_EINVAL; }
+  B2F_CUDA(cudaSetDevice(ctx->device));
+  size_t n = (size_t)nx * ny * n_frames;
+  int rc = arena_reserve(ctx, canny_scratch_bytes(n_frames, nx, ny) + 2 * align256(n) + align256(n_frames * 4));
+  if (rc != B2F_OK) return rc;
+  unsigned char *d_in = ctx->arena.get<unsigned char>(n), *d_out = ctx->arena.get<unsigned char>(n);
+  int *d_nz = ctx->arena.get<int>(n_frames);
+  B2F_ARENA_CHECK(ctx);
+  cudaStream_t st = ctx->stream;
+  B2F_CUDA(cudaMemcpyAsync(d_in, frames, n, cudaMemcpyHostToDevice, st));
+  if ((rc = canny_device(ctx, d_in, n_frames, nx, ny, s, low_thr, high_thr, acc_grad, d_out, d_nz, st)) != B2F_OK) return rc;
+  B2F_CUDA(cudaMemcpyAsync(edges, d_out, n, cudaMemcpyDeviceToHost, st));
+  B2F_CUDA(cudaMemcpyAsync(nonzero, d_nz, sizeof(int) * n_frames, cudaMemcpyDeviceToHost, st));
+  B2F_CUDA(cudaStreamSynchronize(st));
+  return B2F_OK;
+}
+
+int b2f_canny_host(b2f_ctx *ctx, const uint8_t *img, int nx, int ny, double s, double low_thr, double high_thr,
+                   int acc_grad, uint8_t *edges, int *nonzero) {
+  return b2f_canny_batch(ctx, img, 1, nx, ny, s, low_thr, high_thr, acc_grad, edges, nonzero);
+}
+
+}  // extern "C"

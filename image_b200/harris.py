@@ -115,11 +115,11 @@ def harris_response_dev(d_frames, is_u8, n_frames, nx, ny, d_R, stream=None, **k
     p = _lib.HarrisParams(*[d[k] for k in ("k", "sigma_d", "sigma_i", "threshold", "gaussian", "gradient", "strategy",
                                            "Nselect", "measure", "Nscales", "precision", "cells", "verbose", "exact")])
     _lib.check(lib.b2f_harris_response_dev(_lib.context(), _lib.ptr(d_frames), int(bool(is_u8)), n_frames, nx, ny,
-                                           C.byref(p), _lib.ptr(d_R), _lib.ptr(stream) if stream else None))
+                                           C.byref(p), _lib.ptr(d_R), _lib.ptr(stream) if stream is not None else None))
 
 
 def harris_nms_dev(d_R, n_frames, nx, ny, threshold, radius, cap, d_xy, d_strength, d_counts, stream=None):
     lib = _lib.load()
     _lib.check(lib.b2f_harris_nms_dev(_lib.context(), _lib.ptr(d_R), n_frames, nx, ny, float(threshold), int(radius),
                                       int(cap), _lib.ptr(d_xy), _lib.ptr(d_strength), _lib.ptr(d_counts),
-                                      _lib.ptr(stream) if stream else None))
+                                      _lib.ptr(stream) if stream is not None else None))

@@ -45,32 +45,58 @@ int orc_canny_taps(int w, double s, int *coord, double *weight, int cap) {
   return n;
 }
 
+/* 1 if the tap list is the symmetric one (coordinates -R..R, mirror-equal weights) */
+static int taps_symmetric(const int *c, const double *w, int n) {
+  if (n % 2 == 0) return 0;
+  int R = n / 2;
+  for (int k = 0; k <= R; k++)
+    if (c[R - k] != -k || c[R + k] != k || w[R - k] != w[R + k]) return 0;
+  return 1;
+}
+
 /* C2  blur — circular separable convolution, rows then columns, double; result narrowed to
- * float (tools.c:129 `crealf`).  out holds float-representable doubles like the reference. */
+ * float (tools.c:129 `crealf`).  Summation order (part of this restatement's definition, chosen
+ * once and shared with the CUDA kernel so that the two agree bit for bit):
+ *   symmetric tap list (every image at least 2R+2 wide/high):  acc = w0*v0, then for k = 1..R
+ *       acc += wk * (v[-k] + v[+k])        (for u8 rows the pair sum is an exact integer)
+ *   otherwise (tiny images, where the wrap-around coordinates of tools.c:152-153 make the
+ *   kernel asymmetric): acc = 0, then acc += w_t * v[x - c_t] for t ascending. */
+static double conv_at(const int *c, const double *w, int n, int sym, int pos, int len, const void *base,
+                      long stride, int is_u8) {
+#define AT(q) (is_u8 ? (double)((const uint8_t *)base)[(long)(q) * stride] : ((const double *)base)[(long)(q) * stride])
+  if (sym) {
+    int R = n / 2;
+    double acc = w[R] * AT(pos);
+    for (int k = 1; k <= R; k++) {
+      int a = pos - k, b = pos + k;
+      a %= len; if (a < 0) a += len;
+      b %= len; if (b < 0) b += len;
+      acc += w[R + k] * (AT(a) + AT(b));
+    }
+    return acc;
+  }
+  double acc = 0;
+  for (int t = 0; t < n; t++) {
+    int q = pos - c[t]; q %= len; if (q < 0) q += len;
+    acc += w[t] * AT(q);
+  }
+  return acc;
+#undef AT
+}
+
 void orc_canny_blur(const uint8_t *img, int nx, int ny, double s, float *out) {
   int capx = nx, capy = ny;
   int *cx = (int *)malloc(sizeof(int) * capx), *cy = (int *)malloc(sizeof(int) * capy);
   double *wx = (double *)malloc(sizeof(double) * capx), *wy = (double *)malloc(sizeof(double) * capy);
   int tx = orc_canny_taps(nx, s, cx, wx, capx), ty = orc_canny_taps(ny, s, cy, wy, capy);
+  int sym = taps_symmetric(cx, wx, tx) && taps_symmetric(cy, wy, ty) && tx / 2 <= 64 && ty / 2 <= 64;
   double *tmp = (double *)malloc(sizeof(double) * (size_t)nx * ny);
   for (int y = 0; y < ny; y++)
-    for (int x = 0; x < nx; x++) {
-      double acc = 0;
-      for (int t = 0; t < tx; t++) {
-        int q = x - cx[t]; q %= nx; if (q < 0) q += nx;
-        acc += wx[t] * (double)img[(long)y * nx + q];
-      }
-      tmp[(long)y * nx + x] = acc;
-    }
+    for (int x = 0; x < nx; x++)
+      tmp[(long)y * nx + x] = conv_at(cx, wx, tx, sym, x, nx, img + (long)y * nx, 1, 1);
   for (int y = 0; y < ny; y++)
-    for (int x = 0; x < nx; x++) {
-      double acc = 0;
-      for (int t = 0; t < ty; t++) {
-        int q = y - cy[t]; q %= ny; if (q < 0) q += ny;
-        acc += wy[t] * tmp[(long)q * nx + x];
-      }
-      out[(long)y * nx + x] = (float)acc;
-    }
+    for (int x = 0; x < nx; x++)
+      out[(long)y * nx + x] = (float)conv_at(cy, wy, ty, sym, y, ny, tmp + x, nx, 0);
   free(cx); free(cy); free(wx); free(wy); free(tmp);
 }
 

@@ -1,0 +1,88 @@
+"""GPU parity tests of the Canny path (through the C ABI / the image_canny_edge_detector mirror)
+against the oracle and the golden edge maps of the reference's fixture.  Integer edge maps:
+BIT-EXACT is the bar (north_star)."""
+import ast
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", ["default", "cpp_default", "fractional_thr"])
+def test_chairs_golden_edge_map_bit_exact(golden, case):
+    from image_b200.canny import image_canny_edge_detector
+    g = golden("canny_chairs")
+    kw = ast.literal_eval(str(g[case + "_args"]))
+    img = g["image"]
+    out = image_canny_edge_detector(img.T.astype(np.int32), kw["s"], kw["low_thr"], kw["high_thr"], kw["accGrad"])
+    ref = np.unpackbits(g[case + "_edges"])[: img.size].reshape(img.shape).astype(bool)
+    assert out["pixels_nonzero"] == int(g[case + "_nonzero"])
+    assert np.array_equal(out["edges"].T == 255, ref)
+    assert set(np.unique(out["edges"])) <= {0.0, 255.0}
+    assert out["nx"] == img.shape[1] and out["ny"] == img.shape[0]
+
+
+@pytest.mark.parametrize("shape", [(64, 64), (75, 101), (108, 192), (270, 480), (33, 500), (500, 33), (1080, 1920)])
+@pytest.mark.parametrize("acc", [True, False])
+def test_edge_maps_equal_oracle_on_synthetic_frames(oracle, shape, acc):
+    from image_b200 import synth
+    from image_b200.canny import canny_batch
+    ny, nx = shape
+    n = 2 if ny * nx > 500000 else 3
+    frames = np.stack([synth.frame_shapes(600 + i, ny, nx) for i in range(n)])
+    edges, nz = canny_batch(frames, accGrad=acc)
+    for i in range(n):
+        e, cnt = oracle.canny(frames[i], accGrad=acc)
+        assert int(nz[i]) == cnt
+        assert np.array_equal(edges[i], e), "mismatching pixels: %d" % int((edges[i] != e).sum())
+
+
+def test_other_sigmas_and_thresholds(oracle):
+    from image_b200 import synth
+    from image_b200.canny import canny_batch
+    f = np.stack([synth.frame_shapes(700, 150, 210)])
+    for s, lo, hi in [(1.0, 2.0, 6.0), (1.3, 2.7, 7.9), (3.5, 1.0, 4.0), (0.6, 5.0, 20.0), (2.0, -1.0, 0.5), (6.0, 1, 3)]:
+        edges, nz = canny_batch(f, s=s, low_thr=lo, high_thr=hi)
+        e, cnt = oracle.canny(f[0], s=s, low_thr=lo, high_thr=hi)
+        assert int(nz[0]) == cnt and np.array_equal(edges[0], e), (s, lo, hi)
+
+
+def test_tiny_and_degenerate_images(oracle):
+    """Images smaller than the blur support (asymmetric wrapped kernel), 1-pixel-wide images,
+    constant images."""
+    from image_b200.canny import canny_batch
+    rng = np.random.default_rng(4)
+    for ny, nx in [(9, 7), (5, 5), (1, 40), (40, 1), (3, 64), (27, 27), (28, 29), (2, 2)]:
+        f = rng.integers(0, 255, (1, ny, nx)).astype(np.uint8)
+        edges, nz = canny_batch(f)
+        e, cnt = oracle.canny(f[0])
+        assert int(nz[0]) == cnt and np.array_equal(edges[0], e), (ny, nx)
+    flat = np.full((1, 64, 80), 77, np.uint8)
+    edges, nz = canny_batch(flat)
+    assert nz[0] == 0 and not edges.any()
+
+
+def test_int_narrowing_like_reference(oracle):
+    """R passes ints; the reference narrows with (unsigned char) — values outside 0..255 wrap."""
+    from image_b200.canny import image_canny_edge_detector
+    rng = np.random.default_rng(8)
+    img = rng.integers(-300, 600, (70, 90)).astype(np.int32)
+    out = image_canny_edge_detector(img.T)
+    e, cnt = oracle.canny(img)
+    assert out["pixels_nonzero"] == cnt and np.array_equal(out["edges"].T == 255, e == 255)
+
+
+def test_hysteresis_properties_full_hd_batch():
+    """BASELINE config 2 size (1920x1080): size-independent properties — idempotent batch entries,
+    every strong seed survives, raising the low threshold can only remove pixels."""
+    from image_b200 import synth
+    from image_b200.canny import canny_batch
+    f = synth.frame_shapes(800, 1080, 1920)
+    frames = np.stack([f, f, np.roll(f, 100, axis=1)])
+    edges, nz = canny_batch(frames)
+    assert np.array_equal(edges[0], edges[1])
+    assert np.array_equal(np.roll(edges[0], 100, axis=1), edges[2])       # circular blur + clamp: interior only
+    e_hi, _ = canny_batch(frames[:1], low_thr=6.0)
+    assert not np.any((e_hi[0] == 255) & (edges[0] == 0))
+    assert nz[0] == (edges[0] == 255).sum()
