@@ -136,7 +136,7 @@ __global__ void canny_blur_generic_cols(const double *__restrict__ tmp, float *_
 __device__ __forceinline__ double hypot_glibc(double x, double y) {
   x = fabs(x); y = fabs(y);
   double ax = x < y ? y : x, ay = x < y ? x : y;
-  if (ax >= __ddiv_rn(ay, 0x1p-54)) return __dadd_rn(ax, ay);
+  if (ax >= __dmul_rn(ay, 0x1p54)) return __dadd_rn(ax, ay);   // ay/EPS, exact power-of-two scaling
   double h = __dsqrt_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)));
   double t1, t2;
   if (h <= __dmul_rn(2.0, ay)) {
@@ -212,9 +212,18 @@ canny_grad_nms_kernel(const float *__restrict__ data, unsigned char *__restrict_
         v = __dsub_rn(DD(xc, yp), DD(xc, ym));
       }
 #undef DD
-      const double th = atan2(v, h);
+      // Direction cosines.  The reference takes cos/sin of atan2(v,h) (rcpp_canny.cpp:69-70,173); both
+      // are the unit vector (h,v)/|(h,v)| up to ~1 ulp of libm error, which no other libm reproduces
+      // either, so the cosines are formed directly (2 divisions instead of atan2+sincos).  Exact zeros
+      // of h or v keep the libm route: there cos(pi/2 rounded) = 6.1e-17 != 0 decides floor().
       double sn, cs;
-      sincos(th, &sn, &cs);
+      if (h == 0.0 || v == 0.0) {
+        const double th = atan2(v, h);
+        sincos(th, &sn, &cs);
+      } else {
+        cs = __ddiv_rn(h, now);
+        sn = __ddiv_rn(v, now);
+      }
       double nb[2];
 #pragma unroll
       for (int s = 0; s < 2; s++) {                      // dir = -1 (prev), +1 (next): rcpp_canny.cpp:65-85
@@ -238,39 +247,88 @@ canny_grad_nms_kernel(const float *__restrict__ data, unsigned char *__restrict_
 }
 
 // ------------------------------------------------------------------------------------------ hysteresis
+// Two-level union-find.  Level 1: every 32x32 tile resolves its own connectivity in shared memory
+// (no global atomics) and publishes, for each edge pixel, the GLOBAL index of its tile-local root.
+// Level 2: only pixels on tile seams union across tiles with lock-free atomicMin links on the
+// global label plane.  Roots are always the smallest index of their set, as in adsf.c:31-40.
 __device__ __forceinline__ int uf_find(volatile int *L, int a) {
   int p = L[a];
-  while (p != a) { a = p; p = L[a]; }
+  while (p != a) {
+    int g = L[p];
+    if (g != p) L[a] = g;          // path halving: parents only ever move to an ancestor
+    a = p; p = g;
+  }
   return a;
 }
 __device__ __forceinline__ void uf_union(int *L, int a, int b) {
-  // smaller index becomes the root (adsf.c:31-40); lock-free variant with atomicMin
   while (true) {
     a = uf_find(L, a); b = uf_find(L, b);
     if (a == b) return;
     if (a < b) { int t = a; a = b; b = t; }     // a > b : link a under b
     int old = atomicMin(&L[a], b);
     if (old == a) return;
-    a = old;                                     // somebody linked a elsewhere meanwhile: merge that too
+    a = old;                                     // a was linked elsewhere meanwhile: merge that set too
   }
 }
 
-__global__ void hyst_init(const unsigned char *__restrict__ cls, int *__restrict__ L, size_t n) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) L[i] = (int)i;
+constexpr int HT = 32;   // hysteresis tile edge
+__global__ void __launch_bounds__(256)
+hyst_local_kernel(const unsigned char *__restrict__ cls, int *__restrict__ L, int nx, int ny) {
+  __shared__ int lab[HT * HT];
+  __shared__ unsigned char sc[HT * HT];
+  const int x0 = blockIdx.x * HT, y0 = blockIdx.y * HT;
+  const size_t base = (size_t)blockIdx.z * nx * ny;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 8 rows of threads, 4 pixels each
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    int ly = ty + 8 * k, gx = x0 + tx, gy = y0 + ly, i = ly * HT + tx;
+    unsigned char c = (gx < nx && gy < ny) ? cls[base + (size_t)gy * nx + gx] : 0;
+    sc[i] = c;
+    lab[i] = i;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    int ly = ty + 8 * k, i = ly * HT + tx;
+    if (!sc[i]) continue;
+    if (tx + 1 < HT && sc[i + 1]) uf_union(lab, i, i + 1);
+    if (ly + 1 < HT) {
+      if (tx > 0 && sc[i + HT - 1]) uf_union(lab, i, i + HT - 1);
+      if (sc[i + HT]) uf_union(lab, i, i + HT);
+      if (tx + 1 < HT && sc[i + HT + 1]) uf_union(lab, i, i + HT + 1);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    int ly = ty + 8 * k, i = ly * HT + tx, gx = x0 + tx, gy = y0 + ly;
+    if (!sc[i]) continue;
+    int r = uf_find(lab, i);
+    int ry = r / HT, rx = r - ry * HT;
+    L[base + (size_t)gy * nx + gx] = (int)(base + (size_t)(y0 + ry) * nx + (x0 + rx));
+  }
 }
-// unions with the 4 "forward" neighbours (E, SW, S, SE): every 8-adjacency is covered once
-__global__ void hyst_merge(const unsigned char *__restrict__ cls, int *__restrict__ L, int nx, int ny) {
-  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-  if (x >= nx) return;
-  size_t base = (size_t)blockIdx.z * nx * ny;
-  size_t p = base + (size_t)y * nx + x;
+// seams: a pixel on the right / bottom / left edge of its tile unions with its forward neighbours
+// (E, SW, S, SE) that live in another tile.  One thread per seam pixel: 3*HT slots per tile.
+__global__ void hyst_seam_kernel(const unsigned char *__restrict__ cls, int *__restrict__ L, int nx, int ny) {
+  const int slot = threadIdx.x;                                  // 0..95
+  const int x0 = blockIdx.x * HT, y0 = blockIdx.y * HT;
+  int lx, ly;
+  if (slot < HT) { lx = slot; ly = HT - 1; }                     // bottom row
+  else if (slot < 2 * HT) { lx = HT - 1; ly = slot - HT; }       // right column
+  else { lx = 0; ly = slot - 2 * HT; }                           // left column (SW link)
+  if (slot >= HT && ly == HT - 1) return;                        // corners already covered by the bottom row
+  const int x = x0 + lx, y = y0 + ly;
+  if (x >= nx || y >= ny) return;
+  const size_t base = (size_t)blockIdx.z * nx * ny;
+  const size_t p = base + (size_t)y * nx + x;
   if (!cls[p]) return;
-  if (x + 1 < nx && cls[p + 1]) uf_union(L, (int)p, (int)(p + 1));
+  const bool right = lx == HT - 1, bottom = ly == HT - 1, left = lx == 0;
+  if (right && x + 1 < nx && cls[p + 1]) uf_union(L, (int)p, (int)(p + 1));
   if (y + 1 < ny) {
-    if (x > 0 && cls[p + nx - 1]) uf_union(L, (int)p, (int)(p + nx - 1));
-    if (cls[p + nx]) uf_union(L, (int)p, (int)(p + nx));
-    if (x + 1 < nx && cls[p + nx + 1]) uf_union(L, (int)p, (int)(p + nx + 1));
+    if ((bottom || left) && x > 0 && cls[p + nx - 1]) uf_union(L, (int)p, (int)(p + nx - 1));
+    if (bottom && cls[p + nx]) uf_union(L, (int)p, (int)(p + nx));
+    if ((bottom || right) && x + 1 < nx && cls[p + nx + 1]) uf_union(L, (int)p, (int)(p + nx + 1));
   }
 }
 __global__ void hyst_mark(const unsigned char *__restrict__ cls, int *__restrict__ L, unsigned char *__restrict__ strong, size_t n) {
@@ -376,11 +434,12 @@ int canny_device(b2f_ctx *ctx, const unsigned char *d_frames, int n_frames, int 
       blur, cls, nx, ny, acc_grad ? 1 : 0, (int)low_thr, (int)high_thr);   // thresholds truncate like rcpp_canny.cpp:180
   B2F_LAUNCH_CHECK(ctx);
   unsigned nb = (unsigned)((n + 255) / 256);
-  hyst_init<<<nb, 256, 0, st>>>(cls, L, n);
-  B2F_LAUNCH_CHECK(ctx);
   B2F_CUDA(cudaMemsetAsync(strong, 0, n, st));
   B2F_CUDA(cudaMemsetAsync(d_nonzero, 0, sizeof(int) * n_frames, st));
-  hyst_merge<<<dim3(ceil_div(nx, 128), ny, n_frames), 128, 0, st>>>(cls, L, nx, ny);
+  dim3 tiles(ceil_div(nx, HT), ceil_div(ny, HT), n_frames);
+  hyst_local_kernel<<<tiles, 256, 0, st>>>(cls, L, nx, ny);
+  B2F_LAUNCH_CHECK(ctx);
+  hyst_seam_kernel<<<tiles, 3 * HT, 0, st>>>(cls, L, nx, ny);
   B2F_LAUNCH_CHECK(ctx);
   hyst_mark<<<nb, 256, 0, st>>>(cls, L, strong, n);
   B2F_LAUNCH_CHECK(ctx);

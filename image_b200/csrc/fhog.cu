@@ -1,0 +1,367 @@
+// fhog.cu — Felzenszwalb HOG of dlib 19.20 as reached from image.dlib::image_fhog
+// (reference: dlib/image_transforms/fhog.h:698-1046).
+//
+//   fhog_hist_kernel     one CTA = a tile of CT x CT histogram cells.  Phase 1: the RGB pixels
+//                        that vote into the tile (+1 ring for the gradient) are staged in shared
+//                        memory and every pixel's (orientation bin, magnitude) is computed once:
+//                        max-length colour channel with the reference's position-dependent
+//                        tie-break (SIMD body vs scalar tail, fhog.h:48-58 / :133-141), 18-way
+//                        snap with un-fused float ops, correctly rounded sqrt.  Phase 2: ONE thread
+//                        per cell replays that cell's votes in raster order (the order of the
+//                        reference's sequential `hist += v` statements, fhog.h:879-917, :951-954),
+//                        accumulating in a private shared-memory histogram -> the 18-bin
+//                        histograms are BIT-IDENTICAL to the reference, no atomics.
+//   fhog_norm_kernel     per-cell energy (fhog.h:959-968), sequential over the 9 orientations.
+//   fhog_feature_kernel  4-block normalisation, clipping and the 31 features (fhog.h:972-1045)
+//                        with the SSE2 lane and summation order ((l0+l2)+(l1+l3), simd4f.h:549-566).
+// Bilinear weights and cell indices come from per-row / per-column tables built on the host with
+// the reference's own float expressions (fhog.h:823-826, :838-841, :946-949).
+#include "common.cuh"
+#include <cmath>
+#include <vector>
+
+namespace b2f {
+
+struct FhogGeom {
+  int rows, cols, cell;
+  int cells_nr, cells_nc, hog_nr, hog_nc;   // hog_* without padding
+  int visible_nr, visible_nc, simd_end;
+  int out_nr, out_nc, pad_r, pad_c;
+};
+
+static bool fhog_geometry(int rows, int cols, int cell, int frp, int fcp, FhogGeom &g) {
+  g.rows = rows; g.cols = cols; g.cell = cell;
+  g.cells_nr = (int)((float)rows / (float)cell + 0.5);                      // fhog.h:780-781
+  g.cells_nc = (int)((float)cols / (float)cell + 0.5);
+  g.hog_nr = std::max(g.cells_nr - 2, 0); g.hog_nc = std::max(g.cells_nc - 2, 0);
+  g.out_nr = g.out_nc = 0; g.pad_r = (frp - 1) / 2; g.pad_c = (fcp - 1) / 2;
+  if (g.cells_nr == 0 || g.cells_nc == 0 || g.hog_nr == 0 || g.hog_nc == 0) return false;   // hog.clear()
+  g.out_nr = g.hog_nr + frp - 1; g.out_nc = g.hog_nc + fcp - 1;             // init_hog, fhog.h:457
+  g.visible_nr = (int)std::min((long)g.cells_nr * cell, (long)rows) - 1;    // fhog.h:817-818
+  g.visible_nc = (int)std::min((long)g.cells_nc * cell, (long)cols) - 1;
+  int x = 1;
+  for (; x < g.visible_nc - 7; x += 8) {}
+  g.simd_end = x;                                                           // columns < simd_end: simd8 body
+  return true;
+}
+
+// per-row / per-column vote tables
+struct FhogTables {
+  const short *r0, *c0;            // first histogram row / column a pixel votes into
+  const float *vy0, *vy1, *vx0, *vx1;
+  const int *ylo, *yhi, *xlo, *xhi;   // pixel range voting into histogram row R / column C
+};
+
+constexpr int FH_NT = 256;
+
+__device__ __forceinline__ void snap18(float gx, float gy, int &best_o) {
+  const float DX[9] = {1.0000f, 0.9397f, 0.7660f, 0.500f, 0.1736f, -0.1736f, -0.5000f, -0.7660f, -0.9397f};
+  const float DY[9] = {0.0000f, 0.3420f, 0.6428f, 0.8660f, 0.9848f, 0.9848f, 0.8660f, 0.6428f, 0.3420f};
+  float best = 0.f;
+  best_o = 0;
+#pragma unroll
+  for (int o = 0; o < 9; o++) {
+    float d = __fadd_rn(__fmul_rn(gx, DX[o]), __fmul_rn(gy, DY[o]));
+    if (d > best) { best = d; best_o = o; }
+    else if (-d > best) { best = -d; best_o = o + 9; }
+  }
+}
+
+__global__ void __launch_bounds__(FH_NT)
+fhog_hist_kernel(const unsigned char *__restrict__ frames, float *__restrict__ hist, FhogGeom g, FhogTables tb,
+                 int CT, int P /* pixel region edge = (CT+1)*cell + 2 */) {
+  extern __shared__ __align__(16) unsigned char sm[];
+  // layout: sv[P*P] float | shist[18*CT*CT] float | so[P*P] u8 | rgb[(P+2)*(P+2)*3] u8
+  float *sv = reinterpret_cast<float *>(sm);
+  float *shist = sv + P * P;
+  unsigned char *so = reinterpret_cast<unsigned char *>(shist + 18 * CT * CT);
+  unsigned char *srgb = so + ((P * P + 15) & ~15);
+  const int R0 = blockIdx.y * CT, C0 = blockIdx.x * CT;          // first histogram row/col of this tile
+  const int HR = g.cells_nr + 2, HC = g.cells_nc + 2;
+  const int nR = min(CT, HR - R0), nC = min(CT, HC - C0);
+  // pixel range voting into the tile
+  const int py0 = tb.ylo[R0], py1 = tb.yhi[R0 + nR - 1], px0 = tb.xlo[C0], px1 = tb.xhi[C0 + nC - 1];
+  const int ph = py1 - py0, pw = px1 - px0;                       // may be <= 0 (rim cells with no voters)
+  const unsigned char *src = frames + (size_t)blockIdx.z * g.rows * g.cols * 3;
+  const int W2 = pw + 2;
+  if (ph > 0 && pw > 0) {
+    // stage RGB rows [py0-1, py1+1) x cols [px0-1, px1+1) (always inside the image: voters are in [1, visible))
+    const int rowbytes = W2 * 3;
+    for (int i = threadIdx.x; i < (ph + 2) * rowbytes; i += FH_NT) {
+      int r = i / rowbytes, b = i - r * rowbytes;
+      srgb[r * rowbytes + b] = __ldg(src + ((size_t)(py0 - 1 + r) * g.cols + (px0 - 1)) * 3 + b);
+    }
+  }
+  for (int i = threadIdx.x; i < 18 * CT * CT; i += FH_NT) shist[i] = 0.f;
+  __syncthreads();
+  if (ph > 0 && pw > 0) {
+    // phase 1: per-pixel gradient -> (bin, magnitude)
+    for (int i = threadIdx.x; i < ph * pw; i += FH_NT) {
+      int r = i / pw, c = i - r * pw;
+      const unsigned char *p = srgb + ((r + 1) * W2 + (c + 1)) * 3;
+      const bool simd = (px0 + c) < g.simd_end;
+      int bx = 0, by = 0, bl = -1;
+#pragma unroll
+      for (int ch = 0; ch < 3; ch++) {
+        int dx = (int)p[3 + ch] - (int)p[-3 + ch];
+        int dy = (int)p[W2 * 3 + ch] - (int)p[-W2 * 3 + ch];
+        int l = dx * dx + dy * dy;
+        bool take = (ch == 0) || (simd ? !(bl > l) : (l > bl));
+        if (take) { bx = dx; by = dy; bl = l; }
+      }
+      int o;
+      snap18((float)bx, (float)by, o);
+      sv[r * pw + c] = __fsqrt_rn((float)bl);
+      so[r * pw + c] = (unsigned char)o;
+    }
+  }
+  __syncthreads();
+  // phase 2: one thread per histogram cell, votes replayed in raster order
+  const int t = threadIdx.x;
+  if (t < nR * nC && ph > 0 && pw > 0) {
+    const int lr = t / nC, lc = t - lr * nC;
+    const int R = R0 + lr, C = C0 + lc;
+    float *h = shist + t;                       // bin o at h[o * CT*CT]
+    const int HS = CT * CT;
+    const int ya = tb.ylo[R], yb = tb.yhi[R], xa = tb.xlo[C], xb = tb.xhi[C];
+    for (int y = ya; y < yb; y++) {
+      const float wy = (tb.r0[y] == R) ? tb.vy1[y] : tb.vy0[y];
+      const float *rv = sv + (y - py0) * pw - px0;
+      const unsigned char *ro = so + (y - py0) * pw - px0;
+      for (int x = xa; x < xb; x++) {
+        const float wx = (tb.c0[x] == C) ? tb.vx1[x] : tb.vx0[x];
+        const float v = rv[x];
+        const int o = ro[x];
+        // simd body: vy*(vx*v) (fhog.h:867-874) ; scalar tail: (vy*vx)*v (fhog.h:951-954)
+        const float val = (x < g.simd_end) ? __fmul_rn(wy, __fmul_rn(wx, v)) : __fmul_rn(__fmul_rn(wy, wx), v);
+        h[o * HS] = __fadd_rn(h[o * HS], val);
+      }
+    }
+  }
+  __syncthreads();
+  // write the tile's histograms: hist[frame][R][C][18]
+  float *dst = hist + (size_t)blockIdx.z * HR * HC * 18;
+  for (int i = threadIdx.x; i < nR * nC * 18; i += FH_NT) {
+    int cellidx = i / 18, o = i - cellidx * 18;
+    int lr = cellidx / nC, lc = cellidx - lr * nC;
+    dst[((size_t)(R0 + lr) * HC + (C0 + lc)) * 18 + o] = shist[o * CT * CT + cellidx];
+  }
+}
+
+__global__ void fhog_norm_kernel(const float *__restrict__ hist, float *__restrict__ norm, FhogGeom g) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (c >= g.cells_nc) return;
+  const int HC = g.cells_nc + 2;
+  const float *h = hist + ((size_t)blockIdx.z * (g.cells_nr + 2) * HC + (size_t)(r + 1) * HC + (c + 1)) * 18;
+  float n = 0.f;
+#pragma unroll
+  for (int o = 0; o < 9; o++) {
+    float s = __fadd_rn(h[o], h[o + 9]);
+    n = __fadd_rn(n, __fmul_rn(s, s));
+  }
+  norm[((size_t)blockIdx.z * g.cells_nr + r) * g.cells_nc + c] = n;
+}
+
+__global__ void fhog_feature_kernel(const float *__restrict__ hist, const float *__restrict__ norm, float *__restrict__ out,
+                                    FhogGeom g) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= g.hog_nc) return;
+  const int HC = g.cells_nc + 2;
+  const float *N = norm + (size_t)blockIdx.z * g.cells_nr * g.cells_nc;
+#define NN(r, c) N[(size_t)(r) * g.cells_nc + (c)]
+  const float z1[4] = {NN(y + 1, x + 1), NN(y, x + 1), NN(y + 1, x), NN(y, x)};
+  const float z2[4] = {NN(y + 1, x + 2), NN(y, x + 2), NN(y + 1, x + 1), NN(y, x + 1)};
+  const float z3[4] = {NN(y + 2, x + 1), NN(y + 1, x + 1), NN(y + 2, x), NN(y + 1, x)};
+  const float z4[4] = {NN(y + 2, x + 2), NN(y + 1, x + 2), NN(y + 2, x + 1), NN(y + 1, x + 1)};
+#undef NN
+  float nn[4], n[4], tt[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    float s = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(z1[k], z2[k]), z3[k]), z4[k]), 0.0001f);
+    nn[k] = __fmul_rn(0.2f, __fsqrt_rn(s));
+    n[k] = __fdiv_rn(0.1f, nn[k]);
+  }
+  const float *h = hist + ((size_t)blockIdx.z * (g.cells_nr + 2) * HC + (size_t)(y + 2) * HC + (x + 2)) * 18;
+  float hv[18];
+#pragma unroll
+  for (int o = 0; o < 18; o++) hv[o] = h[o];
+  float *o31 = out + (((size_t)blockIdx.z * g.out_nr + (y + g.pad_r)) * g.out_nc + (x + g.pad_c)) * 31;
+#pragma unroll
+  for (int o = 0; o < 18; o += 3) {
+    float hh[3][4];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) hh[j][k] = __fmul_rn(hv[o + j] < nn[k] ? hv[o + j] : nn[k], n[k]);
+      o31[o + j] = __fadd_rn(__fadd_rn(hh[j][0], hh[j][2]), __fadd_rn(hh[j][1], hh[j][3]));
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) tt[k] = __fadd_rn(tt[k], __fadd_rn(__fadd_rn(hh[0][k], hh[1][k]), hh[2][k]));
+  }
+  const float tscale = (float)(2 * 0.2357);
+#pragma unroll
+  for (int k = 0; k < 4; k++) tt[k] = __fmul_rn(tt[k], tscale);
+#pragma unroll
+  for (int o = 0; o < 9; o++) {
+    float tmp = __fadd_rn(hv[o], hv[o + 9]), hk[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) hk[k] = __fmul_rn(tmp < nn[k] ? tmp : nn[k], n[k]);
+    o31[18 + o] = __fadd_rn(__fadd_rn(hk[0], hk[2]), __fadd_rn(hk[1], hk[3]));
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) o31[27 + k] = tt[k];
+}
+
+// ------------------------------------------------------------------------------------------ host
+size_t fhog_scratch_bytes(int n_frames, const FhogGeom &g) {
+  size_t hist = (size_t)n_frames * (g.cells_nr + 2) * (g.cells_nc + 2) * 18 * 4;
+  size_t norm = (size_t)n_frames * g.cells_nr * g.cells_nc * 4;
+  size_t tabs = (size_t)(g.rows + g.cols) * (2 + 4 + 4) + (size_t)(g.cells_nr + g.cells_nc + 4) * 8 + 4096;
+  return align256(hist) + align256(norm) + 12 * align256(tabs) + (1 << 16);
+}
+
+int fhog_device(b2f_ctx *ctx, const unsigned char *d_frames, int n_frames, const FhogGeom &g, float *d_out, cudaStream_t st) {
+  const int cell = g.cell, HR = g.cells_nr + 2, HC = g.cells_nc + 2;
+  // ---- vote tables, reference float expressions
+  std::vector<short> r0(g.rows, 0), c0(g.cols, 0);
+  std::vector<float> vy0(g.rows, 0), vy1(g.rows, 0), vx0(g.cols, 0), vx1(g.cols, 0);
+  for (int y = 1; y < g.visible_nr; y++) {                                   // fhog.h:823-826
+    const float yp = ((float)y + 0.5) / (float)cell - 0.5;
+    const int iyp = (int)std::floor(yp);
+    const float a = yp - iyp;
+    const float b = 1.0 - a;
+    r0[y] = (short)(iyp + 1); vy0[y] = a; vy1[y] = b;
+  }
+  for (int x = 1; x < g.visible_nc; x++) {
+    if (x < g.simd_end) {                                                    // fhog.h:838-841
+      float xx = (float)x;
+      float xp = (xx + 0.5f) / (float)cell + 0.5f;
+      int ixp = (int)xp;
+      float a = xp - (float)ixp;
+      float b = 1.0f - a;
+      c0[x] = (short)ixp; vx0[x] = a; vx1[x] = b;
+    } else {                                                                 // fhog.h:946-949
+      const float xp = ((double)x + 0.5) / (double)cell - 0.5;
+      const int ixp = (int)std::floor(xp);
+      const float a = xp - ixp;
+      const float b = 1.0 - a;
+      c0[x] = (short)(ixp + 1); vx0[x] = a; vx1[x] = b;
+    }
+  }
+  std::vector<int> ylo(HR, 0), yhi(HR, 0), xlo(HC, 0), xhi(HC, 0);
+  // [a[k], b[k]) = contiguous pixel range voting into histogram index k (pixel p votes into first[p]
+  // and first[p]+1; first[] is non-decreasing).  Indices nobody votes into get an empty range placed
+  // so that the span of any run of consecutive indices stays [a[first], b[last]).
+  auto ranges = [](const std::vector<short> &first, int lo, int hi, std::vector<int> &a, std::vector<int> &b) {
+    const int n = (int)a.size();
+    for (int k = 0; k < n; k++) { a[k] = 1 << 30; b[k] = -1; }
+    for (int p = lo; p < hi; p++)
+      for (int k = first[p]; k <= first[p] + 1; k++)
+        if (k >= 0 && k < n) { a[k] = std::min(a[k], p); b[k] = std::max(b[k], p + 1); }
+    int kmin = -1, kmax = -1;
+    for (int k = 0; k < n; k++) if (b[k] > a[k]) { if (kmin < 0) kmin = k; kmax = k; }
+    if (kmin < 0) { for (int k = 0; k < n; k++) a[k] = b[k] = lo; return; }
+    for (int k = 0; k < kmin; k++) a[k] = b[k] = a[kmin];
+    for (int k = kmax + 1; k < n; k++) a[k] = b[k] = b[kmax];
+  };
+  ranges(r0, 1, std::max(g.visible_nr, 1), ylo, yhi);
+  ranges(c0, 1, std::max(g.visible_nc, 1), xlo, xhi);
+
+  // ---- device buffers
+  float *hist = ctx->arena.get<float>((size_t)n_frames * HR * HC * 18);
+  float *norm = ctx->arena.get<float>((size_t)n_frames * g.cells_nr * g.cells_nc);
+  short *d_r0 = ctx->arena.get<short>(g.rows), *d_c0 = ctx->arena.get<short>(g.cols);
+  float *d_vy0 = ctx->arena.get<float>(g.rows), *d_vy1 = ctx->arena.get<float>(g.rows);
+  float *d_vx0 = ctx->arena.get<float>(g.cols), *d_vx1 = ctx->arena.get<float>(g.cols);
+  int *d_ylo = ctx->arena.get<int>(HR), *d_yhi = ctx->arena.get<int>(HR), *d_xlo = ctx->arena.get<int>(HC), *d_xhi = ctx->arena.get<int>(HC);
+  B2F_ARENA_CHECK(ctx);
+#define UP(d, v) B2F_CUDA(cudaMemcpyAsync(d, v.data(), v.size() * sizeof(v[0]), cudaMemcpyHostToDevice, st))
+  UP(d_r0, r0); UP(d_c0, c0); UP(d_vy0, vy0); UP(d_vy1, vy1); UP(d_vx0, vx0); UP(d_vx1, vx1);
+  UP(d_ylo, ylo); UP(d_yhi, yhi); UP(d_xlo, xlo); UP(d_xhi, xhi);
+#undef UP
+  B2F_CUDA(cudaStreamSynchronize(st));   // host tables go out of scope at return
+  FhogTables tb{d_r0, d_c0, d_vy0, d_vy1, d_vx0, d_vx1, d_ylo, d_yhi, d_xlo, d_xhi};
+
+  int CT = std::min(16, std::max(1, 72 / cell));
+  // largest pixel span of any tile (rows / cols) decides the shared-memory footprint
+  int P = 0;
+  for (int R = 0; R < HR; R += CT) P = std::max(P, yhi[std::min(R + CT, HR) - 1] - ylo[R]);
+  for (int C = 0; C < HC; C += CT) P = std::max(P, xhi[std::min(C + CT, HC) - 1] - xlo[C]);
+  P = std::max(P, 1);
+  size_t smem = sizeof(float) * ((size_t)P * P + 18 * CT * CT) + (((size_t)P * P + 15) & ~15) + (size_t)(P + 2) * (P + 2) * 3 + 16;
+  if (smem > 220 * 1024) { set_error("fhog: cell_size %d needs %zu bytes of shared memory per tile", cell, smem); return B2F_EUNSUP; }
+  B2F_CUDA(cudaFuncSetAttribute(fhog_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fhog_hist_kernel<<<dim3(ceil_div(HC, CT), ceil_div(HR, CT), n_frames), FH_NT, smem, st>>>(d_frames, hist, g, tb, CT, P);
+  B2F_LAUNCH_CHECK(ctx);
+  fhog_norm_kernel<<<dim3(ceil_div(g.cells_nc, 128), g.cells_nr, n_frames), 128, 0, st>>>(hist, norm, g);
+  B2F_LAUNCH_CHECK(ctx);
+  if (g.out_nr != g.hog_nr || g.out_nc != g.hog_nc)   // zero border of init_hog (fhog.h:459-470)
+    B2F_CUDA(cudaMemsetAsync(d_out, 0, sizeof(float) * (size_t)n_frames * g.out_nr * g.out_nc * 31, st));
+  fhog_feature_kernel<<<dim3(ceil_div(g.hog_nc, 64), g.hog_nr, n_frames), 64, 0, st>>>(hist, norm, d_out, g);
+  B2F_LAUNCH_CHECK(ctx);
+  return B2F_OK;
+}
+
+static int fhog_check(const char *who, int rows, int cols, int cell, int frp, int fcp) {
+  if (rows <= 0 || cols <= 0) { set_error("%s: bad image size %dx%d", who, rows, cols); return B2F_EINVAL; }
+  if (cell <= 0 || frp <= 0 || fcp <= 0) { set_error("%s: cell_size and the paddings must be > 0 (fhog.h:710-717)", who); return B2F_EINVAL; }
+  if (cell == 1) { set_error("%s: cell_size == 1 (dlib's separate routine fhog.h:495-694) is not implemented on the GPU path", who); return B2F_EUNSUP; }
+  return B2F_OK;
+}
+
+}  // namespace b2f
+
+using namespace b2f;
+
+extern "C" {
+
+int b2f_fhog_size(int rows, int cols, int cell_size, int frp, int fcp, int *hog_nr, int *hog_nc) {
+  if (!hog_nr || !hog_nc) { set_error("b2f_fhog_size: NULL output"); return B2F_EINVAL; }
+  int rc = fhog_check("b2f_fhog_size", rows, cols, cell_size == 1 ? 2 : cell_size, frp, fcp);
+  if (rc != B2F_OK) return rc;
+  FhogGeom g;
+  fhog_geometry(rows, cols, cell_size, frp, fcp, g);
+  *hog_nr = g.out_nr; *hog_nc = g.out_nc;
+  return B2F_OK;
+}
+
+int b2f_fhog_dev(b2f_ctx *ctx, const uint8_t *d_frames, int n_frames, int rows, int cols, int cell_size, int frp, int fcp,
+                 float *d_hog, void *stream) {
+  if (!ctx || !d_frames || n_frames <= 0) { set_error("b2f_fhog_dev: bad argument"); return B2F_EINVAL; }
+  int rc = fhog_check("b2f_fhog_dev", rows, cols, cell_size, frp, fcp);
+  if (rc != B2F_OK) return rc;
+  FhogGeom g;
+  if (!fhog_geometry(rows, cols, cell_size, frp, fcp, g)) return B2F_OK;   // empty output
+  if (!d_hog) { set_error("b2f_fhog_dev: NULL output"); return B2F_EINVAL; }
+  B2F_CUDA(cudaSetDevice(ctx->device));
+  if ((rc = arena_reserve(ctx, fhog_scratch_bytes(n_frames, g))) != B2F_OK) return rc;
+  return fhog_device(ctx, d_frames, n_frames, g, d_hog, stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+int b2f_fhog_batch(b2f_ctx *ctx, const uint8_t *frames, int n_frames, int rows, int cols, int cell_size, int frp, int fcp,
+                   float *hog) {
+  if (!ctx || !frames || n_frames <= 0) { set_error("b2f_fhog_batch: bad argument"); return B2F_EINVAL; }
+  int rc = fhog_check("b2f_fhog_batch", rows, cols, cell_size, frp, fcp);
+  if (rc != B2F_OK) return rc;
+  FhogGeom g;
+  if (!fhog_geometry(rows, cols, cell_size, frp, fcp, g)) return B2F_OK;
+  if (!hog) { set_error("b2f_fhog_batch: NULL output"); return B2F_EINVAL; }
+  B2F_CUDA(cudaSetDevice(ctx->device));
+  size_t in_bytes = (size_t)n_frames * rows * cols * 3, out_n = (size_t)n_frames * g.out_nr * g.out_nc * 31;
+  if ((rc = arena_reserve(ctx, fhog_scratch_bytes(n_frames, g) + align256(in_bytes) + align256(out_n * 4))) != B2F_OK) return rc;
+  unsigned char *d_in = ctx->arena.get<unsigned char>(in_bytes);
+  float *d_out = ctx->arena.get<float>(out_n);
+  B2F_ARENA_CHECK(ctx);
+  cudaStream_t st = ctx->stream;
+  B2F_CUDA(cudaMemcpyAsync(d_in, frames, in_bytes, cudaMemcpyHostToDevice, st));
+  if ((rc = fhog_device(ctx, d_in, n_frames, g, d_out, st)) != B2F_OK) return rc;
+  B2F_CUDA(cudaMemcpyAsync(hog, d_out, out_n * 4, cudaMemcpyDeviceToHost, st));
+  B2F_CUDA(cudaStreamSynchronize(st));
+  return B2F_OK;
+}
+
+int b2f_fhog_host(b2f_ctx *ctx, const uint8_t *rgb, int rows, int cols, int cell_size, int frp, int fcp, float *hog) {
+  return b2f_fhog_batch(ctx, rgb, 1, rows, cols, cell_size, frp, fcp, hog);
+}
+
+}  // extern "C"

@@ -166,29 +166,29 @@ nms_bitmask_kernel(const float *__restrict__ R, unsigned *__restrict__ mask, int
   }
 }
 
-// per-frame: count set bits per row, exclusive scan over rows (one CTA per frame)
+// one warp per row: number of set bits of that row
+__global__ void row_count_kernel(const unsigned *__restrict__ mask, int *__restrict__ row_cnt, int ny, int words_per_row) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31, f = blockIdx.y;
+  if (row >= ny) return;
+  const unsigned *m = mask + ((size_t)f * ny + row) * words_per_row;
+  int c = 0;
+  for (int w = lane; w < words_per_row; w += 32) c += __popc(m[w]);
+  for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (lane == 0) row_cnt[(size_t)f * ny + row] = c;
+}
+// per frame (one CTA): exclusive scan of the row counts, in place; total -> counts[f]
 __global__ void __launch_bounds__(1024)
-row_count_scan_kernel(const unsigned *__restrict__ mask, int *__restrict__ row_off, int *__restrict__ counts,
-                      int ny, int words_per_row) {
+row_scan_kernel(int *__restrict__ row_off, int *__restrict__ counts, int ny) {
   __shared__ int warp_tot[32];
   __shared__ int carry;
-  const unsigned *m = mask + (size_t)blockIdx.x * ny * words_per_row;
   int *off = row_off + (size_t)blockIdx.x * ny;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
   for (int base = 0; base < ny; base += blockDim.x) {
-    // each warp counts rows base + warp*32 .. +31 cooperatively: lane l sums words l, l+32, ...
-    int mycount = 0;   // count of row (base + threadIdx.x), produced via shuffles below
-    for (int rr = 0; rr < 32; rr++) {
-      int row = base + warp * 32 + rr;
-      int c = 0;
-      if (row < ny)
-        for (int w = lane; w < words_per_row; w += 32) c += __popc(m[(size_t)row * words_per_row + w]);
-      for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-      if (lane == rr) mycount = c;
-    }
-    // block-wide exclusive scan of mycount
+    int row = base + threadIdx.x;
+    int mycount = row < ny ? off[row] : 0;
     int incl = mycount;
     for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
     if (lane == 31) warp_tot[warp] = incl;
@@ -200,7 +200,6 @@ row_count_scan_kernel(const unsigned *__restrict__ mask, int *__restrict__ row_o
       warp_tot[lane] = ti - t;   // exclusive
     }
     __syncthreads();
-    int row = base + threadIdx.x;
     int excl = carry + warp_tot[warp] + incl - mycount;
     if (row < ny) off[row] = excl;
     __syncthreads();
@@ -410,7 +409,9 @@ int harris_nms_device(b2f_ctx *ctx, const float *d_R, int n_frames, int nx, int 
   dim3 grid(ceil_div(nx, NMS_TW), ceil_div(ny, NMS_TH), n_frames);
   nms_bitmask_kernel<<<grid, NMS_NT, smem, st>>>(d_R, mask, nx, ny, wpr, Th, radius);
   B2F_LAUNCH_CHECK(ctx);
-  row_count_scan_kernel<<<n_frames, 1024, 0, st>>>(mask, row_off, d_counts, ny, wpr);
+  row_count_kernel<<<dim3(ceil_div(ny, 8), n_frames), 256, 0, st>>>(mask, row_off, ny, wpr);
+  B2F_LAUNCH_CHECK(ctx);
+  row_scan_kernel<<<n_frames, 1024, 0, st>>>(row_off, d_counts, ny);
   B2F_LAUNCH_CHECK(ctx);
   emit_corners_kernel<<<dim3(ceil_div(ny, 8), n_frames), 256, 0, st>>>(mask, row_off, d_R, d_xy, d_strength, nx, ny, wpr, cap);
   B2F_LAUNCH_CHECK(ctx);

@@ -1,0 +1,78 @@
+"""Host-side mirror of image.dlib::image_fhog and image.dlib::image_surf
+(reference: image.dlib/R/image_fhog.R:35-48, R/image_surf.R:83-90) over the C ABI."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def fhog_size(rows, cols, cell=8, frp=1, fcp=1):
+    lib = _lib.load()
+    a, b = C.c_int(0), C.c_int(0)
+    _lib.check(lib.b2f_fhog_size(int(rows), int(cols), int(cell), int(frp), int(fcp), C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+def _rgb_from_r_vector(x, rows, cols):
+    """std::vector<int> x with x[3*c + 3*cols*r + ch], narrowed by rgb_pixel(...) to unsigned char
+    (rcpp_fhog.cpp:19-23 / rcpp_surf.cpp:16-20)."""
+    v = np.asarray(x).ravel()
+    if v.size != rows * cols * 3:
+        raise ValueError("x has %d elements, expected 3*rows*cols = %d" % (v.size, rows * cols * 3))
+    return np.ascontiguousarray((v.astype(np.int64) & 0xFF).astype(np.uint8).reshape(rows, cols, 3))
+
+
+def dlib_fhog(x, rows, cols, cell_size=8, filter_rows_padding=1, filter_cols_padding=1):
+    """The Rcpp export (rcpp_fhog.cpp:10-46).  Returns the same list; `fhog` is the flat vector in
+    the glue's order y + hog_height*(x + hog_width*feat)."""
+    lib = _lib.load()
+    rgb = _rgb_from_r_vector(x, rows, cols)
+    nr, nc = fhog_size(rows, cols, cell_size, filter_rows_padding, filter_cols_padding)
+    hog = np.zeros((nr, nc, 31), np.float32)
+    if nr * nc:
+        _lib.check(lib.b2f_fhog_host(_lib.context(), _lib.ptr(rgb), int(rows), int(cols), int(cell_size),
+                                     int(filter_rows_padding), int(filter_cols_padding), _lib.ptr(hog)))
+    flat = hog.astype(np.float64).transpose(2, 1, 0).ravel()      # [feat][x][y]: y fastest
+    return dict(hog_height=nr, hog_width=nc, fhog=flat, hog_cell_size=int(cell_size),
+                filter_rows_padding=int(filter_rows_padding), filter_cols_padding=int(filter_cols_padding))
+
+
+def image_fhog(x, cell_size=8, filter_rows_padding=1, filter_cols_padding=1):
+    """image_fhog(x, cell_size = 8L, filter_rows_padding = 1L, filter_cols_padding = 1L) as in R.
+    `x` is an R-style integer array of dim [3, width, height] (e.g. as.integer(magick image data));
+    out$fhog is an array [hog_height, hog_width, 31]."""
+    a = np.asarray(x)
+    if a.ndim != 3 or a.shape[0] != 3:
+        raise ValueError("x must be an array of dim c(3, width, height)")
+    width, height = a.shape[1], a.shape[2]
+    out = dlib_fhog(a.ravel(order="F"), rows=height, cols=width, cell_size=int(cell_size),
+                    filter_rows_padding=int(filter_rows_padding), filter_cols_padding=int(filter_cols_padding))
+    out["fhog"] = out["fhog"].reshape((out["hog_height"], out["hog_width"], 31), order="F")
+    return out
+
+
+def fhog_batch(frames, cell=8, frp=1, fcp=1):
+    """Batch form (new surface): uint8 [n, rows, cols, 3] -> float32 [n, hog_nr, hog_nc, 31]."""
+    lib = _lib.load()
+    f = np.ascontiguousarray(frames, dtype=np.uint8)
+    n, rows, cols, _ = f.shape
+    nr, nc = fhog_size(rows, cols, cell, frp, fcp)
+    hog = np.zeros((n, nr, nc, 31), np.float32)
+    if nr * nc:
+        _lib.check(lib.b2f_fhog_batch(_lib.context(), _lib.ptr(f), n, rows, cols, int(cell), int(frp), int(fcp), _lib.ptr(hog)))
+    return hog
+
+
+def fhog_dev(d_frames, n_frames, rows, cols, d_hog, cell=8, frp=1, fcp=1, stream=None):
+    lib = _lib.load()
+    _lib.check(lib.b2f_fhog_dev(_lib.context(), _lib.ptr(d_frames), n_frames, rows, cols, int(cell), int(frp), int(fcp),
+                                _lib.ptr(d_hog), _lib.ptr(stream) if stream is not None else None))
+
+
+def smoke_check(po):
+    from . import synth
+    img = synth.frame_rgb(3, 72, 104)
+    out = image_fhog(np.ascontiguousarray(img.transpose(2, 1, 0)))
+    ref = po.fhog(img, 8, 1, 1, impl="oracle")
+    assert out["fhog"].shape == ref.shape and np.array_equal(out["fhog"], ref), "FHOG differs from the oracle"
