@@ -1,0 +1,490 @@
+// surf.cu — dlib 19.20 SURF as reached from image.dlib::image_surf (SURVEY.md §8a rows S1-S5;
+// reference: dlib/image_keypoint/surf.h:236-288, hessian_pyramid.h, image_transforms/integral_image.h).
+//
+//   surf_grey_rowscan / surf_colscan   grey = (r+g+b)/3 and the inclusive int32 summed-area table
+//                                      (integral_image.h:32-62): warp-shuffle scan along rows, then a
+//                                      coalesced running sum down the columns.
+//   surf_pyramid_kernel                the 4 x 6 box-filter det-of-Hessian maps (hessian_pyramid.h:
+//                                      86-178): 8 box sums per sample from the SAT, exact ints ->
+//                                      doubles, every double op rounded separately (no FMA).
+//   surf_points_kernel                 threshold + 3x3x3 non-max test + the 3-D quadratic refinement
+//                                      with the closed-form 3x3 inverse (hessian_pyramid.h:324-446);
+//                                      survivors are appended with their (octave, interval, r, c) key.
+//   surf_describe_kernel               one CTA per key point: 109-sample dominant orientation with the
+//                                      45 sliding pi/3 windows (surf.h:75-154) and the 4x4x4 descriptor
+//                                      (surf.h:158-232); partial sums are formed in the reference's
+//                                      own order (one thread per window / per descriptor cell).
+//   Host (S5, tiny): candidates are put back into emission order, sorted with the very call the
+//   reference uses — std::sort on reverse iterators (surf.h:268) — cut to max_points and border-tested.
+#include "common.cuh"
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+namespace b2f {
+
+constexpr int S_OCT = 4, S_INT = 6, S_MAPS = S_OCT * S_INT;
+
+struct SurfMap {
+  long long off;       // offset (doubles) inside one frame's pyramid buffer
+  int nr, nc;          // map size  (img / step)
+  int step, border;    // sampling step (pixels), build border in MAP units
+  int lobe;
+  double area_inv;
+};
+struct SurfGeom {
+  int rows, cols;
+  long long pyr_per_frame;
+  SurfMap m[S_MAPS];
+};
+
+static void surf_geometry(int rows, int cols, SurfGeom &g) {
+  g.rows = rows; g.cols = cols;
+  long long off = 0;
+  for (int o = 0; o < S_OCT; o++) {
+    const long step = 2 * (long)(std::pow(2.0, (double)o) + 0.5);                     // get_step_size
+    for (int i = 0; i < S_INT; i++) {
+      SurfMap &m = g.m[o * S_INT + i];
+      m.off = off; m.nr = (int)(rows / step); m.nc = (int)(cols / step); m.step = (int)step;
+      const double lobe_d = 2.0 * (i + 1) + 1;
+      m.border = (int)std::ceil(3 * lobe_d / 2.0);                                    // get_border_size
+      m.lobe = (int)((long)(std::pow(2.0, o + 1.0) + 0.5) * (i + 1) + 1);
+      m.area_inv = 1.0 / std::pow(3.0 * m.lobe, 2.0);
+      off += (long long)m.nr * m.nc;
+    }
+  }
+  g.pyr_per_frame = off;
+}
+
+// ------------------------------------------------------------------------------------------ SAT
+// one warp per row: grey conversion + inclusive scan of the row
+__global__ void surf_grey_rowscan(const unsigned char *__restrict__ rgb, int *__restrict__ sat, int rows, int cols) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const unsigned char *src = rgb + ((size_t)blockIdx.y * rows + row) * (size_t)cols * 3;
+  int *dst = sat + ((size_t)blockIdx.y * rows + row) * (size_t)cols;
+  int carry = 0;
+  for (int c0 = 0; c0 < cols; c0 += 32 * 4) {
+    // each lane takes 4 consecutive pixels
+    int v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      int c = c0 + lane * 4 + k;
+      v[k] = 0;
+      if (c < cols) {
+        const unsigned char *p = src + (size_t)c * 3;
+        v[k] = (int)(((unsigned)p[0] + (unsigned)p[1] + (unsigned)p[2]) / 3u);        // pixel.h:775-783
+      }
+    }
+    v[1] += v[0]; v[2] += v[1]; v[3] += v[2];
+    int incl = v[3];
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    int base = carry + incl - v[3];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { int c = c0 + lane * 4 + k; if (c < cols) dst[c] = base + v[k]; }
+    carry += __shfl_sync(0xffffffffu, incl, 31);
+  }
+}
+// one thread per column: running sum down the rows (coalesced across the warp)
+__global__ void surf_colscan(int *__restrict__ sat, int rows, int cols) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  int *p = sat + (size_t)blockIdx.y * rows * (size_t)cols + c;
+  int acc = 0;
+  for (int r = 0; r < rows; r++) { acc += p[(size_t)r * cols]; p[(size_t)r * cols] = acc; }
+}
+
+__device__ __forceinline__ int sat_box(const int *__restrict__ S, int nc, int l, int t, int r, int b) {
+  // get_sum_of_area, integral_image.h:64-96
+  int tl = 0, tr = 0, bl = 0, br = __ldg(S + (size_t)b * nc + r);
+  if (l - 1 >= 0 && t - 1 >= 0) {
+    tl = __ldg(S + (size_t)(t - 1) * nc + (l - 1));
+    bl = __ldg(S + (size_t)b * nc + (l - 1));
+    tr = __ldg(S + (size_t)(t - 1) * nc + r);
+  } else if (l - 1 >= 0) bl = __ldg(S + (size_t)b * nc + (l - 1));
+  else if (t - 1 >= 0) tr = __ldg(S + (size_t)(t - 1) * nc + r);
+  return br - bl - tr + tl;
+}
+__device__ __forceinline__ int sat_box_centered(const int *S, int nc, int x, int y, int w, int h) {
+  int l = x - w / 2, t = y - h / 2;                                                   // centered_rect
+  return sat_box(S, nc, l, t, l + w - 1, t + h - 1);
+}
+__device__ __forceinline__ int sat_haar_x(const int *S, int nc, int px, int py, int width) {   // integral_image.h:123-150
+  int l = px - width / 2, t = py - width / 2, b = t + width - 1;
+  return sat_box(S, nc, px, t, l + width - 1, b) - sat_box(S, nc, l, t, px - 1, b);
+}
+__device__ __forceinline__ int sat_haar_y(const int *S, int nc, int px, int py, int width) {   // :154-181
+  int l = px - width / 2, t = py - width / 2, r = l + width - 1;
+  return sat_box(S, nc, l, py, r, t + width - 1) - sat_box(S, nc, l, t, r, py - 1);
+}
+
+// ------------------------------------------------------------------------------------------ pyramid
+__global__ void __launch_bounds__(256)
+surf_pyramid_kernel(const int *__restrict__ sat, double *__restrict__ pyr, const __grid_constant__ SurfGeom g) {
+  const SurfMap &m = g.m[blockIdx.y];
+  const int *S = sat + (size_t)blockIdx.z * g.rows * (size_t)g.cols;
+  double *out = pyr + (size_t)blockIdx.z * g.pyr_per_frame + m.off;
+  // valid samples: map rows [border, rmax), cols [border, cmax) with r*step < rows - border*step
+  const int rmax = (g.rows - m.border * m.step + m.step - 1) / m.step, cmax = (g.cols - m.border * m.step + m.step - 1) / m.step;
+  const int wr = rmax - m.border, wc = cmax - m.border;
+  if (wr <= 0 || wc <= 0) return;
+  const long long total = (long long)wr * wc;
+  const int lobe = m.lobe, off = lobe / 2 + 1;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int ri = (int)(idx / wc) + m.border, ci = (int)(idx % wc) + m.border;
+    const int r = ri * m.step, c = ci * m.step;
+    double Dxx = __dsub_rn((double)sat_box_centered(S, g.cols, c, r, lobe * 3, 2 * lobe - 1),
+                           __dmul_rn((double)sat_box_centered(S, g.cols, c, r, lobe, 2 * lobe - 1), 3.0));
+    double Dyy = __dsub_rn((double)sat_box_centered(S, g.cols, c, r, 2 * lobe - 1, lobe * 3),
+                           __dmul_rn((double)sat_box_centered(S, g.cols, c, r, 2 * lobe - 1, lobe), 3.0));
+    // int32 arithmetic like the reference (value_type sums): bl + tr - tl - br
+    int dxy = sat_box_centered(S, g.cols, c - off, r + off, lobe, lobe) + sat_box_centered(S, g.cols, c + off, r - off, lobe, lobe) -
+              sat_box_centered(S, g.cols, c - off, r - off, lobe, lobe) - sat_box_centered(S, g.cols, c + off, r + off, lobe, lobe);
+    double Dxy = (double)dxy;
+    Dxx = __dmul_rn(Dxx, m.area_inv); Dyy = __dmul_rn(Dyy, m.area_inv); Dxy = __dmul_rn(Dxy, m.area_inv);
+    double sign = (__dadd_rn(Dxx, Dyy) < 0) ? -1.0 : 1.0;
+    double det = __dsub_rn(__dmul_rn(Dxx, Dyy), __dmul_rn(__dmul_rn(0.81, Dxy), Dxy));
+    if (det < 0) det = 0;
+    out[(size_t)ri * m.nc + ci] = __dmul_rn(sign, det);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ interest points
+struct SurfCand {
+  long long key;                 // emission order of get_interest_points: (o, i, r, c)
+  double x, y, scale, score, lap;
+};
+
+__device__ __forceinline__ double pval(const double *__restrict__ P, const SurfMap &m, int r, int c) {
+  return fabs(__ldg(P + m.off + (size_t)r * m.nc + c));
+}
+
+__global__ void __launch_bounds__(256)
+surf_points_kernel(const double *__restrict__ pyr, SurfCand *__restrict__ cand, int *__restrict__ counts, int cap,
+                   double thr, const __grid_constant__ SurfGeom g) {
+  const int o = blockIdx.y / (S_INT - 2), i = blockIdx.y % (S_INT - 2) + 1;       // i = 1..4
+  const SurfMap &m = g.m[o * S_INT + i], &ml = g.m[o * S_INT + i - 1], &mh = g.m[o * S_INT + i + 1];
+  const double *P = pyr + (size_t)blockIdx.z * g.pyr_per_frame;
+  const int b = mh.border;                                                         // get_border_size(i+1)
+  const int wr = m.nr - 2 * b - 2, wc = m.nc - 2 * b - 2;
+  if (wr <= 0 || wc <= 0) return;
+  const long long total = (long long)wr * wc;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(idx / wc) + b + 1, c = (int)(idx % wc) + b + 1;
+    const double val = pval(P, m, r, c);
+    if (!(val >= thr)) continue;
+    bool is_max = true;
+    for (int rr = r - 1; rr <= r + 1 && is_max; rr++)
+      for (int cc = c - 1; cc <= c + 1; cc++)
+        if (pval(P, ml, rr, cc) > val || pval(P, m, rr, cc) > val || pval(P, mh, rr, cc) > val) { is_max = false; break; }
+    if (!is_max) continue;
+    // interpolate_point (hessian_pyramid.h:360-446)
+    const double vxp = pval(P, m, r, c + 1), vxm = pval(P, m, r, c - 1), vyp = pval(P, m, r + 1, c), vym = pval(P, m, r - 1, c);
+    const double vsp = pval(P, mh, r, c), vsm = pval(P, ml, r, c);
+    const double g0 = __ddiv_rn(__dsub_rn(vxp, vxm), 2.0), g1 = __ddiv_rn(__dsub_rn(vyp, vym), 2.0), g2 = __ddiv_rn(__dsub_rn(vsp, vsm), 2.0);
+    const double two_val = __dmul_rn(2.0, val);
+    const double Dxx = __dsub_rn(__dadd_rn(vxp, vxm), two_val), Dyy = __dsub_rn(__dadd_rn(vyp, vym), two_val), Dss = __dsub_rn(__dadd_rn(vsp, vsm), two_val);
+    const double Dxy = __ddiv_rn(__dsub_rn(__dsub_rn(__dadd_rn(pval(P, m, r + 1, c + 1), pval(P, m, r - 1, c - 1)), pval(P, m, r - 1, c + 1)), pval(P, m, r + 1, c - 1)), 4.0);
+    const double Dxs = __ddiv_rn(__dsub_rn(__dsub_rn(__dadd_rn(pval(P, mh, r, c + 1), pval(P, ml, r, c - 1)), pval(P, ml, r, c + 1)), pval(P, mh, r, c - 1)), 4.0);
+    const double Dys = __ddiv_rn(__dsub_rn(__dsub_rn(__dadd_rn(pval(P, mh, r + 1, c), pval(P, ml, r - 1, c)), pval(P, ml, r + 1, c)), pval(P, mh, r - 1, c)), 4.0);
+    // inv(3x3) by cofactors (matrix_la.h:922-965, det :1582-1589), every op rounded separately
+    const double a = Dxx, bb = Dxy, cc3 = Dxs, d = Dxy, e = Dyy, f = Dys, gg = Dxs, h = Dys, k = Dss;
+#define MUL __dmul_rn
+#define SUB __dsub_rn
+#define ADD __dadd_rn
+    double de = ADD(SUB(MUL(a, SUB(MUL(e, k), MUL(f, h))), MUL(bb, SUB(MUL(d, k), MUL(f, gg)))), MUL(cc3, SUB(MUL(d, h), MUL(e, gg))));
+    double m00 = 1, m01 = 0, m02 = 0, m10 = 0, m11 = 1, m12 = 0, m20 = 0, m21 = 0, m22 = 1;
+    if (de != 0) {
+      de = __ddiv_rn(1.0, de);
+      m00 = MUL(SUB(MUL(e, k), MUL(f, h)), de); m10 = MUL(SUB(MUL(f, gg), MUL(d, k)), de); m20 = MUL(SUB(MUL(d, h), MUL(e, gg)), de);
+      m01 = MUL(SUB(MUL(cc3, h), MUL(bb, k)), de); m11 = MUL(SUB(MUL(a, k), MUL(cc3, gg)), de); m21 = MUL(SUB(MUL(bb, gg), MUL(a, h)), de);
+      m02 = MUL(SUB(MUL(bb, f), MUL(cc3, e)), de); m12 = MUL(SUB(MUL(cc3, d), MUL(a, f)), de); m22 = MUL(SUB(MUL(a, e), MUL(bb, d)), de);
+    }
+    const double ix = -ADD(ADD(MUL(m00, g0), MUL(m01, g1)), MUL(m02, g2));
+    const double iy = -ADD(ADD(MUL(m10, g0), MUL(m11, g1)), MUL(m12, g2));
+    const double is = -ADD(ADD(MUL(m20, g0), MUL(m21, g1)), MUL(m22, g2));
+    if (!(fmax(fmax(fabs(ix), fabs(iy)), fabs(is)) < 0.5)) continue;
+    SurfCand q;
+    q.x = MUL(ADD((double)c, ix), (double)m.step);
+    q.y = MUL(ADD((double)r, iy), (double)m.step);
+    const double p2 = (double)(1 << (o + 1));                                      // pow(2.0, o+1.0), exact
+    const double lobe = ADD(MUL(p2, ADD(ADD((double)i, is), 1.0)), 1.0);
+    q.scale = MUL(1.2 / 9.0, MUL(3.0, lobe));
+    q.score = val;
+    q.lap = (__ldg(P + m.off + (size_t)r * m.nc + c) > 0) ? 1.0 : -1.0;
+#undef MUL
+#undef SUB
+#undef ADD
+    if (!(q.score >= thr)) continue;
+    q.key = (((long long)(o * S_INT + i) << 40) | ((long long)r << 20) | (long long)c);
+    int slot = atomicAdd(&counts[blockIdx.z], 1);
+    if (slot < cap) cand[(size_t)blockIdx.z * cap + slot] = q;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ orientation + descriptor
+struct SurfKey { double x, y, scale; int frame; int pad; };
+
+__device__ __forceinline__ long long round_half_up(double v) { return (long long)floor(__dadd_rn(v, 0.5)); }   // vector.h:147-148
+
+__global__ void __launch_bounds__(128)
+surf_describe_kernel(const int *__restrict__ sat, const SurfKey *__restrict__ keys, double *__restrict__ angle_out,
+                     double *__restrict__ des_out, int rows, int cols) {
+  __shared__ double sx[112], sy[112], sang[112];
+  __shared__ double wlen[48], wang[48];
+  __shared__ double ux[16 * 49], uy[16 * 49];
+  __shared__ double des[64];
+  __shared__ double s_angle, s_inv;
+  const SurfKey kp = keys[blockIdx.x];
+  const int *S = sat + (size_t)kp.frame * rows * (size_t)cols;
+  const double PI = 3.1415926535897932384626433832795;
+  const int tid = threadIdx.x;
+  const long long sc = (long long)__dadd_rn(kp.scale, 0.5);
+  // ---- samples of compute_dominant_angle (surf.h:99-115): (r,c) in [-6,6]^2 with r^2+c^2 < 36, raster order
+  if (tid < 112) {
+    // enumerate: the tid-th valid offset
+    int n = 0, rr = 0, cc = 0;
+    bool found = false;
+    for (int r = -6; r <= 6 && !found; r++)
+      for (int c = -6; c <= 6; c++)
+        if (r * r + c * c < 36) { if (n == tid) { rr = r; cc = c; found = true; break; } n++; }
+    if (found) {
+      const double x = (double)cc, y = (double)rr, sig = 2.5;
+      const double gauss = __dmul_rn(__ddiv_rn(1.0, __dmul_rn(sig, 2.5066282746310002416123552393401041626930)),
+                                     exp(__ddiv_rn(-__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(__dmul_rn(2.0, sig), sig))));
+      const int px = (int)round_half_up(__dadd_rn((double)(sc * cc), kp.x)), py = (int)round_half_up(__dadd_rn((double)(sc * rr), kp.y));
+      const double hx = __dmul_rn(gauss, (double)sat_haar_x(S, cols, px, py, (int)(4 * sc)));
+      const double hy = __dmul_rn(gauss, (double)sat_haar_y(S, cols, px, py, (int)(4 * sc)));
+      sx[tid] = hx; sy[tid] = hy; sang[tid] = atan2(hy, hx);
+    }
+  }
+  __syncthreads();
+  // ---- 45 sliding windows (surf.h:118-150): one thread per window, samples added in index order
+  if (tid < 45) {
+    const double ang_step = __ddiv_rn(__dmul_rn(2.0, PI), 45.0);
+    const double ang1 = __dsub_rn(__dmul_rn(ang_step, (double)tid), PI), ang2 = __dadd_rn(ang1, __ddiv_rn(PI, 3.0));
+    const double wrap = __dadd_rn(__dmul_rn(-2.0, PI), ang2);
+    double vx = 0, vy = 0;
+    for (int j = 0; j < 109; j++) {
+      const double a = sang[j];
+      if ((ang1 <= a && a <= ang2) || (ang2 > PI && (a >= ang1 || a <= wrap))) { vx = __dadd_rn(vx, sx[j]); vy = __dadd_rn(vy, sy[j]); }
+    }
+    wlen[tid] = __dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy));
+    wang[tid] = atan2(vy, vx);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double max_length = 0, best = 0;
+    for (int k = 0; k < 45; k++) if (wlen[k] > max_length) { max_length = wlen[k]; best = wang[k]; }
+    s_angle = best;
+  }
+  __syncthreads();
+  const double angle = s_angle;
+  // ---- descriptor (surf.h:176-231): 16 cells x up to 7x7 samples; sample values first, in parallel
+  {
+    double sn, cs, isn, ics;
+    sincos(angle, &sn, &cs);
+    sincos(-angle, &isn, &ics);
+    for (int s = tid; s < 16 * 49; s += blockDim.x) {
+      const int cell = s / 49, k = s - cell * 49;
+      const int r = -10 + 5 * (cell / 4), c = -10 + 5 * (cell % 4);
+      const int y = r - 1 + k / 7, x = c - 1 + k % 7;
+      double vx = 0, vy = 0;
+      if (!(y < -10 || y >= 10 || x < -10 || x >= 10)) {
+        const double qx = __dmul_rn((double)x, kp.scale), qy = __dmul_rn((double)y, kp.scale);
+        const double rx = __dsub_rn(__dmul_rn(cs, qx), __dmul_rn(sn, qy)), ry = __dadd_rn(__dmul_rn(sn, qx), __dmul_rn(cs, qy));
+        const int px = (int)round_half_up(__dadd_rn(rx, kp.x)), py = (int)round_half_up(__dadd_rn(ry, kp.y));
+        const int ay = abs(r + 2 - y), ax = abs(c + 2 - x);
+        const double weight = __ddiv_rn(1.0, (double)(4 + ay + ax));
+        const double tx = __dmul_rn(weight, (double)sat_haar_x(S, cols, px, py, (int)(2 * sc)));
+        const double ty = __dmul_rn(weight, (double)sat_haar_y(S, cols, px, py, (int)(2 * sc)));
+        vx = __dsub_rn(__dmul_rn(ics, tx), __dmul_rn(isn, ty));
+        vy = __dadd_rn(__dmul_rn(isn, tx), __dmul_rn(ics, ty));
+      } else {
+        vx = nan(""); vy = 0;           // marks "skipped" (the reference `continue`s)
+      }
+      ux[s] = vx; uy[s] = vy;
+    }
+  }
+  __syncthreads();
+  if (tid < 16) {       // sequential sums per cell, in the reference's (y, x) order
+    double vx = 0, vy = 0, ax = 0, ay = 0;
+    for (int k = 0; k < 49; k++) {
+      const double a = ux[tid * 49 + k], b = uy[tid * 49 + k];
+      if (a != a) continue;
+      vx = __dadd_rn(vx, a); vy = __dadd_rn(vy, b); ax = __dadd_rn(ax, fabs(a)); ay = __dadd_rn(ay, fabs(b));
+    }
+    des[tid * 4 + 0] = vx; des[tid * 4 + 1] = vy; des[tid * 4 + 2] = ax; des[tid * 4 + 3] = ay;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0;
+    for (int j = 0; j < 64; j++) s = __dadd_rn(s, __dmul_rn(des[j], des[j]));
+    const double len = __dadd_rn(__dsqrt_rn(s), 1e-7);
+    s_inv = __ddiv_rn(1.0, len);                                                   // des/len == des * (1/len)
+  }
+  __syncthreads();
+  if (tid < 64) des_out[(size_t)blockIdx.x * 64 + tid] = __dmul_rn(des[tid], s_inv);
+  if (tid == 0) angle_out[blockIdx.x] = angle;
+}
+
+// ------------------------------------------------------------------------------------------ host
+struct ip_mirror {            // interest_point ordering: operator< on score (hessian_pyramid.h:32)
+  double x, y, scale, score, lap;
+  bool operator<(const ip_mirror &p) const { return score < p.score; }
+};
+
+static bool rect_inside(int rows, int cols, double cx, double cy, unsigned long size) {
+  // get_rect(int_img).contains(centered_rect(center, size, size)) with vector<double> -> point rounding
+  long x = (long)std::floor(cx + 0.5), y = (long)std::floor(cy + 0.5);
+  long l = x - (long)size / 2, t = y - (long)size / 2, r = l + (long)size - 1, b = t + (long)size - 1;
+  if (r < l || b < t) return true;        // empty rectangle: rect + *this == *this
+  return l >= 0 && t >= 0 && r <= cols - 1 && b <= rows - 1;
+}
+
+size_t surf_scratch_bytes(int n_frames, const SurfGeom &g, int cand_cap, size_t max_keys) {
+  size_t px = (size_t)n_frames * g.rows * g.cols;
+  return align256(px * 4) + align256((size_t)n_frames * g.pyr_per_frame * 8) + align256((size_t)n_frames * cand_cap * sizeof(SurfCand)) +
+         align256(n_frames * 4) + align256(max_keys * sizeof(SurfKey)) + align256(max_keys * 8) + align256(max_keys * 64 * 8) + (1 << 16);
+}
+
+// d_rgb: n_frames interleaved RGB frames on the device.  out[f] receives the key points of frame f.
+int surf_device(b2f_ctx *ctx, const unsigned char *d_rgb, int n_frames, const SurfGeom &g, long max_points, double thr,
+                int cand_cap, std::vector<std::vector<b2f_surf_point>> &out, cudaStream_t st) {
+  const int rows = g.rows, cols = g.cols;
+  size_t px = (size_t)n_frames * rows * cols;
+  int *sat = ctx->arena.get<int>(px);
+  double *pyr = ctx->arena.get<double>((size_t)n_frames * g.pyr_per_frame);
+  SurfCand *cand = ctx->arena.get<SurfCand>((size_t)n_frames * cand_cap);
+  int *counts = ctx->arena.get<int>(n_frames);
+  B2F_ARENA_CHECK(ctx);
+  surf_grey_rowscan<<<dim3(ceil_div(rows, 8), n_frames), 256, 0, st>>>(d_rgb, sat, rows, cols);
+  B2F_LAUNCH_CHECK(ctx);
+  surf_colscan<<<dim3(ceil_div(cols, 128), n_frames), 128, 0, st>>>(sat, rows, cols);
+  B2F_LAUNCH_CHECK(ctx);
+  B2F_CUDA(cudaMemsetAsync(pyr, 0, sizeof(double) * (size_t)n_frames * g.pyr_per_frame, st));   // the unread rim
+  B2F_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * n_frames, st));
+  {
+    long long biggest = (long long)g.m[0].nr * g.m[0].nc;
+    int bx = (int)std::min<long long>((biggest + 255) / 256, 4096);
+    surf_pyramid_kernel<<<dim3(bx, S_MAPS, n_frames), 256, 0, st>>>(sat, pyr, g);
+    B2F_LAUNCH_CHECK(ctx);
+    surf_points_kernel<<<dim3(bx, S_OCT * (S_INT - 2), n_frames), 256, 0, st>>>(pyr, cand, counts, cand_cap, thr, g);
+    B2F_LAUNCH_CHECK(ctx);
+  }
+  std::vector<int> h_counts(n_frames);
+  B2F_CUDA(cudaMemcpyAsync(h_counts.data(), counts, sizeof(int) * n_frames, cudaMemcpyDeviceToHost, st));
+  B2F_CUDA(cudaStreamSynchronize(st));
+  out.assign(n_frames, std::vector<b2f_surf_point>());
+  std::vector<SurfKey> keys;
+  std::vector<std::pair<int, int>> key_owner;            // (frame, index in out[frame])
+  std::vector<SurfCand> hc;
+  for (int f = 0; f < n_frames; f++) {
+    int n = h_counts[f];
+    if (n > cand_cap) { set_error("surf: frame %d has %d interest points, above the internal capacity %d", f, n, cand_cap); return B2F_ECAP; }
+    hc.resize(n);
+    if (n) B2F_CUDA(cudaMemcpy(hc.data(), cand + (size_t)f * cand_cap, sizeof(SurfCand) * n, cudaMemcpyDeviceToHost));
+    std::sort(hc.begin(), hc.end(), [](const SurfCand &a, const SurfCand &b) { return a.key < b.key; });   // emission order
+    std::vector<ip_mirror> pts(n);
+    for (int k = 0; k < n; k++) pts[k] = ip_mirror{hc[k].x, hc[k].y, hc[k].scale, hc[k].score, hc[k].lap};
+    std::sort(pts.rbegin(), pts.rend());                                             // surf.h:268
+    size_t lim = std::min((size_t)max_points, pts.size());
+    for (size_t k = 0; k < lim; k++) {
+      const unsigned long bsz = (unsigned long)(32 * pts[k].scale);                  // surf.h:275-277
+      if (!rect_inside(rows, cols, pts[k].x, pts[k].y, bsz)) continue;
+      b2f_surf_point sp;
+      memset(&sp, 0, sizeof(sp));
+      sp.x = pts[k].x; sp.y = pts[k].y; sp.scale = pts[k].scale; sp.score = pts[k].score; sp.laplacian = pts[k].lap;
+      key_owner.push_back({f, (int)out[f].size()});
+      out[f].push_back(sp);
+      keys.push_back(SurfKey{sp.x, sp.y, sp.scale, f, 0});
+    }
+  }
+  if (keys.empty()) return B2F_OK;
+  size_t nk = keys.size();
+  SurfKey *d_keys = ctx->arena.get<SurfKey>(nk);
+  double *d_ang = ctx->arena.get<double>(nk), *d_des = ctx->arena.get<double>(nk * 64);
+  B2F_ARENA_CHECK(ctx);
+  B2F_CUDA(cudaMemcpyAsync(d_keys, keys.data(), sizeof(SurfKey) * nk, cudaMemcpyHostToDevice, st));
+  surf_describe_kernel<<<(unsigned)nk, 128, 0, st>>>(sat, d_keys, d_ang, d_des, rows, cols);
+  B2F_LAUNCH_CHECK(ctx);
+  std::vector<double> h_ang(nk), h_des(nk * 64);
+  B2F_CUDA(cudaMemcpyAsync(h_ang.data(), d_ang, sizeof(double) * nk, cudaMemcpyDeviceToHost, st));
+  B2F_CUDA(cudaMemcpyAsync(h_des.data(), d_des, sizeof(double) * nk * 64, cudaMemcpyDeviceToHost, st));
+  B2F_CUDA(cudaStreamSynchronize(st));
+  for (size_t k = 0; k < nk; k++) {
+    b2f_surf_point &sp = out[key_owner[k].first][key_owner[k].second];
+    sp.angle = h_ang[k];
+    memcpy(sp.des, &h_des[k * 64], sizeof(double) * 64);
+  }
+  return B2F_OK;
+}
+
+static int surf_check(const char *who, int rows, int cols, long max_points, double thr) {
+  if (rows <= 0 || cols <= 0) { set_error("%s: bad image size %dx%d", who, rows, cols); return B2F_EINVAL; }
+  if (max_points <= 0 || !(thr >= 0)) { set_error("%s: max_points must be > 0 and detection_threshold >= 0 (surf.h:243-248)", who); return B2F_EINVAL; }
+  if ((long long)rows * cols * 255 > 2147483647LL) {
+    set_error("%s: %dx%d overflows the int32 integral image the reference uses (integral_image_generic<int32>)", who, rows, cols);
+    return B2F_EUNSUP;
+  }
+  return B2F_OK;
+}
+
+static int surf_run(b2f_ctx *ctx, const uint8_t *frames, int n_frames, int rows, int cols, long max_points, double thr,
+                    std::vector<std::vector<b2f_surf_point>> &out) {
+  SurfGeom g;
+  surf_geometry(rows, cols, g);
+  // every sample can at most be one candidate per 3x3x3 neighbourhood; bound by a fraction of octave 0
+  int cand_cap = (int)std::min<long long>(std::max<long long>((long long)g.m[0].nr * g.m[0].nc / 4, 1024), 4000000);
+  size_t max_keys = (size_t)n_frames * std::min<long long>(max_points, cand_cap);
+  B2F_CUDA(cudaSetDevice(ctx->device));
+  size_t in_bytes = (size_t)n_frames * rows * cols * 3;
+  int rc = arena_reserve(ctx, surf_scratch_bytes(n_frames, g, cand_cap, max_keys) + align256(in_bytes));
+  if (rc != B2F_OK) return rc;
+  unsigned char *d_in = ctx->arena.get<unsigned char>(in_bytes);
+  B2F_ARENA_CHECK(ctx);
+  B2F_CUDA(cudaMemcpyAsync(d_in, frames, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return surf_device(ctx, d_in, n_frames, g, max_points, thr, cand_cap, out, ctx->stream);
+}
+
+}  // namespace b2f
+
+using namespace b2f;
+
+extern "C" {
+
+int b2f_surf_host(b2f_ctx *ctx, const uint8_t *rgb, int rows, int cols, long max_points, double detection_threshold,
+                  b2f_surf_point **points, int *n) {
+  if (!ctx || !rgb || !points || !n) { set_error("b2f_surf_host: NULL argument"); return B2F_EINVAL; }
+  *points = nullptr; *n = 0;
+  int rc = surf_check("b2f_surf_host", rows, cols, max_points, detection_threshold);
+  if (rc != B2F_OK) return rc;
+  std::vector<std::vector<b2f_surf_point>> out;
+  if ((rc = surf_run(ctx, rgb, 1, rows, cols, max_points, detection_threshold, out)) != B2F_OK) return rc;
+  size_t m = out[0].size();
+  b2f_surf_point *p = (b2f_surf_point *)malloc(sizeof(b2f_surf_point) * (m ? m : 1));
+  if (!p) { set_error("b2f_surf_host: out of host memory"); return B2F_ENOMEM; }
+  if (m) memcpy(p, out[0].data(), sizeof(b2f_surf_point) * m);
+  *points = p; *n = (int)m;
+  return B2F_OK;
+}
+
+int b2f_surf_batch(b2f_ctx *ctx, const uint8_t *frames, int n_frames, int rows, int cols, long max_points,
+                   double detection_threshold, int cap, b2f_surf_point *points, int *counts) {
+  if (!ctx || !frames || !points || !counts || n_frames <= 0 || cap <= 0) { set_error("b2f_surf_batch: bad argument"); return B2F_EINVAL; }
+  int rc = surf_check("b2f_surf_batch", rows, cols, max_points, detection_threshold);
+  if (rc != B2F_OK) return rc;
+  std::vector<std::vector<b2f_surf_point>> out;
+  if ((rc = surf_run(ctx, frames, n_frames, rows, cols, max_points, detection_threshold, out)) != B2F_OK) return rc;
+  bool over = false;
+  for (int f = 0; f < n_frames; f++) {
+    counts[f] = (int)out[f].size();
+    size_t m = std::min(out[f].size(), (size_t)cap);
+    over |= out[f].size() > (size_t)cap;
+    if (m) memcpy(points + (size_t)f * cap, out[f].data(), sizeof(b2f_surf_point) * m);
+  }
+  if (over) { set_error("b2f_surf_batch: at least one frame has more than cap=%d key points", cap); return B2F_ECAP; }
+  return B2F_OK;
+}
+
+}  // extern "C"

@@ -70,9 +70,64 @@ def fhog_dev(d_frames, n_frames, rows, cols, d_hog, cell=8, frp=1, fcp=1, stream
                                 _lib.ptr(d_hog), _lib.ptr(stream) if stream is not None else None))
 
 
+def dlib_surf_points(x, rows, cols, max_points=10000, detection_threshold=30.0):
+    """The Rcpp export (rcpp_surf.cpp:10-54; C++ default max_points = 10000, the R wrapper's is 1000).
+    Returns list(points, x, y, angle, pyramid_scale, score, laplacian, surf[n, 64])."""
+    lib = _lib.load()
+    rgb = _rgb_from_r_vector(x, rows, cols)
+    pts = C.POINTER(_lib.SurfPoint)()
+    n = C.c_int(0)
+    _lib.check(lib.b2f_surf_host(_lib.context(), _lib.ptr(rgb), int(rows), int(cols), C.c_long(int(max_points)),
+                                 float(detection_threshold), C.byref(pts), C.byref(n)))
+    try:
+        m = n.value
+        rec = np.ctypeslib.as_array(C.cast(pts, C.POINTER(C.c_double)), (m, 70)).copy() if m else np.zeros((0, 70))
+    finally:
+        lib.b2f_free(C.cast(pts, C.c_void_p))
+    return dict(points=m, x=rec[:, 0].copy(), y=rec[:, 1].copy(), angle=rec[:, 2].copy(), pyramid_scale=rec[:, 3].copy(),
+                score=rec[:, 4].copy(), laplacian=rec[:, 5].copy(), surf=rec[:, 6:].copy())
+
+
+def image_surf(x, max_points=1000, detection_threshold=30):
+    """image_surf(x, max_points = 1000, detection_threshold = 30) as in R (R/image_surf.R:83-90):
+    `x` is an R-style integer array [3, width, height]; NaNs in the descriptor become 0."""
+    a = np.asarray(x)
+    if a.ndim != 3 or a.shape[0] != 3:
+        raise ValueError("x must be an array of dim c(3, width, height)")
+    width, height = a.shape[1], a.shape[2]
+    out = dlib_surf_points(a.ravel(order="F"), rows=height, cols=width, max_points=max_points,
+                           detection_threshold=detection_threshold)
+    out["surf"][np.isnan(out["surf"])] = 0
+    return out
+
+
+def surf_batch(frames, max_points=10000, detection_threshold=30.0, cap=None):
+    """Batch form (new surface): uint8 [n, rows, cols, 3] -> list of dicts like dlib_surf_points."""
+    lib = _lib.load()
+    f = np.ascontiguousarray(frames, dtype=np.uint8)
+    n, rows, cols, _ = f.shape
+    cap = int(cap or max_points)
+    rec = np.zeros((n, cap, 70), np.float64)
+    cnt = np.zeros(n, np.int32)
+    _lib.check(lib.b2f_surf_batch(_lib.context(), _lib.ptr(f), n, rows, cols, C.c_long(int(max_points)),
+                                  float(detection_threshold), cap, _lib.ptr(rec), _lib.ptr(cnt)))
+    outs = []
+    for i in range(n):
+        r = rec[i, :cnt[i]]
+        outs.append(dict(points=int(cnt[i]), x=r[:, 0].copy(), y=r[:, 1].copy(), angle=r[:, 2].copy(),
+                         pyramid_scale=r[:, 3].copy(), score=r[:, 4].copy(), laplacian=r[:, 5].copy(), surf=r[:, 6:].copy()))
+    return outs
+
+
 def smoke_check(po):
     from . import synth
     img = synth.frame_rgb(3, 72, 104)
     out = image_fhog(np.ascontiguousarray(img.transpose(2, 1, 0)))
     ref = po.fhog(img, 8, 1, 1, impl="oracle")
     assert out["fhog"].shape == ref.shape and np.array_equal(out["fhog"], ref), "FHOG differs from the oracle"
+    blobs = synth.frame_blobs(4, 240, 320)
+    sp = image_surf(np.ascontiguousarray(blobs.transpose(2, 1, 0)), max_points=200, detection_threshold=5)
+    rs = po.surf(blobs, 200, 5.0, impl="oracle")
+    assert sp["points"] == len(rs["x"]) and np.array_equal(sp["x"], rs["x"]) and np.array_equal(sp["score"], rs["score"]), "SURF key points differ"
+    if sp["points"]:
+        np.testing.assert_allclose(sp["surf"], rs["surf"], rtol=1e-4, atol=1e-9)
