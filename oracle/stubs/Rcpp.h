@@ -12,11 +12,15 @@
 #include <string>
 #include <cstddef>
 #include <stdexcept>
+#include <cstdlib>
+#include <initializer_list>
 
 struct SEXPREC { virtual ~SEXPREC() {} };
 typedef SEXPREC *SEXP;
 
 namespace Rcpp {
+
+inline void stop(const std::string &msg) { throw std::runtime_error(msg); }
 
 struct Dimension { long a, b; Dimension(long a_, long b_) : a(a_), b(b_) {} };
 
