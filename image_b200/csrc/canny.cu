@@ -271,45 +271,96 @@ __device__ __forceinline__ void uf_union(int *L, int a, int b) {
   }
 }
 
-constexpr int HT = 32;   // hysteresis tile edge
+constexpr int HT = 32;   // hysteresis tile edge (one warp lane per column)
+
+__device__ __forceinline__ int run_start(unsigned bits, int x) {
+  // first column of the run of set bits that contains bit x (bit x must be set)
+  return x - __clz(~(bits << (31 - x))) + 1;
+}
+
+// Level 1.  One CTA per 32x32 tile, a warp works on whole rows.  Horizontal runs are found with
+// ballots (no atomics): every pixel of a run is labelled with the run's first pixel.  Only run
+// heads take part in the shared-memory union-find, and a pair of vertically adjacent runs is
+// linked once (at the first column where they touch).  Output per edge pixel: L[p] = GLOBAL index
+// of the tile-local root; rinfo[p] = bit0 "p is a tile root", bit1 "its tile component holds a
+// class-2 pixel".
 __global__ void __launch_bounds__(256)
-hyst_local_kernel(const unsigned char *__restrict__ cls, int *__restrict__ L, int nx, int ny) {
+hyst_local_kernel(const unsigned char *__restrict__ cls, int *__restrict__ L, unsigned char *__restrict__ rinfo, int nx, int ny) {
   __shared__ int lab[HT * HT];
-  __shared__ unsigned char sc[HT * HT];
+  __shared__ unsigned rowmask[HT], strongmask[HT];
+  __shared__ unsigned char cstrong[HT * HT];
   const int x0 = blockIdx.x * HT, y0 = blockIdx.y * HT;
   const size_t base = (size_t)blockIdx.z * nx * ny;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 8 rows of threads, 4 pixels each
+  int root_dummy[4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gx = x0 + lane;
+  {   // stage the tile: one 32-bit load per thread (4 pixels) when rows are word aligned
+    __shared__ __align__(4) unsigned char sc[HT * HT];
+    const int r = threadIdx.x >> 3, w = threadIdx.x & 7, gy = y0 + r, wx = x0 + 4 * w;
+    unsigned v = 0;
+    if (gy < ny) {
+      const unsigned char *row = cls + base + (size_t)gy * nx;
+      if ((nx & 3) == 0 && wx + 3 < nx) v = *reinterpret_cast<const unsigned *>(row + wx);
+      else { for (int b = 0; b < 4; b++) if (wx + b < nx) v |= (unsigned)row[wx + b] << (8 * b); }
+    }
+    reinterpret_cast<unsigned *>(sc)[threadIdx.x] = v;
+    __syncthreads();
+    // hand the staged bytes to the row loop below through registers
+#pragma unroll
+    for (int k = 0; k < 4; k++) root_dummy[k] = sc[(warp + 8 * k) * HT + lane];
+  }
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    int ly = ty + 8 * k, gx = x0 + tx, gy = y0 + ly, i = ly * HT + tx;
-    unsigned char c = (gx < nx && gy < ny) ? cls[base + (size_t)gy * nx + gx] : 0;
-    sc[i] = c;
-    lab[i] = i;
+    const int r = warp + 8 * k;
+    const unsigned char c = (unsigned char)root_dummy[k];
+    const unsigned bits = __ballot_sync(0xffffffffu, c != 0), sb = __ballot_sync(0xffffffffu, c == 2);
+    if (lane == 0) { rowmask[r] = bits; strongmask[r] = sb; }
+    lab[r * HT + lane] = c ? r * HT + run_start(bits, lane) : r * HT + lane;
+    cstrong[r * HT + lane] = 0;
   }
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    int ly = ty + 8 * k, i = ly * HT + tx;
-    if (!sc[i]) continue;
-    if (tx + 1 < HT && sc[i + 1]) uf_union(lab, i, i + 1);
-    if (ly + 1 < HT) {
-      if (tx > 0 && sc[i + HT - 1]) uf_union(lab, i, i + HT - 1);
-      if (sc[i + HT]) uf_union(lab, i, i + HT);
-      if (tx + 1 < HT && sc[i + HT + 1]) uf_union(lab, i, i + HT + 1);
+    const int r = warp + 8 * k;
+    if (r == 0) continue;
+    const unsigned bits = rowmask[r], up = rowmask[r - 1];
+    if (!((bits >> lane) & 1u) || !up) continue;
+    const int st = run_start(bits, lane);
+    const bool isStart = st == lane, isEnd = lane == 31 || !((bits >> (lane + 1)) & 1u);
+    const bool N = (up >> lane) & 1u, NW = lane > 0 && ((up >> (lane - 1)) & 1u), NE = lane < 31 && ((up >> (lane + 1)) & 1u);
+    const int me = r * HT + st;
+    if (N) {
+      if (isStart || !NW) uf_union(lab, me, (r - 1) * HT + run_start(up, lane));
+    } else {
+      if (NW && isStart) uf_union(lab, me, (r - 1) * HT + run_start(up, lane - 1));
+      if (NE && isEnd) uf_union(lab, me, (r - 1) * HT + run_start(up, lane + 1));
+    }
+  }
+  __syncthreads();
+  int root[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int r = warp + 8 * k, i = r * HT + lane;
+    root[k] = -1;
+    if ((rowmask[r] >> lane) & 1u) {
+      root[k] = uf_find(lab, i);
+      if ((strongmask[r] >> lane) & 1u) cstrong[root[k]] = 1;
     }
   }
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    int ly = ty + 8 * k, i = ly * HT + tx, gx = x0 + tx, gy = y0 + ly;
-    if (!sc[i]) continue;
-    int r = uf_find(lab, i);
-    int ry = r / HT, rx = r - ry * HT;
-    L[base + (size_t)gy * nx + gx] = (int)(base + (size_t)(y0 + ry) * nx + (x0 + rx));
+    const int r = warp + 8 * k, i = r * HT + lane, gy = y0 + r;
+    if (gx >= nx || gy >= ny) continue;
+    const size_t p = base + (size_t)gy * nx + gx;
+    if (root[k] < 0) { rinfo[p] = 0; continue; }
+    const int ry = root[k] / HT, rx = root[k] - ry * HT;
+    L[p] = (int)(base + (size_t)(y0 + ry) * nx + (x0 + rx));
+    rinfo[p] = (root[k] == i) ? (unsigned char)(1 | (cstrong[i] << 1)) : (unsigned char)0;
   }
 }
-// seams: a pixel on the right / bottom / left edge of its tile unions with its forward neighbours
-// (E, SW, S, SE) that live in another tile.  One thread per seam pixel: 3*HT slots per tile.
+// Level 2: seams.  A pixel on the right / bottom / left edge of its tile unions with its forward
+// neighbours (E, SW, S, SE) that live in another tile.  3*HT slots per tile.
 __global__ void hyst_seam_kernel(const unsigned char *__restrict__ cls, int *__restrict__ L, int nx, int ny) {
   const int slot = threadIdx.x;                                  // 0..95
   const int x0 = blockIdx.x * HT, y0 = blockIdx.y * HT;
@@ -331,25 +382,78 @@ __global__ void hyst_seam_kernel(const unsigned char *__restrict__ cls, int *__r
     if ((bottom || right) && x + 1 < nx && cls[p + nx + 1]) uf_union(L, (int)p, (int)(p + nx + 1));
   }
 }
-__global__ void hyst_mark(const unsigned char *__restrict__ cls, int *__restrict__ L, unsigned char *__restrict__ strong, size_t n) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n && cls[i] == 2) strong[uf_find(L, (int)i)] = 1;
-}
-__global__ void hyst_emit(const unsigned char *__restrict__ cls, int *__restrict__ L, const unsigned char *__restrict__ strong,
-                          unsigned char *__restrict__ edges, int *__restrict__ nonzero, size_t plane) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t f = blockIdx.y;
-  bool on = false;
-  if (i < plane) {
-    size_t p = f * plane + i;
-    on = cls[p] && strong[uf_find(L, (int)p)];
-    edges[p] = on ? 255 : 0;
+// tile roots whose tile component holds a class-2 pixel mark the global root; 16 pixels per thread
+__global__ void hyst_mark(const unsigned char *__restrict__ rinfo, int *__restrict__ L, unsigned char *__restrict__ strong, size_t n) {
+  size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  if (i0 >= n) return;
+  if (i0 + 16 <= n) {
+    uint4 v = *reinterpret_cast<const uint4 *>(rinfo + i0);
+    unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      if (!w[q]) continue;
+#pragma unroll
+      for (int b = 0; b < 4; b++)
+        if (((w[q] >> (8 * b)) & 0xff) == 3) strong[uf_find(L, (int)(i0 + 4 * q + b))] = 1;
+    }
+  } else {
+    for (size_t i = i0; i < n; i++) if (rinfo[i] == 3) strong[uf_find(L, (int)i)] = 1;
   }
-  unsigned b = __ballot_sync(0xffffffffu, on);
+}
+// every tile root learns whether its global component is strong (bit2 of rinfo)
+__global__ void hyst_resolve(unsigned char *__restrict__ rinfo, int *__restrict__ L, const unsigned char *__restrict__ strong, size_t n) {
+  size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  if (i0 >= n) return;
+  if (i0 + 16 <= n) {
+    uint4 v = *reinterpret_cast<const uint4 *>(rinfo + i0);
+    unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      if (!w[q]) continue;
+#pragma unroll
+      for (int b = 0; b < 4; b++)
+        if ((w[q] >> (8 * b)) & 1u) { size_t i = i0 + 4 * q + b; if (strong[uf_find(L, (int)i)]) rinfo[i] |= 4; }
+    }
+  } else {
+    for (size_t i = i0; i < n; i++) if ((rinfo[i] & 1) && strong[uf_find(L, (int)i)]) rinfo[i] |= 4;
+  }
+}
+// L[p] of an edge pixel is a tile-root node of its component (its own tile root, or an ancestor
+// after path halving): one gather tells whether the pixel survives.  16 pixels per thread.
+__global__ void hyst_emit(const unsigned char *__restrict__ cls, const int *__restrict__ L, const unsigned char *__restrict__ rinfo,
+                          unsigned char *__restrict__ edges, int *__restrict__ nonzero, size_t plane, int vec) {
+  const size_t f = blockIdx.y;
+  const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  int mine = 0;
+  if (i0 < plane) {
+    const size_t p0 = f * plane + i0;
+    if (vec && i0 + 16 <= plane) {
+      uint4 v = *reinterpret_cast<const uint4 *>(cls + p0);
+      unsigned w[4] = {v.x, v.y, v.z, v.w}, o[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        if (!w[q]) continue;
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+          if ((w[q] >> (8 * b)) & 0xff) {
+            if (rinfo[L[p0 + 4 * q + b]] & 4) { o[q] |= 0xffu << (8 * b); mine++; }
+          }
+      }
+      *reinterpret_cast<uint4 *>(edges + p0) = make_uint4(o[0], o[1], o[2], o[3]);
+    } else {
+      for (size_t i = i0; i < plane && i < i0 + 16; i++) {
+        size_t p = f * plane + i;
+        bool on = cls[p] && (rinfo[L[p]] & 4);
+        edges[p] = on ? 255 : 0;
+        mine += on;
+      }
+    }
+  }
+  for (int o = 16; o; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
   __shared__ int cnt;
   if (threadIdx.x == 0) cnt = 0;
   __syncthreads();
-  if ((threadIdx.x & 31) == 0 && b) atomicAdd(&cnt, __popc(b));
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&cnt, mine);
   __syncthreads();
   if (threadIdx.x == 0 && cnt) atomicAdd(&nonzero[f], cnt);
 }
@@ -383,7 +487,7 @@ static bool symmetric_taps(const std::vector<int> &c, const std::vector<double> 
 
 size_t canny_scratch_bytes(int n_frames, int nx, int ny) {
   size_t n = (size_t)n_frames * nx * ny;
-  return align256(n * 4) /*blur*/ + align256(n) /*cls*/ + align256(n * 4) /*labels*/ + align256(n) /*strong*/ +
+  return align256(n * 4) /*blur*/ + align256(n) /*cls*/ + align256(n * 4) /*labels*/ + align256(n) /*strong*/ + align256(n) /*rinfo*/ +
          align256(n * 8) /*generic path rows*/ + (1 << 16);
 }
 
@@ -396,6 +500,7 @@ int canny_device(b2f_ctx *ctx, const unsigned char *d_frames, int n_frames, int 
   unsigned char *cls = ctx->arena.get<unsigned char>(n);
   int *L = ctx->arena.get<int>(n);
   unsigned char *strong = ctx->arena.get<unsigned char>(n);
+  unsigned char *rinfo = ctx->arena.get<unsigned char>(n);
   std::vector<int> cx, cy; std::vector<double> wx, wy;
   make_taps(nx, s, cx, wx); make_taps(ny, s, cy, wy);
   CannyTaps tx, ty;
@@ -433,17 +538,20 @@ int canny_device(b2f_ctx *ctx, const unsigned char *d_frames, int n_frames, int 
   canny_grad_nms_kernel<<<dim3(ceil_div(nx, CG_T), ceil_div(ny, CG_T), n_frames), CG_NT, 0, st>>>(
       blur, cls, nx, ny, acc_grad ? 1 : 0, (int)low_thr, (int)high_thr);   // thresholds truncate like rcpp_canny.cpp:180
   B2F_LAUNCH_CHECK(ctx);
-  unsigned nb = (unsigned)((n + 255) / 256);
   B2F_CUDA(cudaMemsetAsync(strong, 0, n, st));
   B2F_CUDA(cudaMemsetAsync(d_nonzero, 0, sizeof(int) * n_frames, st));
   dim3 tiles(ceil_div(nx, HT), ceil_div(ny, HT), n_frames);
-  hyst_local_kernel<<<tiles, 256, 0, st>>>(cls, L, nx, ny);
+  hyst_local_kernel<<<tiles, 256, 0, st>>>(cls, L, rinfo, nx, ny);
   B2F_LAUNCH_CHECK(ctx);
   hyst_seam_kernel<<<tiles, 3 * HT, 0, st>>>(cls, L, nx, ny);
   B2F_LAUNCH_CHECK(ctx);
-  hyst_mark<<<nb, 256, 0, st>>>(cls, L, strong, n);
+  unsigned nb16 = (unsigned)((n + 16 * 256 - 1) / (16 * 256));
+  hyst_mark<<<nb16, 256, 0, st>>>(rinfo, L, strong, n);
   B2F_LAUNCH_CHECK(ctx);
-  hyst_emit<<<dim3((unsigned)((plane + 255) / 256), n_frames), 256, 0, st>>>(cls, L, strong, d_edges, d_nonzero, plane);
+  hyst_resolve<<<nb16, 256, 0, st>>>(rinfo, L, strong, n);
+  B2F_LAUNCH_CHECK(ctx);
+  const int vec = (plane % 16 == 0) && ((reinterpret_cast<uintptr_t>(d_edges) & 15) == 0);
+  hyst_emit<<<dim3((unsigned)((plane + 16 * 256 - 1) / (16 * 256)), n_frames), 256, 0, st>>>(cls, L, rinfo, d_edges, d_nonzero, plane, vec);
   B2F_LAUNCH_CHECK(ctx);
   return B2F_OK;
 }

@@ -59,6 +59,7 @@ struct b2f_ctx {
   void *pinned = nullptr; // pinned host staging
   size_t pinned_cap = 0;
   long long launches = 0;
+  void *fhog_lut = nullptr;   // 511x511 orientation-snap table (fhog.cu), built on first use
 };
 
 namespace b2f {

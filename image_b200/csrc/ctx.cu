@@ -97,6 +97,7 @@ void b2f_shutdown(b2f_ctx *c) {
   cudaStreamSynchronize(c->stream);
   if (c->arena.base) cudaFree(c->arena.base);
   if (c->pinned) cudaFreeHost(c->pinned);
+  if (c->fhog_lut) cudaFree(c->fhog_lut);
   cudaStreamDestroy(c->stream);
   delete c;
 }

@@ -67,84 +67,119 @@ __device__ __forceinline__ void snap18(float gx, float gy, int &best_o) {
   }
 }
 
+// ---- pass 1: per-pixel (orientation bin, gradient magnitude), written in a cell-phase
+// de-interleaved layout  idx(y,x) = y*PW + (x % cell)*NCB + x / cell  so that pass 2 (one thread per
+// cell, consecutive threads = consecutive cells) reads consecutive addresses.
+constexpr int FP_TW = 64, FP_TH = 16;
+constexpr int FP_RB = ((FP_TW + 2) * 3 + 3 + 3) & ~3;      // staged bytes per row, word aligned (+ up to 3 lead bytes)
+
+// 18-way orientation snap for every integer gradient (gx, gy) in [-255, 255]^2, built once per
+// context with the same un-fused float expressions (snap18): lut[(gy+255)*512 + gx+255].
+__global__ void fhog_lut_kernel(unsigned char *__restrict__ lut) {
+  int gx = (int)(blockIdx.x * blockDim.x + threadIdx.x) - 255, gy = (int)blockIdx.y - 255;
+  if (gx > 255) return;
+  int o;
+  snap18((float)gx, (float)gy, o);
+  lut[(gy + 255) * 512 + gx + 255] = (unsigned char)o;
+}
+
 __global__ void __launch_bounds__(FH_NT)
-fhog_hist_kernel(const unsigned char *__restrict__ frames, float *__restrict__ hist, FhogGeom g, FhogTables tb,
-                 int CT, int P /* pixel region edge = (CT+1)*cell + 2 */) {
-  extern __shared__ __align__(16) unsigned char sm[];
-  // layout: sv[P*P] float | shist[18*CT*CT] float | so[P*P] u8 | rgb[(P+2)*(P+2)*3] u8
-  float *sv = reinterpret_cast<float *>(sm);
-  float *shist = sv + P * P;
-  unsigned char *so = reinterpret_cast<unsigned char *>(shist + 18 * CT * CT);
-  unsigned char *srgb = so + ((P * P + 15) & ~15);
-  const int R0 = blockIdx.y * CT, C0 = blockIdx.x * CT;          // first histogram row/col of this tile
-  const int HR = g.cells_nr + 2, HC = g.cells_nc + 2;
-  const int nR = min(CT, HR - R0), nC = min(CT, HC - C0);
-  // pixel range voting into the tile
-  const int py0 = tb.ylo[R0], py1 = tb.yhi[R0 + nR - 1], px0 = tb.xlo[C0], px1 = tb.xhi[C0 + nC - 1];
-  const int ph = py1 - py0, pw = px1 - px0;                       // may be <= 0 (rim cells with no voters)
+fhog_pixel_kernel(const unsigned char *__restrict__ frames, float *__restrict__ vmag, unsigned char *__restrict__ obin,
+                  FhogGeom g, const int *__restrict__ colidx, int PW, const unsigned char *__restrict__ lut, int aligned) {
+  __shared__ __align__(16) unsigned char srgb[(FP_TH + 2) * FP_RB];
+  const int x0 = 1 + blockIdx.x * FP_TW, y0 = 1 + blockIdx.y * FP_TH;       // voters live in [1, visible)
   const unsigned char *src = frames + (size_t)blockIdx.z * g.rows * g.cols * 3;
-  const int W2 = pw + 2;
-  if (ph > 0 && pw > 0) {
-    // stage RGB rows [py0-1, py1+1) x cols [px0-1, px1+1) (always inside the image: voters are in [1, visible))
-    const int rowbytes = W2 * 3;
-    for (int i = threadIdx.x; i < (ph + 2) * rowbytes; i += FH_NT) {
-      int r = i / rowbytes, b = i - r * rowbytes;
-      srgb[r * rowbytes + b] = __ldg(src + ((size_t)(py0 - 1 + r) * g.cols + (px0 - 1)) * 3 + b);
+  const int b0 = (x0 - 1) * 3;                      // first byte of the staged row segment
+  const int lead = aligned ? (b0 & 3) : 0;          // bytes in front of it when loading whole words
+  const int rowlimit = g.cols * 3;
+  if (aligned) {
+    const int w0 = (b0 - lead) >> 2;
+    for (int i = threadIdx.x; i < (FP_TH + 2) * (FP_RB / 4); i += FH_NT) {
+      int r = i / (FP_RB / 4), w = i - r * (FP_RB / 4);
+      int gy = min(y0 - 1 + r, g.rows - 1);
+      int wb = min((w0 + w) * 4, rowlimit - 4);     // rows are multiples of 4 bytes on this path
+      reinterpret_cast<unsigned *>(srgb)[r * (FP_RB / 4) + w] = __ldg(reinterpret_cast<const unsigned *>(src + (size_t)gy * rowlimit + wb));
+    }
+  } else {
+    for (int i = threadIdx.x; i < (FP_TH + 2) * FP_RB; i += FH_NT) {
+      int r = i / FP_RB, b = i - r * FP_RB;
+      int gy = min(y0 - 1 + r, g.rows - 1), gxb = min(b0 + b, rowlimit - 1);
+      srgb[i] = __ldg(src + (size_t)gy * rowlimit + gxb);
     }
   }
-  for (int i = threadIdx.x; i < 18 * CT * CT; i += FH_NT) shist[i] = 0.f;
   __syncthreads();
-  if (ph > 0 && pw > 0) {
-    // phase 1: per-pixel gradient -> (bin, magnitude)
-    for (int i = threadIdx.x; i < ph * pw; i += FH_NT) {
-      int r = i / pw, c = i - r * pw;
-      const unsigned char *p = srgb + ((r + 1) * W2 + (c + 1)) * 3;
-      const bool simd = (px0 + c) < g.simd_end;
-      int bx = 0, by = 0, bl = -1;
+  const size_t plane = (size_t)g.rows * PW;
+  float *vout = vmag + (size_t)blockIdx.z * plane;
+  unsigned char *oout = obin + (size_t)blockIdx.z * plane;
+  for (int i = threadIdx.x; i < FP_TW * FP_TH; i += FH_NT) {
+    const int r = i / FP_TW, c = i - r * FP_TW;
+    const int x = x0 + c, y = y0 + r;
+    if (x >= g.visible_nc || y >= g.visible_nr) continue;
+    const unsigned char *p = srgb + (r + 1) * FP_RB + lead + (c + 1) * 3;
+    const bool simd = x < g.simd_end;
+    int bx = 0, by = 0, bl = -1;
 #pragma unroll
-      for (int ch = 0; ch < 3; ch++) {
-        int dx = (int)p[3 + ch] - (int)p[-3 + ch];
-        int dy = (int)p[W2 * 3 + ch] - (int)p[-W2 * 3 + ch];
-        int l = dx * dx + dy * dy;
-        bool take = (ch == 0) || (simd ? !(bl > l) : (l > bl));
-        if (take) { bx = dx; by = dy; bl = l; }
-      }
-      int o;
-      snap18((float)bx, (float)by, o);
-      sv[r * pw + c] = __fsqrt_rn((float)bl);
-      so[r * pw + c] = (unsigned char)o;
+    for (int ch = 0; ch < 3; ch++) {
+      int dx = (int)p[3 + ch] - (int)p[-3 + ch];
+      int dy = (int)p[FP_RB + ch] - (int)p[-FP_RB + ch];
+      int l = dx * dx + dy * dy;
+      bool take = (ch == 0) || (simd ? !(bl > l) : (l > bl));
+      if (take) { bx = dx; by = dy; bl = l; }
     }
+    const int o = __ldg(lut + ((by + 255) << 9) + (bx + 255));
+    const size_t idx = (size_t)y * PW + __ldg(colidx + x);
+    vout[idx] = __fsqrt_rn((float)bl);
+    oout[idx] = (unsigned char)o;
   }
-  __syncthreads();
-  // phase 2: one thread per histogram cell, votes replayed in raster order
-  const int t = threadIdx.x;
-  if (t < nR * nC && ph > 0 && pw > 0) {
-    const int lr = t / nC, lc = t - lr * nC;
-    const int R = R0 + lr, C = C0 + lc;
-    float *h = shist + t;                       // bin o at h[o * CT*CT]
-    const int HS = CT * CT;
+}
+
+// ---- pass 2: one thread per histogram cell replays that cell's votes in raster order into a
+// private shared-memory histogram (bank = thread, conflict-free); bit-identical to the reference.
+constexpr int FC_NT = 128;
+__global__ void __launch_bounds__(FC_NT)
+fhog_cell_kernel(const float *__restrict__ vmag, const unsigned char *__restrict__ obin, float *__restrict__ hist,
+                 FhogGeom g, FhogTables tb, const int *__restrict__ colidx, int PW, int KW /* cached x weights per thread */) {
+  extern __shared__ float sh[];          // [18][FC_NT] histogram, then [KW][FC_NT] x weights
+  float *swx = sh + 18 * FC_NT;
+  const int HR = g.cells_nr + 2, HC = g.cells_nc + 2;
+  const int R = blockIdx.y, C = blockIdx.x * FC_NT + threadIdx.x;
+#pragma unroll
+  for (int o = 0; o < 18; o++) sh[o * FC_NT + threadIdx.x] = 0.f;
+  if (C < HC) {
+    const size_t plane = (size_t)g.rows * PW;
+    const float *vin = vmag + (size_t)blockIdx.z * plane;
+    const unsigned char *oin = obin + (size_t)blockIdx.z * plane;
     const int ya = tb.ylo[R], yb = tb.yhi[R], xa = tb.xlo[C], xb = tb.xhi[C];
+    float *h = sh + threadIdx.x;
+    float *wxs = swx + threadIdx.x;
+    const int nxw = min(xb - xa, KW);
+    // x weight of pixel xa+k for THIS cell; a set sign bit marks the scalar-tail product order
+    for (int k = 0; k < nxw; k++) {
+      const int x = xa + k;
+      const float wx = (__ldg(tb.c0 + x) == C) ? __ldg(tb.vx1 + x) : __ldg(tb.vx0 + x);
+      wxs[k * FC_NT] = (x < g.simd_end) ? wx : -wx;
+    }
     for (int y = ya; y < yb; y++) {
-      const float wy = (tb.r0[y] == R) ? tb.vy1[y] : tb.vy0[y];
-      const float *rv = sv + (y - py0) * pw - px0;
-      const unsigned char *ro = so + (y - py0) * pw - px0;
+      const float wy = (__ldg(tb.r0 + y) == R) ? __ldg(tb.vy1 + y) : __ldg(tb.vy0 + y);
+      const size_t rowoff = (size_t)y * PW;
       for (int x = xa; x < xb; x++) {
-        const float wx = (tb.c0[x] == C) ? tb.vx1[x] : tb.vx0[x];
-        const float v = rv[x];
-        const int o = ro[x];
+        const int k = x - xa;
+        float wq;
+        if (k < KW) wq = wxs[k * FC_NT];
+        else { const float wx = (__ldg(tb.c0 + x) == C) ? __ldg(tb.vx1 + x) : __ldg(tb.vx0 + x); wq = (x < g.simd_end) ? wx : -wx; }
+        const size_t idx = rowoff + __ldg(colidx + x);
+        const float v = __ldg(vin + idx);
+        const int o = __ldg(oin + idx);
         // simd body: vy*(vx*v) (fhog.h:867-874) ; scalar tail: (vy*vx)*v (fhog.h:951-954)
-        const float val = (x < g.simd_end) ? __fmul_rn(wy, __fmul_rn(wx, v)) : __fmul_rn(__fmul_rn(wy, wx), v);
-        h[o * HS] = __fadd_rn(h[o * HS], val);
+        const bool tail = __float_as_int(wq) < 0;
+        const float wx = fabsf(wq);
+        const float val = tail ? __fmul_rn(__fmul_rn(wy, wx), v) : __fmul_rn(wy, __fmul_rn(wx, v));
+        h[o * FC_NT] = __fadd_rn(h[o * FC_NT], val);
       }
     }
-  }
-  __syncthreads();
-  // write the tile's histograms: hist[frame][R][C][18]
-  float *dst = hist + (size_t)blockIdx.z * HR * HC * 18;
-  for (int i = threadIdx.x; i < nR * nC * 18; i += FH_NT) {
-    int cellidx = i / 18, o = i - cellidx * 18;
-    int lr = cellidx / nC, lc = cellidx - lr * nC;
-    dst[((size_t)(R0 + lr) * HC + (C0 + lc)) * 18 + o] = shist[o * CT * CT + cellidx];
+    float *dst = hist + ((size_t)blockIdx.z * HR * HC + (size_t)R * HC + C) * 18;
+#pragma unroll
+    for (int o = 0; o < 18; o++) dst[o] = h[o * FC_NT];
   }
 }
 
@@ -217,7 +252,8 @@ size_t fhog_scratch_bytes(int n_frames, const FhogGeom &g) {
   size_t hist = (size_t)n_frames * (g.cells_nr + 2) * (g.cells_nc + 2) * 18 * 4;
   size_t norm = (size_t)n_frames * g.cells_nr * g.cells_nc * 4;
   size_t tabs = (size_t)(g.rows + g.cols) * (2 + 4 + 4) + (size_t)(g.cells_nr + g.cells_nc + 4) * 8 + 4096;
-  return align256(hist) + align256(norm) + 12 * align256(tabs) + (1 << 16);
+  size_t vplane = (size_t)g.rows * (size_t)(g.cell * (g.cols / g.cell + 2)) * n_frames;
+  return align256(hist) + align256(norm) + align256(vplane * 4) + align256(vplane) + 12 * align256(tabs) + (1 << 16);
 }
 
 int fhog_device(b2f_ctx *ctx, const unsigned char *d_frames, int n_frames, const FhogGeom &g, float *d_out, cudaStream_t st) {
@@ -270,29 +306,46 @@ int fhog_device(b2f_ctx *ctx, const unsigned char *d_frames, int n_frames, const
   // ---- device buffers
   float *hist = ctx->arena.get<float>((size_t)n_frames * HR * HC * 18);
   float *norm = ctx->arena.get<float>((size_t)n_frames * g.cells_nr * g.cells_nc);
+  const size_t vplane = (size_t)g.rows * (size_t)(cell * (g.cols / cell + 2));
+  float *vmag = ctx->arena.get<float>((size_t)n_frames * vplane);
+  unsigned char *obin = ctx->arena.get<unsigned char>((size_t)n_frames * vplane);
   short *d_r0 = ctx->arena.get<short>(g.rows), *d_c0 = ctx->arena.get<short>(g.cols);
   float *d_vy0 = ctx->arena.get<float>(g.rows), *d_vy1 = ctx->arena.get<float>(g.rows);
   float *d_vx0 = ctx->arena.get<float>(g.cols), *d_vx1 = ctx->arena.get<float>(g.cols);
+  const int NCB0 = g.cols / cell + 2;
+  std::vector<int> colidx(g.cols);
+  for (int x = 0; x < g.cols; x++) colidx[x] = (x % cell) * NCB0 + x / cell;      // cell-phase de-interleaved column
+  int *d_colidx = ctx->arena.get<int>(g.cols);
   int *d_ylo = ctx->arena.get<int>(HR), *d_yhi = ctx->arena.get<int>(HR), *d_xlo = ctx->arena.get<int>(HC), *d_xhi = ctx->arena.get<int>(HC);
   B2F_ARENA_CHECK(ctx);
 #define UP(d, v) B2F_CUDA(cudaMemcpyAsync(d, v.data(), v.size() * sizeof(v[0]), cudaMemcpyHostToDevice, st))
   UP(d_r0, r0); UP(d_c0, c0); UP(d_vy0, vy0); UP(d_vy1, vy1); UP(d_vx0, vx0); UP(d_vx1, vx1);
-  UP(d_ylo, ylo); UP(d_yhi, yhi); UP(d_xlo, xlo); UP(d_xhi, xhi);
+  UP(d_ylo, ylo); UP(d_yhi, yhi); UP(d_xlo, xlo); UP(d_xhi, xhi); UP(d_colidx, colidx);
 #undef UP
   B2F_CUDA(cudaStreamSynchronize(st));   // host tables go out of scope at return
   FhogTables tb{d_r0, d_c0, d_vy0, d_vy1, d_vx0, d_vx1, d_ylo, d_yhi, d_xlo, d_xhi};
 
-  int CT = std::min(16, std::max(1, 72 / cell));
-  // largest pixel span of any tile (rows / cols) decides the shared-memory footprint
-  int P = 0;
-  for (int R = 0; R < HR; R += CT) P = std::max(P, yhi[std::min(R + CT, HR) - 1] - ylo[R]);
-  for (int C = 0; C < HC; C += CT) P = std::max(P, xhi[std::min(C + CT, HC) - 1] - xlo[C]);
-  P = std::max(P, 1);
-  size_t smem = sizeof(float) * ((size_t)P * P + 18 * CT * CT) + (((size_t)P * P + 15) & ~15) + (size_t)(P + 2) * (P + 2) * 3 + 16;
-  if (smem > 220 * 1024) { set_error("fhog: cell_size %d needs %zu bytes of shared memory per tile", cell, smem); return B2F_EUNSUP; }
-  B2F_CUDA(cudaFuncSetAttribute(fhog_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  fhog_hist_kernel<<<dim3(ceil_div(HC, CT), ceil_div(HR, CT), n_frames), FH_NT, smem, st>>>(d_frames, hist, g, tb, CT, P);
+  const int NCB = g.cols / cell + 2, PW = cell * NCB;
+  if (!ctx->fhog_lut) {       // one-time 256 KB orientation table
+    void *lut = nullptr;
+    B2F_CUDA(cudaMalloc(&lut, 512 * 512));
+    fhog_lut_kernel<<<dim3(2, 511), 256, 0, st>>>((unsigned char *)lut);
+    B2F_LAUNCH_CHECK(ctx);
+    ctx->fhog_lut = lut;
+  }
+  fhog_pixel_kernel<<<dim3(ceil_div(std::max(g.visible_nc - 1, 1), FP_TW), ceil_div(std::max(g.visible_nr - 1, 1), FP_TH), n_frames), FH_NT, 0, st>>>(
+      d_frames, vmag, obin, g, d_colidx, PW, (const unsigned char *)ctx->fhog_lut,
+      (g.cols % 4 == 0 && (reinterpret_cast<uintptr_t>(d_frames) & 3) == 0) ? 1 : 0);
   B2F_LAUNCH_CHECK(ctx);
+  {
+    int maxw = 1;
+    for (int C = 0; C < HC; C++) maxw = std::max(maxw, xhi[C] - xlo[C]);
+    const int KW = std::min(maxw, 96);
+    size_t smem = sizeof(float) * (size_t)(18 + KW) * FC_NT;
+    B2F_CUDA(cudaFuncSetAttribute(fhog_cell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fhog_cell_kernel<<<dim3(ceil_div(HC, FC_NT), HR, n_frames), FC_NT, smem, st>>>(vmag, obin, hist, g, tb, d_colidx, PW, KW);
+    B2F_LAUNCH_CHECK(ctx);
+  }
   fhog_norm_kernel<<<dim3(ceil_div(g.cells_nc, 128), g.cells_nr, n_frames), 128, 0, st>>>(hist, norm, g);
   B2F_LAUNCH_CHECK(ctx);
   if (g.out_nr != g.hog_nr || g.out_nc != g.hog_nc)   // zero border of init_hog (fhog.h:459-470)

@@ -129,15 +129,17 @@ nms_bitmask_kernel(const float *__restrict__ R, unsigned *__restrict__ mask, int
   const int TH2 = NMS_TH + 2 * radius;
   const int x0 = blockIdx.x * NMS_TW, y0 = blockIdx.y * NMS_TH;
   const float *Rf = R + (size_t)nx * ny * blockIdx.z;
-  for (int i = threadIdx.x; i < P * TH2; i += NMS_NT) {
-    int r = i / P, c = i - r * P;
-    int gx = x0 - radius + c, gy = y0 - radius + r;
-    float v = -INFINITY;
-    if (gx >= 0 && gx < nx && gy >= 0 && gy < ny) v = __ldg(Rf + (size_t)gy * nx + gx);
-    tile[i] = v;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;    // 8 warps
+  for (int r = warp; r < TH2; r += NMS_NT / 32) {                // a warp streams whole tile rows
+    const int gy = y0 - radius + r;
+    const bool rowok = gy >= 0 && gy < ny;
+    const float *src = Rf + (size_t)(rowok ? gy : 0) * nx;
+    for (int c = lane; c < P; c += 32) {
+      const int gx = x0 - radius + c;
+      tile[r * P + c] = (rowok && gx >= 0 && gx < nx) ? __ldg(src + gx) : -INFINITY;
+    }
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;    // 8 warps
 #pragma unroll 1
   for (int s = warp; s < NMS_TH * (NMS_TW / 32); s += NMS_NT / 32) {
     int row = s / (NMS_TW / 32), seg = s - row * (NMS_TW / 32);
