@@ -29,55 +29,74 @@ struct CannyTaps {
 // ------------------------------------------------------------------------------------------ blur
 constexpr int CB_TW = 32, CB_TH = 128, CB_NT = 256;
 
-__device__ __forceinline__ double u32_to_double(unsigned s) {
-  // exact int -> double without the conversion unit: (2^52 + s) - 2^52
-  return __dadd_rn(__hiloint2double(0x43300000, (int)s), -4503599627370496.0);
+__device__ __forceinline__ int wrap_index(int p, int n) {   // circular addressing, tools.c:151-155
+  while (p < 0) p += n;
+  while (p >= n) p -= n;
+  return p;
 }
 
+// Shared memory: the input tile is converted to double ONCE at load time (u8 -> double is exact),
+// so both passes are pure DADD/DMUL streams: pair sum, product, accumulate (40 fp64 ops / output).
 template <int RT>
 __global__ void __launch_bounds__(CB_NT)
 canny_blur_kernel(const unsigned char *__restrict__ frames, float *__restrict__ out, int nx, int ny,
                   const __grid_constant__ CannyTaps tx, const __grid_constant__ CannyTaps ty) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(16) double smem_d[];
   const int RX = RT ? RT : tx.R, RY = RT ? RT : ty.R;
   const int TILE_H = CB_TH + 2 * RY, TILE_W = CB_TW + 2 * RX;
-  const int TP = (TILE_W + 3) & ~3;                       // u8 pitch
-  double *rowbuf = reinterpret_cast<double *>(smem_raw);  // [TILE_H][CB_TW]
-  unsigned char *tile = smem_raw + sizeof(double) * (size_t)TILE_H * CB_TW;
+  const int TP = (TILE_W + 1) & ~1;                       // pitch in doubles, even (16-byte rows)
+  double *rowbuf = smem_d;                                // [TILE_H][CB_TW]
+  double *tile = smem_d + (size_t)TILE_H * CB_TW;         // [TILE_H][TP]
   const int x0 = blockIdx.x * CB_TW, y0 = blockIdx.y * CB_TH;
   const unsigned char *src = frames + (size_t)blockIdx.z * nx * ny;
-  // ---- load with wrap-around (circular convolution)
-  for (int i = threadIdx.x; i < TILE_H * TILE_W; i += CB_NT) {
-    int r = i / TILE_W, c = i - r * TILE_W;
-    int gx = (x0 - RX + c) % nx; if (gx < 0) gx += nx;
-    int gy = (y0 - RY + r) % ny; if (gy < 0) gy += ny;
-    tile[r * TP + c] = __ldg(src + (size_t)gy * nx + gx);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // ---- load with wrap-around: a warp streams whole tile rows
+  for (int r = warp; r < TILE_H; r += CB_NT / 32) {
+    const unsigned char *row = src + (size_t)wrap_index(y0 - RY + r, ny) * nx;
+    for (int c = lane; c < TILE_W; c += 32)
+      tile[r * TP + c] = (double)__ldg(row + wrap_index(x0 - RX + c, nx));
   }
   __syncthreads();
-  // ---- row pass: rowbuf[r][c] = w0*v0 + sum_k wk*(v[-k]+v[+k])   (pair sums are exact integers)
-  {
-    const int c = threadIdx.x & 31;
-    for (int r = threadIdx.x >> 5; r < TILE_H; r += CB_NT / 32) {
-      const unsigned char *p = tile + r * TP + c + RX;
-      double acc = __dmul_rn(tx.w[0], u32_to_double(p[0]));
+  // ---- row pass: rowbuf[r][c] = w0*v0 + sum_k wk*(v[-k]+v[+k]); 4 outputs per thread when RT>0
+  if (RT) {
+    constexpr int RR = RT ? RT : 1;
+    constexpr int NV = 4 + 2 * RR;                         // inputs of 4 consecutive outputs
+    for (int it = threadIdx.x; it < TILE_H * (CB_TW / 4); it += CB_NT) {
+      const int r = it / (CB_TW / 4), g = it - r * (CB_TW / 4);
+      const double *p = tile + r * TP + 4 * g;             // output col j uses tile cols j .. j+2R
+      double v[NV];
 #pragma unroll
-      for (int k = 1; k <= (RT ? RT : CANNY_MAXR); k++) {
-        if (!RT && k > RX) break;
-        acc = __dadd_rn(acc, __dmul_rn(tx.w[k], u32_to_double((unsigned)p[-k] + (unsigned)p[k])));
+      for (int q = 0; q < NV / 2; q++) { double2 t = *reinterpret_cast<const double2 *>(p + 2 * q); v[2 * q] = t.x; v[2 * q + 1] = t.y; }
+      double o[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        double acc = __dmul_rn(tx.w[0], v[j + RR]);
+#pragma unroll
+        for (int k = 1; k <= RR; k++) acc = __dadd_rn(acc, __dmul_rn(tx.w[k], __dadd_rn(v[j + RR - k], v[j + RR + k])));
+        o[j] = acc;
       }
-      rowbuf[r * CB_TW + c] = acc;
+      double *d = rowbuf + r * CB_TW + 4 * g;
+      *reinterpret_cast<double2 *>(d) = make_double2(o[0], o[1]);
+      *reinterpret_cast<double2 *>(d + 2) = make_double2(o[2], o[3]);
+    }
+  } else {
+    for (int r = warp; r < TILE_H; r += CB_NT / 32) {
+      const double *p = tile + r * TP + lane + RX;
+      double acc = __dmul_rn(tx.w[0], p[0]);
+      for (int k = 1; k <= RX; k++) acc = __dadd_rn(acc, __dmul_rn(tx.w[k], __dadd_rn(p[-k], p[k])));
+      rowbuf[r * CB_TW + lane] = acc;
     }
   }
   __syncthreads();
   // ---- column pass, register-blocked 8 rows per thread, then narrow to float (tools.c:129)
   {
-    const int c = threadIdx.x & 31;
+    const int c = lane;
     const int gx = x0 + c;
     float *dst = out + (size_t)blockIdx.z * nx * ny;
     if (RT) {
       constexpr int RB = 8;
       constexpr int RR = RT ? RT : 1;
-      for (int rg = threadIdx.x >> 5; rg < CB_TH / RB; rg += CB_NT / 32) {
+      for (int rg = warp; rg < CB_TH / RB; rg += CB_NT / 32) {
         double v[RB + 2 * RR];
 #pragma unroll
         for (int q = 0; q < RB + 2 * RR; q++) v[q] = rowbuf[(rg * RB + q) * CB_TW + c];
@@ -91,7 +110,7 @@ canny_blur_kernel(const unsigned char *__restrict__ frames, float *__restrict__ 
         }
       }
     } else {
-      for (int r = threadIdx.x >> 5; r < CB_TH; r += CB_NT / 32) {
+      for (int r = warp; r < CB_TH; r += CB_NT / 32) {
         const double *p = rowbuf + (r + RY) * CB_TW + c;
         double acc = __dmul_rn(ty.w[0], p[0]);
         for (int k = 1; k <= RY; k++) acc = __dadd_rn(acc, __dmul_rn(ty.w[k], __dadd_rn(p[-k * CB_TW], p[k * CB_TW])));
@@ -156,86 +175,84 @@ constexpr int CG_GH = 2;                 // halo of the grad tile (bilin can tou
 constexpr int CG_GW = CG_T + 2 * CG_GH;  // 36
 constexpr int CG_DW = CG_GW + 2;         // data tile 38
 
+// Tile layout.  Data tile entry (i,j) <-> image pixel (x0-3+i, y0-3+j) CLAMPED to the image
+// (value()/extend(), rcpp_canny.cpp:38-62).  Because the tile itself is clamped, the gradient at the
+// clamped pixel (cx,cy) can be read with plain +-1 offsets around the tile entry of (cx,cy): the
+// neighbour of an edge pixel is again the edge pixel, which is what the tile holds one entry further.
 __global__ void __launch_bounds__(CG_NT)
 canny_grad_nms_kernel(const float *__restrict__ data, unsigned char *__restrict__ cls, int nx, int ny, int accGrad,
                       int low_thr, int high_thr) {
   __shared__ float sd[CG_DW * CG_DW];
-  __shared__ double sg[CG_GW * CG_GW];
+  __shared__ double sg[CG_GW * CG_GW], sh[CG_GW * CG_GW], sv[CG_GW * CG_GW];
   const int x0 = blockIdx.x * CG_T, y0 = blockIdx.y * CG_T;
   const float *src = data + (size_t)blockIdx.z * nx * ny;
-  // data tile entry (i,j) <-> global (x0-3+i, y0-3+j), clamped to the image (rcpp_canny.cpp:38-62)
-  for (int t = threadIdx.x; t < CG_DW * CG_DW; t += CG_NT) {
-    int j = t / CG_DW, i = t - j * CG_DW;
-    int gx = min(max(x0 - 3 + i, 0), nx - 1), gy = min(max(y0 - 3 + j, 0), ny - 1);
-    sd[t] = __ldg(src + (size_t)gy * nx + gx);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int j = warp; j < CG_DW; j += CG_NT / 32) {
+    const float *row = src + (size_t)min(max(y0 - 3 + j, 0), ny - 1) * nx;
+    for (int i = lane; i < CG_DW; i += 32) sd[j * CG_DW + i] = __ldg(row + min(max(x0 - 3 + i, 0), nx - 1));
   }
   __syncthreads();
-  // grad tile entry (i,j) <-> global (x0-2+i, y0-2+j) clamped; gradient evaluated AT the clamped pixel
+  // gradient at every grad-tile entry (i,j) <-> pixel (x0-2+i, y0-2+j) clamped
   for (int t = threadIdx.x; t < CG_GW * CG_GW; t += CG_NT) {
-    int j = t / CG_GW, i = t - j * CG_GW;
-    int cx = min(max(x0 - 2 + i, 0), nx - 1), cy = min(max(y0 - 2 + j, 0), ny - 1);
-    // neighbours of the clamped pixel are themselves clamped: index the data tile by clamped coords
-    int xm = min(max(cx - 1, 0), nx - 1) - (x0 - 3), xp = min(max(cx + 1, 0), nx - 1) - (x0 - 3), xc = cx - (x0 - 3);
-    int ym = min(max(cy - 1, 0), ny - 1) - (y0 - 3), yp = min(max(cy + 1, 0), ny - 1) - (y0 - 3), yc = cy - (y0 - 3);
-#define DD(a, b) ((double)sd[(b) * CG_DW + (a)])
+    const int j = t / CG_GW, i = t - j * CG_GW;
+    // tile coordinates of the clamped pixel
+    const int xc = min(max(x0 - 2 + i, 0), nx - 1) - (x0 - 3), yc = min(max(y0 - 2 + j, 0), ny - 1) - (y0 - 3);
+    const float *d = sd + yc * CG_DW + xc;
+#define DD(dx, dy) ((double)d[(dy) * CG_DW + (dx)])
     double h, v;
-    if (accGrad) {
-      h = __dmul_rn(2.0, __dsub_rn(DD(xp, yc), DD(xm, yc)));
-      h = __dadd_rn(h, DD(xp, yp)); h = __dsub_rn(h, DD(xm, yp)); h = __dadd_rn(h, DD(xp, ym)); h = __dsub_rn(h, DD(xm, ym));
-      v = __dmul_rn(2.0, __dsub_rn(DD(xc, yp), DD(xc, ym)));
-      v = __dadd_rn(v, DD(xp, yp)); v = __dsub_rn(v, DD(xp, ym)); v = __dadd_rn(v, DD(xm, yp)); v = __dsub_rn(v, DD(xm, ym));
-    } else {
-      h = __dsub_rn(DD(xp, yc), DD(xm, yc));
-      v = __dsub_rn(DD(xc, yp), DD(xc, ym));
+    if (accGrad) {      // expression order of rcpp_canny.cpp:157-163
+      h = __dmul_rn(2.0, __dsub_rn(DD(1, 0), DD(-1, 0)));
+      h = __dadd_rn(h, DD(1, 1)); h = __dsub_rn(h, DD(-1, 1)); h = __dadd_rn(h, DD(1, -1)); h = __dsub_rn(h, DD(-1, -1));
+      v = __dmul_rn(2.0, __dsub_rn(DD(0, 1), DD(0, -1)));
+      v = __dadd_rn(v, DD(1, 1)); v = __dsub_rn(v, DD(1, -1)); v = __dadd_rn(v, DD(-1, 1)); v = __dsub_rn(v, DD(-1, -1));
+    } else {            // :167-169
+      h = __dsub_rn(DD(1, 0), DD(-1, 0));
+      v = __dsub_rn(DD(0, 1), DD(0, -1));
     }
+#undef DD
+    sh[t] = h; sv[t] = v;
     sg[t] = hypot_glibc(h, v);
   }
   __syncthreads();
+  const bool interior = x0 >= 2 && y0 >= 2 && x0 + CG_T + 2 <= nx && y0 + CG_T + 2 <= ny;
   for (int t = threadIdx.x; t < CG_T * CG_T; t += CG_NT) {
-    int ly = t / CG_T, lx = t - ly * CG_T;
-    int gx = x0 + lx, gy = y0 + ly;
+    const int ly = t / CG_T, lx = t - ly * CG_T;
+    const int gx = x0 + lx, gy = y0 + ly;
     if (gx >= nx || gy >= ny) continue;
-    const double now = sg[(ly + CG_GH) * CG_GW + lx + CG_GH];
+    const int ci = (ly + CG_GH) * CG_GW + lx + CG_GH;
+    const double now = sg[ci];
     unsigned char c = 0;
     if (!(now <= (double)low_thr)) {
-      // recompute h, v of this pixel (cheaper than keeping two more planes in shared memory)
-      int xm = min(max(gx - 1, 0), nx - 1) - (x0 - 3), xp = min(max(gx + 1, 0), nx - 1) - (x0 - 3), xc = gx - (x0 - 3);
-      int ym = min(max(gy - 1, 0), ny - 1) - (y0 - 3), yp = min(max(gy + 1, 0), ny - 1) - (y0 - 3), yc = gy - (y0 - 3);
-      double h, v;
-      if (accGrad) {
-        h = __dmul_rn(2.0, __dsub_rn(DD(xp, yc), DD(xm, yc)));
-        h = __dadd_rn(h, DD(xp, yp)); h = __dsub_rn(h, DD(xm, yp)); h = __dadd_rn(h, DD(xp, ym)); h = __dsub_rn(h, DD(xm, ym));
-        v = __dmul_rn(2.0, __dsub_rn(DD(xc, yp), DD(xc, ym)));
-        v = __dadd_rn(v, DD(xp, yp)); v = __dsub_rn(v, DD(xp, ym)); v = __dadd_rn(v, DD(xm, yp)); v = __dsub_rn(v, DD(xm, ym));
-      } else {
-        h = __dsub_rn(DD(xp, yc), DD(xm, yc));
-        v = __dsub_rn(DD(xc, yp), DD(xc, ym));
-      }
-#undef DD
-      // Direction cosines.  The reference takes cos/sin of atan2(v,h) (rcpp_canny.cpp:69-70,173); both
-      // are the unit vector (h,v)/|(h,v)| up to ~1 ulp of libm error, which no other libm reproduces
-      // either, so the cosines are formed directly (2 divisions instead of atan2+sincos).  Exact zeros
-      // of h or v keep the libm route: there cos(pi/2 rounded) = 6.1e-17 != 0 decides floor().
+      const double h = sh[ci], v = sv[ci];
+      // Direction cosines.  The reference takes cos/sin of atan2(v,h) (rcpp_canny.cpp:69-70,173): the
+      // unit vector (h,v)/|(h,v)| up to ~1 ulp of libm error that no other libm reproduces either, and
+      // the bilinear interpolation below is continuous in them, so they are formed directly.  Exact
+      // zeros of h or v keep the libm route: there cos(pi/2 rounded) = 6.1e-17 != 0 decides floor().
       double sn, cs;
       if (h == 0.0 || v == 0.0) {
         const double th = atan2(v, h);
         sincos(th, &sn, &cs);
       } else {
-        cs = __ddiv_rn(h, now);
-        sn = __ddiv_rn(v, now);
+        const double inv = __ddiv_rn(1.0, now);
+        cs = __dmul_rn(h, inv);
+        sn = __dmul_rn(v, inv);
       }
       double nb[2];
 #pragma unroll
       for (int s = 0; s < 2; s++) {                      // dir = -1 (prev), +1 (next): rcpp_canny.cpp:65-85
         const double dir = s ? 1.0 : -1.0;
-        double xt = __dmul_rn(dir, cs), yt = __dmul_rn(dir, sn);
-        double x1 = floor(xt), x2 = __dadd_rn(x1, 1.0), y1 = floor(yt), y2 = __dadd_rn(y1, 1.0);
-        // value(x + x1, ...): clamp in image coordinates, then index the grad tile
-        int ix1 = min(max(gx + (int)x1, 0), nx - 1) - (x0 - CG_GH), ix2 = min(max(gx + (int)x2, 0), nx - 1) - (x0 - CG_GH);
-        int iy1 = min(max(gy + (int)y1, 0), ny - 1) - (y0 - CG_GH), iy2 = min(max(gy + (int)y2, 0), ny - 1) - (y0 - CG_GH);
-        double wa = __dsub_rn(x2, xt), wb = __dsub_rn(xt, x1);
-        double g1 = __dadd_rn(__dmul_rn(wa, sg[iy1 * CG_GW + ix1]), __dmul_rn(wb, sg[iy1 * CG_GW + ix2]));
-        double g2 = __dadd_rn(__dmul_rn(wa, sg[iy2 * CG_GW + ix1]), __dmul_rn(wb, sg[iy2 * CG_GW + ix2]));
+        const double xt = __dmul_rn(dir, cs), yt = __dmul_rn(dir, sn);
+        const double x1 = floor(xt), x2 = __dadd_rn(x1, 1.0), y1 = floor(yt), y2 = __dadd_rn(y1, 1.0);
+        int ix1, ix2, iy1, iy2;
+        if (interior) {
+          ix1 = lx + CG_GH + (int)x1; ix2 = ix1 + 1; iy1 = ly + CG_GH + (int)y1; iy2 = iy1 + 1;
+        } else {      // value(x + x1, ...): clamp in image coordinates, then index the grad tile
+          ix1 = min(max(gx + (int)x1, 0), nx - 1) - (x0 - CG_GH); ix2 = min(max(gx + (int)x2, 0), nx - 1) - (x0 - CG_GH);
+          iy1 = min(max(gy + (int)y1, 0), ny - 1) - (y0 - CG_GH); iy2 = min(max(gy + (int)y2, 0), ny - 1) - (y0 - CG_GH);
+        }
+        const double wa = __dsub_rn(x2, xt), wb = __dsub_rn(xt, x1);
+        const double g1 = __dadd_rn(__dmul_rn(wa, sg[iy1 * CG_GW + ix1]), __dmul_rn(wb, sg[iy1 * CG_GW + ix2]));
+        const double g2 = __dadd_rn(__dmul_rn(wa, sg[iy2 * CG_GW + ix1]), __dmul_rn(wb, sg[iy2 * CG_GW + ix2]));
         nb[s] = __dadd_rn(__dmul_rn(__dsub_rn(y2, yt), g1), __dmul_rn(__dsub_rn(yt, y1), g2));
       }
       if (now <= nb[0] || now <= nb[1]) c = 0;
@@ -307,11 +324,11 @@ hyst_local_kernel(const unsigned char *__restrict__ cls, int *__restrict__ L, un
     __syncthreads();
     // hand the staged bytes to the row loop below through registers
 #pragma unroll
-    for (int k = 0; k < 4; k++) root_dummy[k] = sc[(warp + 8 * k) * HT + lane];
+    for (int k = 0; k < 4; k++) root_dummy[k] = sc[(4 * warp + k) * HT + lane];
   }
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    const int r = warp + 8 * k;
+    const int r = 4 * warp + k;
     const unsigned char c = (unsigned char)root_dummy[k];
     const unsigned bits = __ballot_sync(0xffffffffu, c != 0), sb = __ballot_sync(0xffffffffu, c == 2);
     if (lane == 0) { rowmask[r] = bits; strongmask[r] = sb; }
@@ -319,28 +336,33 @@ hyst_local_kernel(const unsigned char *__restrict__ cls, int *__restrict__ L, un
     cstrong[r * HT + lane] = 0;
   }
   __syncthreads();
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const int r = warp + 8 * k;
-    if (r == 0) continue;
-    const unsigned bits = rowmask[r], up = rowmask[r - 1];
-    if (!((bits >> lane) & 1u) || !up) continue;
-    const int st = run_start(bits, lane);
-    const bool isStart = st == lane, isEnd = lane == 31 || !((bits >> (lane + 1)) & 1u);
-    const bool N = (up >> lane) & 1u, NW = lane > 0 && ((up >> (lane - 1)) & 1u), NE = lane < 31 && ((up >> (lane + 1)) & 1u);
-    const int me = r * HT + st;
-    if (N) {
-      if (isStart || !NW) uf_union(lab, me, (r - 1) * HT + run_start(up, lane));
-    } else {
-      if (NW && isStart) uf_union(lab, me, (r - 1) * HT + run_start(up, lane - 1));
-      if (NE && isEnd) uf_union(lab, me, (r - 1) * HT + run_start(up, lane + 1));
+  // vertical links.  Pass 0: every warp links rows 4w+1..4w+3 of its own strip top-down (short
+  // chains, no contention between warps); pass 1: the 7 strip seams (row 4w against row 4w-1).
+  for (int pass = 0; pass < 2; pass++) {
+    for (int k = (pass ? 0 : 1); k < (pass ? 1 : 4); k++) {
+      const int r = 4 * warp + k;
+      if (r == 0) continue;
+      const unsigned bits = rowmask[r], up = rowmask[r - 1];
+      if (((bits >> lane) & 1u) && up) {
+        const int st = run_start(bits, lane);
+        const bool isStart = st == lane, isEnd = lane == 31 || !((bits >> (lane + 1)) & 1u);
+        const bool N = (up >> lane) & 1u, NW = lane > 0 && ((up >> (lane - 1)) & 1u), NE = lane < 31 && ((up >> (lane + 1)) & 1u);
+        const int me = r * HT + st;
+        if (N) {
+          if (isStart || !NW) uf_union(lab, me, (r - 1) * HT + run_start(up, lane));
+        } else {
+          if (NW && isStart) uf_union(lab, me, (r - 1) * HT + run_start(up, lane - 1));
+          if (NE && isEnd) uf_union(lab, me, (r - 1) * HT + run_start(up, lane + 1));
+        }
+      }
+      __syncwarp();
     }
+    __syncthreads();
   }
-  __syncthreads();
   int root[4];
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    const int r = warp + 8 * k, i = r * HT + lane;
+    const int r = 4 * warp + k, i = r * HT + lane;
     root[k] = -1;
     if ((rowmask[r] >> lane) & 1u) {
       root[k] = uf_find(lab, i);
@@ -350,7 +372,7 @@ hyst_local_kernel(const unsigned char *__restrict__ cls, int *__restrict__ L, un
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    const int r = warp + 8 * k, i = r * HT + lane, gy = y0 + r;
+    const int r = 4 * warp + k, i = r * HT + lane, gy = y0 + r;
     if (gx >= nx || gy >= ny) continue;
     const size_t p = base + (size_t)gy * nx + gx;
     if (root[k] < 0) { rinfo[p] = 0; continue; }
@@ -508,7 +530,7 @@ int canny_device(b2f_ctx *ctx, const unsigned char *d_frames, int n_frames, int 
   if (sym) {
     B2F_ARENA_CHECK(ctx);
     dim3 grid(ceil_div(nx, CB_TW), ceil_div(ny, CB_TH), n_frames);
-    size_t smem = sizeof(double) * (size_t)(CB_TH + 2 * ty.R) * CB_TW + (size_t)(CB_TH + 2 * ty.R) * ((CB_TW + 2 * tx.R + 3) & ~3);
+    size_t smem = sizeof(double) * ((size_t)(CB_TH + 2 * ty.R) * CB_TW + (size_t)(CB_TH + 2 * ty.R) * ((CB_TW + 2 * tx.R + 1) & ~1));
     if (tx.R == 13 && ty.R == 13) {
       static bool cfg = false;
       if (!cfg) { B2F_CUDA(cudaFuncSetAttribute(canny_blur_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = true; }

@@ -159,22 +159,39 @@ fhog_cell_kernel(const float *__restrict__ vmag, const unsigned char *__restrict
       const float wx = (__ldg(tb.c0 + x) == C) ? __ldg(tb.vx1 + x) : __ldg(tb.vx0 + x);
       wxs[k * FC_NT] = (x < g.simd_end) ? wx : -wx;
     }
+    // column offsets advance incrementally (no dependent table load); the loads of a chunk of 8
+    // pixels are issued together so the sequential adds do not wait on memory one by one
+    const int NCB = PW / g.cell;
+    const int ph0 = xa % g.cell, q0 = xa / g.cell;
     for (int y = ya; y < yb; y++) {
       const float wy = (__ldg(tb.r0 + y) == R) ? __ldg(tb.vy1 + y) : __ldg(tb.vy0 + y);
-      const size_t rowoff = (size_t)y * PW;
-      for (int x = xa; x < xb; x++) {
-        const int k = x - xa;
-        float wq;
-        if (k < KW) wq = wxs[k * FC_NT];
-        else { const float wx = (__ldg(tb.c0 + x) == C) ? __ldg(tb.vx1 + x) : __ldg(tb.vx0 + x); wq = (x < g.simd_end) ? wx : -wx; }
-        const size_t idx = rowoff + __ldg(colidx + x);
-        const float v = __ldg(vin + idx);
-        const int o = __ldg(oin + idx);
-        // simd body: vy*(vx*v) (fhog.h:867-874) ; scalar tail: (vy*vx)*v (fhog.h:951-954)
-        const bool tail = __float_as_int(wq) < 0;
-        const float wx = fabsf(wq);
-        const float val = tail ? __fmul_rn(__fmul_rn(wy, wx), v) : __fmul_rn(wy, __fmul_rn(wx, v));
-        h[o * FC_NT] = __fadd_rn(h[o * FC_NT], val);
+      const float *vrow = vin + (size_t)y * PW;
+      const unsigned char *orow = oin + (size_t)y * PW;
+      int ph = ph0, q = q0;
+      for (int xc = xa; xc < xb; xc += 8) {
+        float v[8]; int o[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const int idx = ph * NCB + q;
+          const bool in = xc + j < xb;
+          v[j] = in ? __ldg(vrow + idx) : 0.f;
+          o[j] = in ? (int)__ldg(orow + idx) : 0;
+          if (++ph == g.cell) { ph = 0; q++; }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const int x = xc + j;
+          if (x >= xb) break;
+          const int k = x - xa;
+          float wq;
+          if (k < KW) wq = wxs[k * FC_NT];
+          else { const float wx = (__ldg(tb.c0 + x) == C) ? __ldg(tb.vx1 + x) : __ldg(tb.vx0 + x); wq = (x < g.simd_end) ? wx : -wx; }
+          // simd body: vy*(vx*v) (fhog.h:867-874) ; scalar tail: (vy*vx)*v (fhog.h:951-954)
+          const bool tail = __float_as_int(wq) < 0;
+          const float wx = fabsf(wq);
+          const float val = tail ? __fmul_rn(__fmul_rn(wy, wx), v[j]) : __fmul_rn(wy, __fmul_rn(wx, v[j]));
+          h[o[j] * FC_NT] = __fadd_rn(h[o[j] * FC_NT], val);
+        }
       }
     }
     float *dst = hist + ((size_t)blockIdx.z * HR * HC + (size_t)R * HC + C) * 18;
