@@ -51,10 +51,36 @@ canny_blur_kernel(const unsigned char *__restrict__ frames, float *__restrict__ 
   const unsigned char *src = frames + (size_t)blockIdx.z * nx * ny;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // ---- load with wrap-around: a warp streams whole tile rows
-  for (int r = warp; r < TILE_H; r += CB_NT / 32) {
-    const unsigned char *row = src + (size_t)wrap_index(y0 - RY + r, ny) * nx;
-    for (int c = lane; c < TILE_W; c += 32)
-      tile[r * TP + c] = (double)__ldg(row + wrap_index(x0 - RX + c, nx));
+  //      (column offsets are per lane and hoisted; 6 rows are fetched per batch so that up to 18
+  //       independent byte loads are in flight per thread instead of one load-use chain per row)
+  {
+    constexpr int MAXC = 3;                               // covers TILE_W <= 96 (RX <= 32); wider tiles loop
+    int cofs[MAXC];
+#pragma unroll
+    for (int q = 0; q < MAXC; q++) cofs[q] = wrap_index(x0 - RX + lane + 32 * q, nx);
+    constexpr int RBATCH = 6;
+    for (int r0 = warp; r0 < TILE_H; r0 += (CB_NT / 32) * RBATCH) {
+      unsigned char b[RBATCH][MAXC];
+#pragma unroll
+      for (int k = 0; k < RBATCH; k++) {
+        const int r = r0 + (CB_NT / 32) * k;
+        const unsigned char *row = src + (size_t)wrap_index(y0 - RY + min(r, TILE_H - 1), ny) * nx;
+#pragma unroll
+        for (int q = 0; q < MAXC; q++) b[k][q] = (lane + 32 * q < TILE_W) ? __ldg(row + cofs[q]) : (unsigned char)0;
+      }
+#pragma unroll
+      for (int k = 0; k < RBATCH; k++) {
+        const int r = r0 + (CB_NT / 32) * k;
+        if (r < TILE_H) {
+#pragma unroll
+          for (int q = 0; q < MAXC; q++) if (lane + 32 * q < TILE_W) tile[r * TP + lane + 32 * q] = (double)b[k][q];
+        }
+      }
+    }
+    for (int r = warp; r < TILE_H; r += CB_NT / 32) {     // columns beyond 96 (very large s only)
+      const unsigned char *row = src + (size_t)wrap_index(y0 - RY + r, ny) * nx;
+      for (int c = lane + 32 * MAXC; c < TILE_W; c += 32) tile[r * TP + c] = (double)__ldg(row + wrap_index(x0 - RX + c, nx));
+    }
   }
   __syncthreads();
   // ---- row pass: rowbuf[r][c] = w0*v0 + sum_k wk*(v[-k]+v[+k]); 4 outputs per thread when RT>0
@@ -121,29 +147,40 @@ canny_blur_kernel(const unsigned char *__restrict__ frames, float *__restrict__ 
   }
 }
 
-// generic tap lists (tiny images where the wrapped kernel is not symmetric): one thread per pixel,
-// taps applied in ascending coordinate order — the order the oracle uses for that case.
-struct TapList { const int *coord; const double *weight; int n; };
+// Un-tiled fallback (tiny images whose wrapped kernel is not symmetric, or radii too large for the
+// tile): one thread per pixel.  sym != 0: centre tap then symmetric pairs (the order of the tiled
+// kernel and of the oracle); sym == 0: taps in ascending coordinate order (the oracle's order then).
+struct TapList { const int *coord; const double *weight; int n; int sym; };
 __global__ void canny_blur_generic_rows(const unsigned char *__restrict__ frames, double *__restrict__ tmp, int nx, int ny,
                                         TapList t) {
   int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x >= nx) return;
   const unsigned char *src = frames + (size_t)blockIdx.z * nx * ny + (size_t)y * nx;
-  double acc = 0;
-  for (int i = 0; i < t.n; i++) {
-    int q = (x - t.coord[i]) % nx; if (q < 0) q += nx;
-    acc = __dadd_rn(acc, __dmul_rn(t.weight[i], (double)src[q]));
+  double acc;
+  if (t.sym) {
+    const int R = t.n / 2;
+    acc = __dmul_rn(t.weight[R], (double)src[x]);
+    for (int k = 1; k <= R; k++)
+      acc = __dadd_rn(acc, __dmul_rn(t.weight[R + k], __dadd_rn((double)src[wrap_index(x - k, nx)], (double)src[wrap_index(x + k, nx)])));
+  } else {
+    acc = 0;
+    for (int i = 0; i < t.n; i++) acc = __dadd_rn(acc, __dmul_rn(t.weight[i], (double)src[wrap_index(x - t.coord[i], nx)]));
   }
   tmp[(size_t)blockIdx.z * nx * ny + (size_t)y * nx + x] = acc;
 }
 __global__ void canny_blur_generic_cols(const double *__restrict__ tmp, float *__restrict__ out, int nx, int ny, TapList t) {
   int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x >= nx) return;
-  const double *src = tmp + (size_t)blockIdx.z * nx * ny;
-  double acc = 0;
-  for (int i = 0; i < t.n; i++) {
-    int q = (y - t.coord[i]) % ny; if (q < 0) q += ny;
-    acc = __dadd_rn(acc, __dmul_rn(t.weight[i], src[(size_t)q * nx + x]));
+  const double *src = tmp + (size_t)blockIdx.z * nx * ny + x;
+  double acc;
+  if (t.sym) {
+    const int R = t.n / 2;
+    acc = __dmul_rn(t.weight[R], src[(size_t)y * nx]);
+    for (int k = 1; k <= R; k++)
+      acc = __dadd_rn(acc, __dmul_rn(t.weight[R + k], __dadd_rn(src[(size_t)wrap_index(y - k, ny) * nx], src[(size_t)wrap_index(y + k, ny) * nx])));
+  } else {
+    acc = 0;
+    for (int i = 0; i < t.n; i++) acc = __dadd_rn(acc, __dmul_rn(t.weight[i], src[(size_t)wrap_index(y - t.coord[i], ny) * nx]));
   }
   out[(size_t)blockIdx.z * nx * ny + (size_t)y * nx + x] = __double2float_rn(acc);
 }
@@ -526,17 +563,17 @@ int canny_device(b2f_ctx *ctx, const unsigned char *d_frames, int n_frames, int 
   std::vector<int> cx, cy; std::vector<double> wx, wy;
   make_taps(nx, s, cx, wx); make_taps(ny, s, cy, wy);
   CannyTaps tx, ty;
-  bool sym = symmetric_taps(cx, wx, tx) && symmetric_taps(cy, wy, ty);
-  if (sym) {
+  const bool sym = symmetric_taps(cx, wx, tx) && symmetric_taps(cy, wy, ty);   // same rule as the oracle (R <= 64)
+  size_t smem = 0;
+  if (sym) smem = sizeof(double) * ((size_t)(CB_TH + 2 * ty.R) * CB_TW + (size_t)(CB_TH + 2 * ty.R) * ((CB_TW + 2 * tx.R + 1) & ~1));
+  if (sym && smem <= 200 * 1024) {
     B2F_ARENA_CHECK(ctx);
     dim3 grid(ceil_div(nx, CB_TW), ceil_div(ny, CB_TH), n_frames);
-    size_t smem = sizeof(double) * ((size_t)(CB_TH + 2 * ty.R) * CB_TW + (size_t)(CB_TH + 2 * ty.R) * ((CB_TW + 2 * tx.R + 1) & ~1));
     if (tx.R == 13 && ty.R == 13) {
       static bool cfg = false;
       if (!cfg) { B2F_CUDA(cudaFuncSetAttribute(canny_blur_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = true; }
       canny_blur_kernel<13><<<grid, CB_NT, smem, st>>>(d_frames, blur, nx, ny, tx, ty);
     } else {
-      if (smem > 200 * 1024) { set_error("canny: s=%g needs %zu bytes of shared memory", s, smem); return B2F_EUNSUP; }
       B2F_CUDA(cudaFuncSetAttribute(canny_blur_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       canny_blur_kernel<0><<<grid, CB_NT, smem, st>>>(d_frames, blur, nx, ny, tx, ty);
     }
@@ -552,9 +589,9 @@ int canny_device(b2f_ctx *ctx, const unsigned char *d_frames, int n_frames, int 
     B2F_CUDA(cudaMemcpyAsync(dwx + wx.size(), wy.data(), wy.size() * 8, cudaMemcpyHostToDevice, st));
     B2F_CUDA(cudaStreamSynchronize(st));   // host vectors go out of scope below
     dim3 grid(ceil_div(nx, 128), ny, n_frames);
-    canny_blur_generic_rows<<<grid, 128, 0, st>>>(d_frames, tmp, nx, ny, TapList{dcx, dwx, (int)cx.size()});
+    canny_blur_generic_rows<<<grid, 128, 0, st>>>(d_frames, tmp, nx, ny, TapList{dcx, dwx, (int)cx.size(), sym ? 1 : 0});
     B2F_LAUNCH_CHECK(ctx);
-    canny_blur_generic_cols<<<grid, 128, 0, st>>>(tmp, blur, nx, ny, TapList{dcx + cx.size(), dwx + wx.size(), (int)cy.size()});
+    canny_blur_generic_cols<<<grid, 128, 0, st>>>(tmp, blur, nx, ny, TapList{dcx + cx.size(), dwx + wx.size(), (int)cy.size(), sym ? 1 : 0});
     B2F_LAUNCH_CHECK(ctx);
   }
   canny_grad_nms_kernel<<<dim3(ceil_div(nx, CG_T), ceil_div(ny, CG_T), n_frames), CG_NT, 0, st>>>(

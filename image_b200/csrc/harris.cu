@@ -5,7 +5,7 @@
 //   NMS             nms_bitmask_kernel: window predicate of harris.cpp:141-255 -> 1 bit / pixel
 //   compaction      row_count / row_scan / emit kernels -> corners in raster order (harris.cpp:250-252)
 //   selection, sub-pixel, scale check (H7, <1 % of the time): host code in harris_host.cpp
-#include "harris_kernels.cuh"
+#include "harris_kernels2.cuh"
 #include "harris_host.h"
 #include <cmath>
 #include <algorithm>
@@ -272,14 +272,25 @@ template <int RD, int RI, bool U8, int GRAD>
 static int launch_fused_t(b2f_ctx *ctx, const void *d_frames, int n_frames, int nx, int ny, float *d_R,
                           const HarrisConsts &kc, cudaStream_t st) {
   using C = FusedCfg<RD, RI>;
+  using C2 = Fused2Cfg<RD, RI>;
   auto kern = harris_fused_kernel<RD, RI, U8, GRAD>;
+  auto kern2 = harris_fused2_kernel<RD, RI, U8, GRAD>;
   static bool configured = false;   // per instantiation
   if (!configured) {
     B2F_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    B2F_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2::SMEM));
     configured = true;
   }
+  static const bool force_v1 = getenv("B2F_HARRIS_V1") != nullptr;
   dim3 grid(ceil_div(nx, C::TW), ceil_div(ny, C::TH), n_frames);
-  kern<<<grid, C::NT, C::SMEM, st>>>(d_frames, d_R, nx, ny, kc);
+  // the packed kernel needs 4-pixel aligned rows; it takes the interior tiles, v1 the border ring
+  const bool v2 = !force_v1 && (nx % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_frames) & 15) == 0) &&
+                  ((reinterpret_cast<uintptr_t>(d_R) & 7) == 0) && nx >= 64 + 24 && ny >= 64 + 24;
+  if (v2) {
+    kern2<<<grid, C2::NT, C2::SMEM, st>>>(d_frames, d_R, nx, ny, kc);
+    B2F_LAUNCH_CHECK(ctx);
+  }
+  kern<<<grid, C::NT, C::SMEM, st>>>(d_frames, d_R, nx, ny, kc, v2 ? 1 : 0);
   B2F_LAUNCH_CHECK(ctx);
   return B2F_OK;
 }

@@ -78,11 +78,17 @@ __device__ __forceinline__ int reflect_index(int p, int n) {
   return min(max(p, 0), n - 1);
 }
 
+// tiles whose +-12 halo lies inside the frame are taken by harris_fused2_kernel (harris_kernels2.cuh)
+__device__ __forceinline__ bool harris_tile_is_interior(int x0, int y0, int nx, int ny) {
+  return x0 >= 12 && y0 >= 12 && x0 + 64 + 12 <= nx && y0 + 64 + 12 <= ny;
+}
+
 template <int RD, int RI, bool U8, int GRAD>
 __global__ void __launch_bounds__(256, 2)
 harris_fused_kernel(const void *__restrict__ frames, float *__restrict__ Rout, int nx, int ny,
-                    const __grid_constant__ HarrisConsts kc) {
+                    const __grid_constant__ HarrisConsts kc, int border_ring_only) {
   using C = FusedCfg<RD, RI>;
+  if (border_ring_only && harris_tile_is_interior(blockIdx.x * C::TW, blockIdx.y * C::TH, nx, ny)) return;
   extern __shared__ __align__(16) float smem[];
   float *sIN = smem;                    // region X (input tile, later Is)
   float *sIS = smem;
