@@ -7,9 +7,9 @@
 // aligned 8-byte word:
 //     row pass    (taps along x): partner = the pixel one ROW below  -> tile stored row-pair interleaved
 //     column pass (taps along y): partner = the pixel one COLUMN right -> tile stored plain row-major
-//   stage A  u8/f32 tile (+12 halo) -> sINp   [44][88] float2 (rows 2k,2k+1 interleaved)
-//   stage B  row blur sigma_d        -> sR1    [88][80] float  (plain)
-//   stage C  column blur sigma_d     -> sISp   [41][80] float2 (row-pair interleaved), aliases sINp
+//   stage A  u8/f32 tile (+12 halo) -> sINp   [44][88(+2)] float2 (rows 2k,2k+1 interleaved)
+//   stage B  row blur sigma_d        -> sR1    [88][80(+2)] float  (plain)
+//   stage C  column blur sigma_d     -> sISp   [41][80(+2)] float2 (row-pair interleaved), aliases sINp
 //   stage D  gradient, products, row blur sigma_i, streamed position by position (each product is
 //            scattered into the <= 4 outputs it contributes to; nothing but accumulators stays live)
 //                                    -> sAR    [3][78][64] float (plain), aliases sR1
@@ -31,11 +31,20 @@ template <int RD, int RI> struct Fused2Cfg {
   static constexpr int G = RI + 1;                              // halo of Is needed by the products (8)
   static constexpr int R1_W = TW + 2 * G;                       // 80 : global x0-G .. x0+TW+G-1
   static constexpr int R1_H = IN_H;                             // 88 : same rows as IN
-  static constexpr int IS_H = TH + 2 * G + 2;                   // 82 : global y0-G-1 .. (one extra row on top and bottom keeps row pairs aligned)
+  static constexpr int IS_H = TH + 2 * G;                       // 80 : global y0-G .. ; AR row a <-> Is row a+1, so an AR row pair straddles two Is pair lines
   static constexpr int IS_W = R1_W;
   static constexpr int AR_H = TH + 2 * RI;                      // 78 : global y0-RI ..
-  static constexpr int REGION_X = (IN_H * IN_W > IS_H * IS_W) ? IN_H * IN_W : IS_H * IS_W;   // floats
-  static constexpr int REGION_Y = (R1_H * R1_W > 3 * AR_H * TW) ? R1_H * R1_W : 3 * AR_H * TW;
+  // Pitches.  Whenever consecutive threads walk consecutive ROWS (row passes B and D: 16-byte loads of
+  // float2 pairs, 16-byte stores of 4 outputs) the row stride must be an odd multiple of 16 bytes
+  // modulo 128 so that a quarter warp covers all 32 banks: pitch % 4 == 2 for float2 rows, and for the
+  // plain float tiles written two rows at a time.
+  static constexpr int IN_P = IN_W + 2;                         // 90 float2
+  static constexpr int IS_P = IS_W + 2;                         // 82 float2
+  static constexpr int R1_P = R1_W + 2;                         // 82 float
+  static constexpr int AR_P = TW + 2;                           // 66 float
+  static_assert(IN_P % 4 == 2 && IS_P % 4 == 2 && R1_P % 4 == 2 && AR_P % 4 == 2, "bank-conflict-free pitches");
+  static constexpr int REGION_X = (IN_H * IN_P > IS_H * IS_P) ? IN_H * IN_P : IS_H * IS_P;   // floats
+  static constexpr int REGION_Y = (R1_H * R1_P > 3 * AR_H * AR_P) ? R1_H * R1_P : 3 * AR_H * AR_P;
   static constexpr size_t SMEM = sizeof(float) * (REGION_X + REGION_Y);
   static_assert(RD + 1 + RI + 1 <= HALO, "halo too small");
   static_assert(HALO - G - RD >= 0, "row-blur taps must stay inside the input tile");
@@ -82,7 +91,7 @@ harris_fused2_kernel(const void *__restrict__ frames, float *__restrict__ Rout, 
         const int it = tid + k * C::NT;
         if (it < ITEMS) {
           const int rp = it / VW, v = it - rp * VW;
-          float4 *d = reinterpret_cast<float4 *>(sINp + rp * C::IN_W + 4 * v);
+          float4 *d = reinterpret_cast<float4 *>(sINp + rp * C::IN_P + 4 * v);
           d[0] = make_float4((float)(a[k] & 0xff), (float)(b[k] & 0xff), (float)((a[k] >> 8) & 0xff), (float)((b[k] >> 8) & 0xff));
           d[1] = make_float4((float)((a[k] >> 16) & 0xff), (float)((b[k] >> 16) & 0xff), (float)(a[k] >> 24), (float)(b[k] >> 24));
         }
@@ -103,7 +112,7 @@ harris_fused2_kernel(const void *__restrict__ frames, float *__restrict__ Rout, 
         const int it = tid + k * C::NT;
         if (it < ITEMS) {
           const int rp = it / VW, v = it - rp * VW;
-          float4 *d = reinterpret_cast<float4 *>(sINp + rp * C::IN_W + 4 * v);
+          float4 *d = reinterpret_cast<float4 *>(sINp + rp * C::IN_P + 4 * v);
           d[0] = make_float4(a[k].x, b[k].x, a[k].y, b[k].y);
           d[1] = make_float4(a[k].z, b[k].z, a[k].w, b[k].w);
         }
@@ -118,9 +127,10 @@ harris_fused2_kernel(const void *__restrict__ frames, float *__restrict__ Rout, 
     constexpr int OFF = C::HALO - C::G - RD;                   // first tap of R1 col 0 sits at IN col OFF (=1)
     constexpr int NP = 4 + 2 * RD + OFF;                       // positions loaded from the 4-aligned start (11) -> round up even
     constexpr int NL = (NP + 1) / 2 * 2;                       // 12
-    for (int it = tid; it < (C::R1_H / 2) * GROUPS; it += C::NT) {
-      const int rp = it / GROUPS, g = it - rp * GROUPS;
-      const float2 *p = sINp + rp * C::IN_W + 4 * g;
+    constexpr int RPS = C::R1_H / 2;                           // 44 row pairs; consecutive threads = consecutive row pairs
+    for (int it = tid; it < RPS * GROUPS; it += C::NT) {
+      const int g = it / RPS, rp = it - g * RPS;
+      const float2 *p = sINp + rp * C::IN_P + 4 * g;
       float2 v[NL];
 #pragma unroll
       for (int q = 0; q < NL / 2; q++) {
@@ -136,9 +146,10 @@ harris_fused2_kernel(const void *__restrict__ frames, float *__restrict__ Rout, 
         for (int t = 1; t <= RD; t++) acc = __ffma2_rn(f2s(kc.wd[t]), __fadd2_rn(v[c - t], v[c + t]), acc);
         o[j] = acc;
       }
-      float *d = sR1 + (2 * rp) * C::R1_W + 4 * g;
+      float *d = sR1 + (2 * rp) * C::R1_P + 4 * g;
       *reinterpret_cast<float4 *>(d) = make_float4(o[0].x, o[1].x, o[2].x, o[3].x);
-      *reinterpret_cast<float4 *>(d + C::R1_W) = make_float4(o[0].y, o[1].y, o[2].y, o[3].y);
+      *reinterpret_cast<float2 *>(d + C::R1_P) = make_float2(o[0].y, o[1].y);      // odd rows are only 8-byte aligned
+      *reinterpret_cast<float2 *>(d + C::R1_P + 2) = make_float2(o[2].y, o[3].y);
     }
   }
   __syncthreads();
@@ -146,20 +157,20 @@ harris_fused2_kernel(const void *__restrict__ frames, float *__restrict__ Rout, 
   // ---- stage C: column blur sigma_d, packed over column pairs -> sISp (row-pair interleaved) --
   {
     constexpr int CP = C::IS_W / 2;                            // 40 column pairs
-    constexpr int RB = 12;                                     // Is rows per item (6 row pairs)
-    constexpr int RGS = (C::IS_H + RB - 1) / RB;               // 7
-    constexpr int OFFR = C::HALO - C::G - 1 - RD;              // Is row 0 (global y0-G-1) uses R1 rows OFFR .. OFFR+2RD (=0)
+    constexpr int RB = 10;                                     // Is rows per item (5 row pairs)
+    constexpr int RGS = (C::IS_H + RB - 1) / RB;               // 8
+    constexpr int OFFR = C::HALO - C::G - RD;                  // Is row 0 (global y0-G) uses R1 rows OFFR .. OFFR+2RD (=1)
     static_assert(OFFR >= 0, "R1 must cover the taps of Is row 0");
     for (int it = tid; it < CP * RGS; it += C::NT) {
       const int rg = it / CP, cp = it - rg * CP;
-      const float *p = sR1 + (rg * RB + OFFR) * C::R1_W + 2 * cp;
+      const float *p = sR1 + (rg * RB + OFFR) * C::R1_P + 2 * cp;
       float2 acc[RB];
 #pragma unroll
       for (int j = 0; j < RB; j++) acc[j] = f2s(0.f);
 #pragma unroll
       for (int q = 0; q < RB + 2 * RD; q++) {
         const int row = min(rg * RB + OFFR + q, C::R1_H - 1) - (rg * RB + OFFR);      // clamp (last group overruns)
-        const float2 v = *reinterpret_cast<const float2 *>(p + row * C::R1_W);
+        const float2 v = *reinterpret_cast<const float2 *>(p + row * C::R1_P);
 #pragma unroll
         for (int j = 0; j < RB; j++) {
           const int t = q - j - RD;
@@ -170,71 +181,124 @@ harris_fused2_kernel(const void *__restrict__ frames, float *__restrict__ Rout, 
       for (int j = 0; j < RB; j += 2) {
         const int i = rg * RB + j;                             // Is row (even)
         if (i < C::IS_H)
-          *reinterpret_cast<float4 *>(sISp + (i >> 1) * C::IS_W + 2 * cp) = make_float4(acc[j].x, acc[j + 1].x, acc[j].y, acc[j + 1].y);
+          *reinterpret_cast<float4 *>(sISp + (i >> 1) * C::IS_P + 2 * cp) = make_float4(acc[j].x, acc[j + 1].x, acc[j].y, acc[j + 1].y);
       }
     }
   }
   __syncthreads();
 
   // ---- stage D: gradient + products + row blur sigma_i, streamed -> sAR (plain) ---------------
+  // One item = 4 AR rows x 4 output columns.  AR rows (4k .. 4k+3) <-> Is rows (4k+1 .. 4k+4); with Is
+  // rows paired (even, odd) the three pair lines P0=(4k,4k+1), P1=(4k+2,4k+3), P2=(4k+4,4k+5) hold
+  // everything: for the row pair (4k+1, 4k+2)   gy = (Is[4k+2]-Is[4k], Is[4k+3]-Is[4k+1]) = P1 - P0 (packed),
+  //                                              gx from P0.y and P1.x;
+  //             for the row pair (4k+3, 4k+4)   gy = P2 - P1,  gx from P1.y and P2.x.
   {
     constexpr int GROUPS = C::TW / 4;                          // 16
     constexpr int NPOS = 4 + 2 * RI;                           // 18 product positions per item
     constexpr int NL = (NPOS + 2 + 1) / 2 * 2;                 // 20 Is columns loaded per line
+    constexpr int QS = (C::AR_H + 3) / 4;                      // 20 row quads (the last one is half empty)
+    constexpr int PL = C::AR_H * C::AR_P;                      // plane stride (multiple of 4 floats)
+    static_assert(PL % 4 == 0, "plane stride keeps 16-byte alignment");
     float2 w2[RI + 1];
 #pragma unroll
     for (int t = 0; t <= RI; t++) w2[t] = f2s(kc.wir[t]);
-    for (int it = tid; it < (C::AR_H / 2) * GROUPS; it += C::NT) {
-      const int ap = it / GROUPS, g = it - ap * GROUPS;
-      // AR rows (2ap, 2ap+1) <-> Is rows (2ap+2, 2ap+3) = pair line ap+1; product col q <-> Is col 4g+1+q
-      const float2 *l1 = sISp + (ap + 1) * C::IS_W + 4 * g;
-      const float2 *l0 = l1 - C::IS_W, *l2 = l1 + C::IS_W;
-      float2 m[NL];
-      float up[NL], dn[NL];                                    // Is[2ap+1] (l0.y) and Is[2ap+4] (l2.x)
+    for (int it = tid; it < QS * GROUPS; it += C::NT) {
+      const int g = it / QS, k = it - g * QS;                  // consecutive threads = consecutive row quads
+      const float2 *l0 = sISp + (2 * k) * C::IS_P + 4 * g;     // pair line 2k   = Is rows 4k, 4k+1
+      const float2 *l1 = l0 + C::IS_P;                         // pair line 2k+1 = Is rows 4k+2, 4k+3
+      const float2 *l2 = sISp + min(2 * k + 2, C::IS_H / 2 - 1) * C::IS_P + 4 * g;   // rows 4k+4, 4k+5 (clamped for the half-empty last quad)
+      float2 a0[4], b0[4], c0[4], a1[4], b1[4], c1[4];
 #pragma unroll
-      for (int q = 0; q < NL / 2; q++) {
-        float4 t = *reinterpret_cast<const float4 *>(l1 + 2 * q);
-        m[2 * q] = f2(t.x, t.y); m[2 * q + 1] = f2(t.z, t.w);
-        float4 a = *reinterpret_cast<const float4 *>(l0 + 2 * q);
-        float4 b = *reinterpret_cast<const float4 *>(l2 + 2 * q);
-        up[2 * q] = a.y; up[2 * q + 1] = a.w;
-        dn[2 * q] = b.x; dn[2 * q + 1] = b.z;
+      for (int j = 0; j < 4; j++) { a0[j] = b0[j] = c0[j] = a1[j] = b1[j] = c1[j] = f2s(0.f); }
+      float2 p0[3], p1[3], p2[3];                              // sliding window of Is columns q, q+1, q+2
+      {
+        float4 t0 = *reinterpret_cast<const float4 *>(l0), t1 = *reinterpret_cast<const float4 *>(l1), t2 = *reinterpret_cast<const float4 *>(l2);
+        p0[0] = f2(t0.x, t0.y); p0[1] = f2(t0.z, t0.w); p1[0] = f2(t1.x, t1.y); p1[1] = f2(t1.z, t1.w); p2[0] = f2(t2.x, t2.y); p2[1] = f2(t2.z, t2.w);
       }
-      float2 aa[4], ab[4], ac[4];
-#pragma unroll
-      for (int j = 0; j < 4; j++) { aa[j] = f2s(0.f); ab[j] = f2s(0.f); ac[j] = f2s(0.f); }
 #pragma unroll
       for (int q = 0; q < NPOS; q++) {
-        float2 gx, gy;
-        if (GRAD == 0) {                                       // central differences; the 0.5 factors live in kc.wir
-          gx = sub2(m[q + 2], m[q]);
-          gy = f2(m[q + 1].y - up[q + 1], dn[q + 1] - m[q + 1].x);
-        } else {                                               // Sobel/8 (gradient.cpp:77-82)
-          // rows: r0 = 2ap+2 (u = up, c = m.x, d = m.y), r1 = 2ap+3 (u = m.x, c = m.y, d = dn)
-          const float gx0 = fmaf(0.25f, m[q + 2].x - m[q].x, 0.125f * (up[q + 2] + m[q + 2].y - up[q] - m[q].y));
-          const float gx1 = fmaf(0.25f, m[q + 2].y - m[q].y, 0.125f * (m[q + 2].x + dn[q + 2] - m[q].x - dn[q]));
-          const float gy0 = fmaf(0.25f, m[q + 1].y - up[q + 1], 0.125f * (m[q + 2].y + m[q].y - up[q + 2] - up[q]));
-          const float gy1 = fmaf(0.25f, dn[q + 1] - m[q + 1].x, 0.125f * (dn[q + 2] + dn[q] - m[q + 2].x - m[q].x));
-          gx = f2(gx0, gx1); gy = f2(gy0, gy1);
-        }
-        const float2 pa = __fmul2_rn(gx, gx), pb = __fmul2_rn(gx, gy), pc = __fmul2_rn(gy, gy);
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int t = q - j - RI;
-          if (t >= -RI && t <= RI) {
-            const float2 w = w2[t < 0 ? -t : t];
-            aa[j] = __ffma2_rn(w, pa, aa[j]); ab[j] = __ffma2_rn(w, pb, ab[j]); ac[j] = __ffma2_rn(w, pc, ac[j]);
+        // bring in column q+2 (pairs of columns are fetched as one 16-byte load on even q)
+        if ((q & 1) == 0) {
+          float4 t0 = *reinterpret_cast<const float4 *>(l0 + q + 2), t1 = *reinterpret_cast<const float4 *>(l1 + q + 2), t2 = *reinterpret_cast<const float4 *>(l2 + q + 2);
+          p0[2] = f2(t0.x, t0.y); p1[2] = f2(t1.x, t1.y); p2[2] = f2(t2.x, t2.y);
+          // stash column q+3 in slot 0 AFTER it has been consumed below: keep it in temporaries
+          float2 n0 = f2(t0.z, t0.w), n1 = f2(t1.z, t1.w), n2 = f2(t2.z, t2.w);
+          // ---- products at column q+1 for both row pairs
+          float2 gxA, gyA, gxB, gyB;
+          if (GRAD == 0) {
+            gyA = sub2(p1[1], p0[1]);                                            // rows 4k+1, 4k+2
+            gxA = f2(p0[2].y - p0[0].y, p1[2].x - p1[0].x);
+            gyB = sub2(p2[1], p1[1]);                                            // rows 4k+3, 4k+4
+            gxB = f2(p1[2].y - p1[0].y, p2[2].x - p2[0].x);
+          } else {
+            gxA = f2(fmaf(0.25f, p0[2].y - p0[0].y, 0.125f * (p0[2].x + p1[2].x - p0[0].x - p1[0].x)),
+                     fmaf(0.25f, p1[2].x - p1[0].x, 0.125f * (p0[2].y + p1[2].y - p0[0].y - p1[0].y)));
+            gyA = f2(fmaf(0.25f, p1[1].x - p0[1].x, 0.125f * (p1[2].x + p1[0].x - p0[2].x - p0[0].x)),
+                     fmaf(0.25f, p1[1].y - p0[1].y, 0.125f * (p1[2].y + p1[0].y - p0[2].y - p0[0].y)));
+            gxB = f2(fmaf(0.25f, p1[2].y - p1[0].y, 0.125f * (p1[2].x + p2[2].x - p1[0].x - p2[0].x)),
+                     fmaf(0.25f, p2[2].x - p2[0].x, 0.125f * (p1[2].y + p2[2].y - p1[0].y - p2[0].y)));
+            gyB = f2(fmaf(0.25f, p2[1].x - p1[1].x, 0.125f * (p2[2].x + p2[0].x - p1[2].x - p1[0].x)),
+                     fmaf(0.25f, p2[1].y - p1[1].y, 0.125f * (p2[2].y + p2[0].y - p1[2].y - p1[0].y)));
           }
+          {
+            const float2 pa = __fmul2_rn(gxA, gxA), pb = __fmul2_rn(gxA, gyA), pc = __fmul2_rn(gyA, gyA);
+            const float2 qa = __fmul2_rn(gxB, gxB), qb = __fmul2_rn(gxB, gyB), qc = __fmul2_rn(gyB, gyB);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              const int t = q - j - RI;
+              if (t >= -RI && t <= RI) {
+                const float2 w = w2[t < 0 ? -t : t];
+                a0[j] = __ffma2_rn(w, pa, a0[j]); b0[j] = __ffma2_rn(w, pb, b0[j]); c0[j] = __ffma2_rn(w, pc, c0[j]);
+                a1[j] = __ffma2_rn(w, qa, a1[j]); b1[j] = __ffma2_rn(w, qb, b1[j]); c1[j] = __ffma2_rn(w, qc, c1[j]);
+              }
+            }
+          }
+          // slide: (q, q+1, q+2) -> (q+1, q+2, q+3)
+          p0[0] = p0[1]; p0[1] = p0[2]; p0[2] = n0; p1[0] = p1[1]; p1[1] = p1[2]; p1[2] = n1; p2[0] = p2[1]; p2[1] = p2[2]; p2[2] = n2;
+        } else {
+          float2 gxA, gyA, gxB, gyB;
+          if (GRAD == 0) {
+            gyA = sub2(p1[1], p0[1]);
+            gxA = f2(p0[2].y - p0[0].y, p1[2].x - p1[0].x);
+            gyB = sub2(p2[1], p1[1]);
+            gxB = f2(p1[2].y - p1[0].y, p2[2].x - p2[0].x);
+          } else {
+            gxA = f2(fmaf(0.25f, p0[2].y - p0[0].y, 0.125f * (p0[2].x + p1[2].x - p0[0].x - p1[0].x)),
+                     fmaf(0.25f, p1[2].x - p1[0].x, 0.125f * (p0[2].y + p1[2].y - p0[0].y - p1[0].y)));
+            gyA = f2(fmaf(0.25f, p1[1].x - p0[1].x, 0.125f * (p1[2].x + p1[0].x - p0[2].x - p0[0].x)),
+                     fmaf(0.25f, p1[1].y - p0[1].y, 0.125f * (p1[2].y + p1[0].y - p0[2].y - p0[0].y)));
+            gxB = f2(fmaf(0.25f, p1[2].y - p1[0].y, 0.125f * (p1[2].x + p2[2].x - p1[0].x - p2[0].x)),
+                     fmaf(0.25f, p2[2].x - p2[0].x, 0.125f * (p1[2].y + p2[2].y - p1[0].y - p2[0].y)));
+            gyB = f2(fmaf(0.25f, p2[1].x - p1[1].x, 0.125f * (p2[2].x + p2[0].x - p1[2].x - p1[0].x)),
+                     fmaf(0.25f, p2[1].y - p1[1].y, 0.125f * (p2[2].y + p2[0].y - p1[2].y - p1[0].y)));
+          }
+          const float2 pa = __fmul2_rn(gxA, gxA), pb = __fmul2_rn(gxA, gyA), pc = __fmul2_rn(gyA, gyA);
+          const float2 qa = __fmul2_rn(gxB, gxB), qb = __fmul2_rn(gxB, gyB), qc = __fmul2_rn(gyB, gyB);
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const int t = q - j - RI;
+            if (t >= -RI && t <= RI) {
+              const float2 w = w2[t < 0 ? -t : t];
+              a0[j] = __ffma2_rn(w, pa, a0[j]); b0[j] = __ffma2_rn(w, pb, b0[j]); c0[j] = __ffma2_rn(w, pc, c0[j]);
+              a1[j] = __ffma2_rn(w, qa, a1[j]); b1[j] = __ffma2_rn(w, qb, b1[j]); c1[j] = __ffma2_rn(w, qc, c1[j]);
+            }
+          }
+          p0[0] = p0[1]; p0[1] = p0[2]; p1[0] = p1[1]; p1[1] = p1[2]; p2[0] = p2[1]; p2[1] = p2[2];
         }
       }
-      float *o = sAR + (2 * ap) * C::TW + 4 * g;
-      constexpr int PL = C::AR_H * C::TW;
-      *reinterpret_cast<float4 *>(o) = make_float4(aa[0].x, aa[1].x, aa[2].x, aa[3].x);
-      *reinterpret_cast<float4 *>(o + C::TW) = make_float4(aa[0].y, aa[1].y, aa[2].y, aa[3].y);
-      *reinterpret_cast<float4 *>(o + PL) = make_float4(ab[0].x, ab[1].x, ab[2].x, ab[3].x);
-      *reinterpret_cast<float4 *>(o + PL + C::TW) = make_float4(ab[0].y, ab[1].y, ab[2].y, ab[3].y);
-      *reinterpret_cast<float4 *>(o + 2 * PL) = make_float4(ac[0].x, ac[1].x, ac[2].x, ac[3].x);
-      *reinterpret_cast<float4 *>(o + 2 * PL + C::TW) = make_float4(ac[0].y, ac[1].y, ac[2].y, ac[3].y);
+      // AR rows 4k, 4k+1 (pair A) and 4k+2, 4k+3 (pair B); the last quad only has pair A
+      float *o = sAR + (4 * k) * C::AR_P + 4 * g;
+#define ST_ROWPAIR(dst, v)                                                                   \
+      *reinterpret_cast<float4 *>(dst) = make_float4(v[0].x, v[1].x, v[2].x, v[3].x);            \
+      *reinterpret_cast<float2 *>((dst) + C::AR_P) = make_float2(v[0].y, v[1].y);                \
+      *reinterpret_cast<float2 *>((dst) + C::AR_P + 2) = make_float2(v[2].y, v[3].y);
+      ST_ROWPAIR(o, a0) ST_ROWPAIR(o + PL, b0) ST_ROWPAIR(o + 2 * PL, c0)
+      if (4 * k + 2 < C::AR_H) {
+        float *o2 = o + 2 * C::AR_P;
+        ST_ROWPAIR(o2, a1) ST_ROWPAIR(o2 + PL, b1) ST_ROWPAIR(o2 + 2 * PL, c1)
+      }
+#undef ST_ROWPAIR
     }
   }
   __syncthreads();
@@ -243,21 +307,21 @@ harris_fused2_kernel(const void *__restrict__ frames, float *__restrict__ Rout, 
   {
     constexpr int RB = 8;
     constexpr int CP = C::TW / 2;                              // 32
-    constexpr int PL = C::AR_H * C::TW;
+    constexpr int PL = C::AR_H * C::AR_P;
     float2 w2[RI + 1];
 #pragma unroll
     for (int t = 0; t <= RI; t++) w2[t] = f2s(kc.wic[t]);
     for (int it = tid; it < CP * (C::TH / RB); it += C::NT) {
       const int rg = it / CP, cp = it - rg * CP;
-      const float *p = sAR + (rg * RB) * C::TW + 2 * cp;      // output row j uses AR rows j .. j+2RI
+      const float *p = sAR + (rg * RB) * C::AR_P + 2 * cp;    // output row j uses AR rows j .. j+2RI
       float2 aa[RB], ab[RB], ac[RB];
 #pragma unroll
       for (int j = 0; j < RB; j++) { aa[j] = f2s(0.f); ab[j] = f2s(0.f); ac[j] = f2s(0.f); }
 #pragma unroll
       for (int q = 0; q < RB + 2 * RI; q++) {
-        const float2 va = *reinterpret_cast<const float2 *>(p + q * C::TW);
-        const float2 vb = *reinterpret_cast<const float2 *>(p + q * C::TW + PL);
-        const float2 vc = *reinterpret_cast<const float2 *>(p + q * C::TW + 2 * PL);
+        const float2 va = *reinterpret_cast<const float2 *>(p + q * C::AR_P);
+        const float2 vb = *reinterpret_cast<const float2 *>(p + q * C::AR_P + PL);
+        const float2 vc = *reinterpret_cast<const float2 *>(p + q * C::AR_P + 2 * PL);
 #pragma unroll
         for (int j = 0; j < RB; j++) {
           const int t = q - j - RI;
