@@ -217,8 +217,8 @@ constexpr int CG_DW = CG_GW + 2;         // data tile 38
 // clamped pixel (cx,cy) can be read with plain +-1 offsets around the tile entry of (cx,cy): the
 // neighbour of an edge pixel is again the edge pixel, which is what the tile holds one entry further.
 __global__ void __launch_bounds__(CG_NT)
-canny_grad_nms_kernel(const float *__restrict__ data, unsigned char *__restrict__ cls, int nx, int ny, int accGrad,
-                      int low_thr, int high_thr) {
+canny_grad_nms_kernel(const float *__restrict__ data, unsigned char *__restrict__ cls, unsigned *__restrict__ Ebits,
+                      unsigned *__restrict__ Sbits, int nx, int ny, int accGrad, int low_thr, int high_thr) {
   __shared__ float sd[CG_DW * CG_DW];
   __shared__ double sg[CG_GW * CG_GW], sh[CG_GW * CG_GW], sv[CG_GW * CG_GW];
   const int x0 = blockIdx.x * CG_T, y0 = blockIdx.y * CG_T;
@@ -255,11 +255,11 @@ canny_grad_nms_kernel(const float *__restrict__ data, unsigned char *__restrict_
   for (int t = threadIdx.x; t < CG_T * CG_T; t += CG_NT) {
     const int ly = t / CG_T, lx = t - ly * CG_T;
     const int gx = x0 + lx, gy = y0 + ly;
-    if (gx >= nx || gy >= ny) continue;
+    const bool inimg = gx < nx && gy < ny;
     const int ci = (ly + CG_GH) * CG_GW + lx + CG_GH;
     const double now = sg[ci];
     unsigned char c = 0;
-    if (!(now <= (double)low_thr)) {
+    if (inimg && !(now <= (double)low_thr)) {
       const double h = sh[ci], v = sv[ci];
       // Direction cosines.  The reference takes cos/sin of atan2(v,h) (rcpp_canny.cpp:69-70,173): the
       // unit vector (h,v)/|(h,v)| up to ~1 ulp of libm error that no other libm reproduces either, and
@@ -296,7 +296,174 @@ canny_grad_nms_kernel(const float *__restrict__ data, unsigned char *__restrict_
       else if (now >= (double)high_thr) c = 2;
       else c = 1;
     }
-    cls[(size_t)blockIdx.z * nx * ny + (size_t)gy * nx + gx] = c;
+    if (inimg) cls[(size_t)blockIdx.z * nx * ny + (size_t)gy * nx + gx] = c;
+    // one bit per pixel for the propagation kernels: word r of this tile = row y0+r, bit x = column x0+x
+    const unsigned eb = __ballot_sync(0xffffffffu, c != 0), sb = __ballot_sync(0xffffffffu, c == 2);
+    if (lx == 0) {
+      const size_t w = (((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 32 + ly;
+      Ebits[w] = eb; Sbits[w] = sb;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ gradient + NMS, speculative
+// Same decision as canny_grad_nms_kernel, reached in two tiers:
+//   tier 1 (every pixel, fp32): gradient, magnitude, direction and the two bilinear neighbours in
+//           single precision, together with a bound on how far those values can be from the
+//           reference's doubles.  If every comparison of rcpp_canny.cpp:97-103 (now vs prev / next /
+//           low / high) is decided with a margin larger than the bound, the class is final.
+//   tier 2 (the rare undecided pixel): the exact double evaluation of that pixel alone, including
+//           glibc-exact hypot of its up to nine neighbour magnitudes.
+// The output is therefore identical to the all-double kernel; B2F_CANNY_EXACT=1 selects the latter.
+// Error budget of tier 1 (float data are exact inputs): h,v are 6-term sums of floats bounded by
+// 8*255, so |dh|,|dv| <= 8*2^-24*2040 < 1e-3; |d grad| <= sqrt(2)*1e-3 + 2^-22*grad < 2.2e-3; a bilinear
+// value inherits that plus (|d cos| + |d sin|) * (spread of the four corner magnitudes), with
+// |d cos|,|d sin| <= 3.2e-3/now + 2^-21.  The margins used below are at least twice these figures.
+__device__ __forceinline__ void exact_hv(const float *d, int accGrad, double &h, double &v) {
+#define DD(dx, dy) ((double)d[(dy) * CG_DW + (dx)])
+  if (accGrad) {
+    h = __dmul_rn(2.0, __dsub_rn(DD(1, 0), DD(-1, 0)));
+    h = __dadd_rn(h, DD(1, 1)); h = __dsub_rn(h, DD(-1, 1)); h = __dadd_rn(h, DD(1, -1)); h = __dsub_rn(h, DD(-1, -1));
+    v = __dmul_rn(2.0, __dsub_rn(DD(0, 1), DD(0, -1)));
+    v = __dadd_rn(v, DD(1, 1)); v = __dsub_rn(v, DD(1, -1)); v = __dadd_rn(v, DD(-1, 1)); v = __dsub_rn(v, DD(-1, -1));
+  } else {
+    h = __dsub_rn(DD(1, 0), DD(-1, 0));
+    v = __dsub_rn(DD(0, 1), DD(0, -1));
+  }
+#undef DD
+}
+
+// exact class of pixel (gx,gy) from the clamped float data tile (tile entry (i,j) <-> pixel
+// (x0-3+i, y0-3+j) clamped) — the reference's arithmetic, operation by operation.
+__device__ __noinline__ unsigned char canny_exact_class(const float *sd, int x0, int y0, int gx, int gy, int nx, int ny,
+                                                        int accGrad, int low_thr, int high_thr) {
+  auto grad_at = [&](int px, int py) -> double {      // magnitude at image pixel (px,py) (already clamped)
+    double h, v;
+    exact_hv(sd + (py - (y0 - 3)) * CG_DW + (px - (x0 - 3)), accGrad, h, v);
+    return hypot_glibc(h, v);
+  };
+  double h, v;
+  exact_hv(sd + (gy - (y0 - 3)) * CG_DW + (gx - (x0 - 3)), accGrad, h, v);
+  const double now = hypot_glibc(h, v);
+  if (now <= (double)low_thr) return 0;
+  double sn, cs;
+  if (h == 0.0 || v == 0.0) { const double th = atan2(v, h); sincos(th, &sn, &cs); }
+  else { const double inv = __ddiv_rn(1.0, now); cs = __dmul_rn(h, inv); sn = __dmul_rn(v, inv); }
+  double nb[2];
+  for (int s = 0; s < 2; s++) {
+    const double dir = s ? 1.0 : -1.0;
+    const double xt = __dmul_rn(dir, cs), yt = __dmul_rn(dir, sn);
+    const double x1 = floor(xt), x2 = __dadd_rn(x1, 1.0), y1 = floor(yt), y2 = __dadd_rn(y1, 1.0);
+    const int ax1 = min(max(gx + (int)x1, 0), nx - 1), ax2 = min(max(gx + (int)x2, 0), nx - 1);
+    const int ay1 = min(max(gy + (int)y1, 0), ny - 1), ay2 = min(max(gy + (int)y2, 0), ny - 1);
+    const double wa = __dsub_rn(x2, xt), wb = __dsub_rn(xt, x1);
+    const double g1 = __dadd_rn(__dmul_rn(wa, grad_at(ax1, ay1)), __dmul_rn(wb, grad_at(ax2, ay1)));
+    const double g2 = __dadd_rn(__dmul_rn(wa, grad_at(ax1, ay2)), __dmul_rn(wb, grad_at(ax2, ay2)));
+    nb[s] = __dadd_rn(__dmul_rn(__dsub_rn(y2, yt), g1), __dmul_rn(__dsub_rn(yt, y1), g2));
+  }
+  if (now <= nb[0] || now <= nb[1]) return 0;
+  return now >= (double)high_thr ? 2 : 1;
+}
+
+__global__ void __launch_bounds__(CG_NT)
+canny_grad_nms_spec_kernel(const float *__restrict__ data, unsigned char *__restrict__ cls, unsigned *__restrict__ Ebits,
+                           unsigned *__restrict__ Sbits, int nx, int ny, int accGrad, int low_thr, int high_thr,
+                           unsigned long long *__restrict__ fallback_count) {
+  __shared__ float sd[CG_DW * CG_DW];
+  __shared__ float fg[CG_GW * CG_GW], fh[CG_GW * CG_GW], fv[CG_GW * CG_GW];
+  const int x0 = blockIdx.x * CG_T, y0 = blockIdx.y * CG_T;
+  const float *src = data + (size_t)blockIdx.z * nx * ny;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  {   // data tile, clamped; 5 rows per warp, both column chunks of all rows fetched before any store
+    const int c0 = min(max(x0 - 3 + lane, 0), nx - 1), c1 = min(max(x0 - 3 + lane + 32, 0), nx - 1);
+    float a[5], b[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+      const int j = warp + 8 * k;
+      const float *row = src + (size_t)min(max(y0 - 3 + min(j, CG_DW - 1), 0), ny - 1) * nx;
+      a[k] = __ldg(row + c0); b[k] = __ldg(row + c1);
+    }
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+      const int j = warp + 8 * k;
+      if (j < CG_DW) { sd[j * CG_DW + lane] = a[k]; if (lane + 32 < CG_DW) sd[j * CG_DW + lane + 32] = b[k]; }
+    }
+  }
+  __syncthreads();
+  // tier-1 gradient tile (fp32)
+  for (int t = threadIdx.x; t < CG_GW * CG_GW; t += CG_NT) {
+    const int j = t / CG_GW, i = t - j * CG_GW;
+    const int xc = min(max(x0 - 2 + i, 0), nx - 1) - (x0 - 3), yc = min(max(y0 - 2 + j, 0), ny - 1) - (y0 - 3);
+    const float *d = sd + yc * CG_DW + xc;
+    float h, v;
+    if (accGrad) {
+      h = 2.f * (d[1] - d[-1]) + d[CG_DW + 1] - d[CG_DW - 1] + d[-CG_DW + 1] - d[-CG_DW - 1];
+      v = 2.f * (d[CG_DW] - d[-CG_DW]) + d[CG_DW + 1] - d[-CG_DW + 1] + d[CG_DW - 1] - d[-CG_DW - 1];
+    } else {
+      h = d[1] - d[-1];
+      v = d[CG_DW] - d[-CG_DW];
+    }
+    fh[t] = h; fv[t] = v;
+    fg[t] = sqrtf(h * h + v * v);
+  }
+  __syncthreads();
+  const bool interior = x0 >= 2 && y0 >= 2 && x0 + CG_T + 2 <= nx && y0 + CG_T + 2 <= ny;
+  const float lowf = (float)low_thr, highf = (float)high_thr;
+  int nfall = 0;
+  for (int t = threadIdx.x; t < CG_T * CG_T; t += CG_NT) {
+    const int ly = t / CG_T, lx = t - ly * CG_T;
+    const int gx = x0 + lx, gy = y0 + ly;
+    const bool inimg = gx < nx && gy < ny;
+    const int ci = (ly + CG_GH) * CG_GW + lx + CG_GH;
+    unsigned char c = 0;
+    if (inimg) {
+      const float now = fg[ci];
+      const float T0 = 4.5e-3f;                                  // 2 x bound on |d grad|
+      bool undecided = false;
+      if (now < lowf - T0) c = 0;                                // certainly now <= low
+      else if (now <= lowf + T0) undecided = true;
+      else {
+        const float inv = 1.0f / now;
+        const float cs = fh[ci] * inv, sn = fv[ci] * inv;
+        float nbv[2], tol[2];
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+          const float xt = s ? cs : -cs, yt = s ? sn : -sn;
+          const float x1 = floorf(xt), y1 = floorf(yt);
+          int ix1, ix2, iy1, iy2;
+          if (interior) { ix1 = lx + CG_GH + (int)x1; ix2 = ix1 + 1; iy1 = ly + CG_GH + (int)y1; iy2 = iy1 + 1; }
+          else {
+            ix1 = min(max(gx + (int)x1, 0), nx - 1) - (x0 - CG_GH); ix2 = min(max(gx + (int)x1 + 1, 0), nx - 1) - (x0 - CG_GH);
+            iy1 = min(max(gy + (int)y1, 0), ny - 1) - (y0 - CG_GH); iy2 = min(max(gy + (int)y1 + 1, 0), ny - 1) - (y0 - CG_GH);
+          }
+          const float g11 = fg[iy1 * CG_GW + ix1], g12 = fg[iy1 * CG_GW + ix2], g21 = fg[iy2 * CG_GW + ix1], g22 = fg[iy2 * CG_GW + ix2];
+          const float wb = xt - x1, wa = 1.f - wb, wd = yt - y1, wc = 1.f - wd;
+          nbv[s] = wc * (wa * g11 + wb * g12) + wd * (wa * g21 + wb * g22);
+          const float spread = fmaxf(fmaxf(g11, g12), fmaxf(g21, g22)) - fminf(fminf(g11, g12), fminf(g21, g22));
+          tol[s] = 2.f * T0 + 8.f * (1e-3f * inv + 5e-7f) * spread;
+        }
+        // the direction is ambiguous for the reference's floor() when a cosine is within its error of 0
+        const float dcs = 8.f * (1e-3f * inv + 5e-7f);
+        if (fabsf(cs) <= dcs || fabsf(sn) <= dcs) undecided = true;
+        else if (now < nbv[0] - tol[0] || now < nbv[1] - tol[1]) c = 0;      // certainly suppressed
+        else if (now > nbv[0] + tol[0] && now > nbv[1] + tol[1]) {           // certainly a maximum
+          if (now >= highf + T0) c = 2;
+          else if (now < highf - T0) c = 1;
+          else undecided = true;
+        } else undecided = true;
+      }
+      if (undecided) { c = canny_exact_class(sd, x0, y0, gx, gy, nx, ny, accGrad, low_thr, high_thr); nfall++; }
+      cls[(size_t)blockIdx.z * nx * ny + (size_t)gy * nx + gx] = c;
+    }
+    const unsigned eb = __ballot_sync(0xffffffffu, c != 0), sb = __ballot_sync(0xffffffffu, c == 2);
+    if (lx == 0) {
+      const size_t w = (((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 32 + ly;
+      Ebits[w] = eb; Sbits[w] = sb;
+    }
+  }
+  if (fallback_count) {
+    for (int o = 16; o; o >>= 1) nfall += __shfl_xor_sync(0xffffffffu, nfall, o);
+    if (lane == 0 && nfall) atomicAdd(fallback_count, (unsigned long long)nfall);
   }
 }
 
@@ -517,6 +684,103 @@ __global__ void hyst_emit(const unsigned char *__restrict__ cls, const int *__re
   if (threadIdx.x == 0 && cnt) atomicAdd(&nonzero[f], cnt);
 }
 
+// ------------------------------------------------------------------------------------------ hysteresis, fast path
+// Reachability from the class-2 seeds by synchronous propagation on 1-bit-per-pixel planes.  One warp
+// owns a 32x32 tile: lane r holds the edge word e and the reached word s of row r.  A local step is a
+// 3x3 dilation of s restricted to e followed by an O(1) flood along horizontal runs (carry trick);
+// steps repeat until the tile is stable.  Tiles exchange their boundary bits once per launch, so a
+// launch advances the front by at least one tile; launches repeat until one of them changes nothing
+// (flag protocol below).  The result is the same set as the union-find formulation (connected
+// components of class != 0 that contain a class-2 pixel, rcpp_canny.cpp:184-215) — reached in a
+// different order, and set union does not care.
+__device__ __forceinline__ unsigned run_fill(unsigned e, unsigned x) {
+  // all bits of the runs of e that contain a bit of x (x subset of e)
+  const unsigned up = (e ^ (e + x)) & e;                       // seed .. top of its run
+  const unsigned er = __brev(e), xr = __brev(x);
+  const unsigned dn = __brev((er ^ (er + xr)) & er);           // seed .. bottom of its run
+  return up | dn | x;
+}
+
+__global__ void __launch_bounds__(256)
+hyst_prop_kernel(const unsigned *__restrict__ Ebits, unsigned *__restrict__ Sbits, const int *__restrict__ flag_in,
+                 int *__restrict__ flag_out, int TX, int TY, int n_tiles) {
+  if (*flag_in == 0) return;                                   // converged in an earlier launch
+  const int lane = threadIdx.x & 31;
+  const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (tile >= n_tiles) return;
+  const int tx = tile % TX, ty = (tile / TX) % TY;
+  const size_t base = (size_t)tile * 32;
+  const unsigned e = Ebits[base + lane];
+  if (!__any_sync(0xffffffffu, e != 0)) return;
+  unsigned s = Sbits[base + lane];
+  const unsigned s_in = s;
+  // boundary bits of the 8 neighbouring tiles (tile-major layout: neighbour tile index +-1, +-TX)
+  const bool hasL = tx > 0, hasR = tx + 1 < TX, hasU = ty > 0, hasD = ty + 1 < TY;
+  const unsigned sl = hasL ? Sbits[base - 32 + lane] : 0u, sr = hasR ? Sbits[base + 32 + lane] : 0u;
+  const unsigned lbit = sl >> 31, rbit = sr & 1u;              // my row: left tile's column 31, right tile's column 0
+  unsigned up_row = 0, dn_row = 0, up_l = 0, up_r = 0, dn_l = 0, dn_r = 0;
+  if (hasU) {
+    const size_t u = base - (size_t)TX * 32;
+    up_row = Sbits[u + 31];
+    if (hasL) up_l = Sbits[u - 32 + 31] >> 31;
+    if (hasR) up_r = Sbits[u + 32 + 31] & 1u;
+  }
+  if (hasD) {
+    const size_t d = base + (size_t)TX * 32;
+    dn_row = Sbits[d];
+    if (hasL) dn_l = Sbits[d - 32] >> 31;
+    if (hasR) dn_r = Sbits[d + 32] & 1u;
+  }
+  for (int iter = 0; iter < 96; iter++) {
+    // horizontally spread row words (with the carry-in bits of the side tiles)
+    const unsigned h = s | (s << 1) | (s >> 1) | lbit | (rbit << 31);
+    unsigned hu = __shfl_up_sync(0xffffffffu, h, 1), hd = __shfl_down_sync(0xffffffffu, h, 1);
+    // neighbours' side bits for the rows above / below
+    const unsigned lu = __shfl_up_sync(0xffffffffu, lbit, 1), ru = __shfl_up_sync(0xffffffffu, rbit, 1);
+    const unsigned ld = __shfl_down_sync(0xffffffffu, lbit, 1), rd = __shfl_down_sync(0xffffffffu, rbit, 1);
+    (void)lu; (void)ru; (void)ld; (void)rd;                    // already folded into h of those lanes
+    if (lane == 0) hu = up_row | (up_row << 1) | (up_row >> 1) | up_l | (up_r << 31);
+    if (lane == 31) hd = dn_row | (dn_row << 1) | (dn_row >> 1) | dn_l | (dn_r << 31);
+    const unsigned seeds = e & (h | hu | hd);
+    const unsigned ns = run_fill(e, seeds) | s;
+    const bool ch = ns != s;
+    s = ns;
+    if (!__any_sync(0xffffffffu, ch)) break;
+  }
+  const bool changed = s != s_in;
+  if (changed) Sbits[base + lane] = s;
+  if (__any_sync(0xffffffffu, changed) && lane == 0) *flag_out = 1;
+}
+
+// edges (0/255 bytes) and per-frame counts from the final reached bits
+__global__ void __launch_bounds__(256)
+hyst_emit_bits_kernel(const unsigned *__restrict__ Sbits, unsigned char *__restrict__ edges, int *__restrict__ nonzero,
+                      int nx, int ny, int TX, int TY) {
+  const int tx = blockIdx.x, ty = blockIdx.y, f = blockIdx.z;
+  const int r = threadIdx.x >> 3, part = threadIdx.x & 7;      // 32 rows x 8 groups of 4 pixels
+  const unsigned w = Sbits[(((size_t)f * TY + ty) * TX + tx) * 32 + r];
+  const int gy = ty * 32 + r, gx = tx * 32 + 4 * part;
+  const unsigned nib = (w >> (4 * part)) & 0xfu;
+  int cnt = 0;
+  if (gy < ny && gx < nx) {
+    unsigned char *dst = edges + (size_t)f * nx * ny + (size_t)gy * nx + gx;
+    if ((nx & 3) == 0 && (reinterpret_cast<uintptr_t>(edges) & 3) == 0) {
+      const unsigned v = ((nib & 1u) ? 0xffu : 0u) | ((nib & 2u) ? 0xff00u : 0u) | ((nib & 4u) ? 0xff0000u : 0u) | ((nib & 8u) ? 0xff000000u : 0u);
+      *reinterpret_cast<unsigned *>(dst) = v;
+      cnt = __popc(nib);
+    } else {
+      for (int b = 0; b < 4; b++) if (gx + b < nx) { const bool on = (nib >> b) & 1u; dst[b] = on ? 255 : 0; cnt += on; }
+    }
+  }
+  for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  __shared__ int tot;
+  if (threadIdx.x == 0) tot = 0;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&tot, cnt);
+  __syncthreads();
+  if (threadIdx.x == 0 && tot) atomicAdd(&nonzero[f], tot);
+}
+
 // ------------------------------------------------------------------------------------------ host
 // tap list of one axis: orc_canny_taps restated (tools.c:146-163): wrap coordinates, exp(-c^2/s^2),
 // unit sum over the full period, taps below 2^-64 dropped.
@@ -546,7 +810,7 @@ static bool symmetric_taps(const std::vector<int> &c, const std::vector<double> 
 
 size_t canny_scratch_bytes(int n_frames, int nx, int ny) {
   size_t n = (size_t)n_frames * nx * ny;
-  return align256(n * 4) /*blur*/ + align256(n) /*cls*/ + align256(n * 4) /*labels*/ + align256(n) /*strong*/ + align256(n) /*rinfo*/ +
+  return align256(n * 4) /*blur*/ + align256(n) /*cls*/ + align256(n * 4) /*labels*/ + align256(n) /*strong*/ + align256(n) /*rinfo*/ + 2 * align256((size_t)(ceil_div(nx, 32) + 1) * (ceil_div(ny, 32) + 1) * n_frames * 128) /*bit planes*/ + 4096 +
          align256(n * 8) /*generic path rows*/ + (1 << 16);
 }
 
@@ -560,6 +824,9 @@ int canny_device(b2f_ctx *ctx, const unsigned char *d_frames, int n_frames, int 
   int *L = ctx->arena.get<int>(n);
   unsigned char *strong = ctx->arena.get<unsigned char>(n);
   unsigned char *rinfo = ctx->arena.get<unsigned char>(n);
+  const size_t n_words = (size_t)ceil_div(nx, 32) * ceil_div(ny, 32) * n_frames * 32;
+  unsigned *Ebits = ctx->arena.get<unsigned>(n_words), *Sbits = ctx->arena.get<unsigned>(n_words);
+  int *flags = ctx->arena.get<int>(64);
   std::vector<int> cx, cy; std::vector<double> wx, wy;
   make_taps(nx, s, cx, wx); make_taps(ny, s, cy, wy);
   CannyTaps tx, ty;
@@ -594,11 +861,40 @@ int canny_device(b2f_ctx *ctx, const unsigned char *d_frames, int n_frames, int 
     canny_blur_generic_cols<<<grid, 128, 0, st>>>(tmp, blur, nx, ny, TapList{dcx + cx.size(), dwx + wx.size(), (int)cy.size(), sym ? 1 : 0});
     B2F_LAUNCH_CHECK(ctx);
   }
-  canny_grad_nms_kernel<<<dim3(ceil_div(nx, CG_T), ceil_div(ny, CG_T), n_frames), CG_NT, 0, st>>>(
-      blur, cls, nx, ny, acc_grad ? 1 : 0, (int)low_thr, (int)high_thr);   // thresholds truncate like rcpp_canny.cpp:180
+  const int TX = ceil_div(nx, CG_T), TY = ceil_div(ny, CG_T), n_tiles = TX * TY * n_frames;
+  static const bool force_exact = getenv("B2F_CANNY_EXACT") != nullptr;
+  if (force_exact)
+    canny_grad_nms_kernel<<<dim3(TX, TY, n_frames), CG_NT, 0, st>>>(
+        blur, cls, Ebits, Sbits, nx, ny, acc_grad ? 1 : 0, (int)low_thr, (int)high_thr);   // thresholds truncate like rcpp_canny.cpp:180
+  else
+    canny_grad_nms_spec_kernel<<<dim3(TX, TY, n_frames), CG_NT, 0, st>>>(
+        blur, cls, Ebits, Sbits, nx, ny, acc_grad ? 1 : 0, (int)low_thr, (int)high_thr, nullptr);
   B2F_LAUNCH_CHECK(ctx);
-  B2F_CUDA(cudaMemsetAsync(strong, 0, n, st));
   B2F_CUDA(cudaMemsetAsync(d_nonzero, 0, sizeof(int) * n_frames, st));
+  // ---- hysteresis, fast path: bit-plane propagation.  Launch i runs only if launch i-1 changed something.
+  constexpr int MAX_ROUNDS = 48;
+  B2F_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * (MAX_ROUNDS + 2), st));
+  {
+    const int one = 1;
+    B2F_CUDA(cudaMemcpyAsync(flags, &one, sizeof(int), cudaMemcpyHostToDevice, st));
+  }
+  static const bool force_uf = getenv("B2F_CANNY_UNIONFIND") != nullptr;
+  int still = 1;
+  if (!force_uf) {
+    for (int i = 0; i < MAX_ROUNDS; i++) {
+      hyst_prop_kernel<<<ceil_div(n_tiles, 8), 256, 0, st>>>(Ebits, Sbits, flags + i, flags + i + 1, TX, TY, n_tiles);
+      B2F_LAUNCH_CHECK(ctx);
+    }
+    B2F_CUDA(cudaMemcpyAsync(&still, flags + MAX_ROUNDS, sizeof(int), cudaMemcpyDeviceToHost, st));
+    B2F_CUDA(cudaStreamSynchronize(st));      // one host decision per call: did the propagation converge?
+  }
+  if (!still) {
+    hyst_emit_bits_kernel<<<dim3(TX, TY, n_frames), 256, 0, st>>>(Sbits, d_edges, d_nonzero, nx, ny, TX, TY);
+    B2F_LAUNCH_CHECK(ctx);
+    return B2F_OK;
+  }
+  // ---- fallback (fronts that need more than MAX_ROUNDS tile hops): two-level union-find, always exact
+  B2F_CUDA(cudaMemsetAsync(strong, 0, n, st));
   dim3 tiles(ceil_div(nx, HT), ceil_div(ny, HT), n_frames);
   hyst_local_kernel<<<tiles, 256, 0, st>>>(cls, L, rinfo, nx, ny);
   B2F_LAUNCH_CHECK(ctx);
