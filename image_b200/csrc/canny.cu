@@ -299,8 +299,8 @@ canny_grad_nms_kernel(const float *__restrict__ data, unsigned char *__restrict_
     if (inimg) cls[(size_t)blockIdx.z * nx * ny + (size_t)gy * nx + gx] = c;
     // one bit per pixel for the propagation kernels: word r of this tile = row y0+r, bit x = column x0+x
     const unsigned eb = __ballot_sync(0xffffffffu, c != 0), sb = __ballot_sync(0xffffffffu, c == 2);
-    if (lx == 0) {
-      const size_t w = (((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 32 + ly;
+    if (lx == 0 && gy < ny) {
+      const size_t w = ((size_t)blockIdx.z * ny + gy) * gridDim.x + blockIdx.x;        // row-major bit planes
       Ebits[w] = eb; Sbits[w] = sb;
     }
   }
@@ -409,7 +409,11 @@ canny_grad_nms_spec_kernel(const float *__restrict__ data, unsigned char *__rest
   __syncthreads();
   const bool interior = x0 >= 2 && y0 >= 2 && x0 + CG_T + 2 <= nx && y0 + CG_T + 2 <= ny;
   const float lowf = (float)low_thr, highf = (float)high_thr;
-  int nfall = 0;
+  __shared__ unsigned char scls[CG_T * CG_T];
+  __shared__ unsigned short squeue[CG_T * CG_T];
+  __shared__ int qn;
+  if (threadIdx.x == 0) qn = 0;
+  __syncthreads();
   for (int t = threadIdx.x; t < CG_T * CG_T; t += CG_NT) {
     const int ly = t / CG_T, lx = t - ly * CG_T;
     const int gx = x0 + lx, gy = y0 + ly;
@@ -452,19 +456,30 @@ canny_grad_nms_spec_kernel(const float *__restrict__ data, unsigned char *__rest
           else undecided = true;
         } else undecided = true;
       }
-      if (undecided) { c = canny_exact_class(sd, x0, y0, gx, gy, nx, ny, accGrad, low_thr, high_thr); nfall++; }
-      cls[(size_t)blockIdx.z * nx * ny + (size_t)gy * nx + gx] = c;
+      if (undecided) squeue[atomicAdd(&qn, 1)] = (unsigned short)t;
     }
+    scls[t] = c;
+  }
+  __syncthreads();
+  // tier 2: the undecided pixels of this tile, one thread each (no divergence against decided lanes)
+  const int nq = qn;
+  for (int i = threadIdx.x; i < nq; i += CG_NT) {
+    const int t = squeue[i], ly = t / CG_T, lx = t - ly * CG_T;
+    scls[t] = canny_exact_class(sd, x0, y0, x0 + lx, y0 + ly, nx, ny, accGrad, low_thr, high_thr);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < CG_T * CG_T; t += CG_NT) {
+    const int ly = t / CG_T, lx = t - ly * CG_T;
+    const int gx = x0 + lx, gy = y0 + ly;
+    const unsigned char c = scls[t];
+    if (gx < nx && gy < ny) cls[(size_t)blockIdx.z * nx * ny + (size_t)gy * nx + gx] = c;
     const unsigned eb = __ballot_sync(0xffffffffu, c != 0), sb = __ballot_sync(0xffffffffu, c == 2);
-    if (lx == 0) {
-      const size_t w = (((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 32 + ly;
+    if (lx == 0 && gy < ny) {
+      const size_t w = ((size_t)blockIdx.z * ny + gy) * gridDim.x + blockIdx.x;      // row-major bit planes
       Ebits[w] = eb; Sbits[w] = sb;
     }
   }
-  if (fallback_count) {
-    for (int o = 16; o; o >>= 1) nfall += __shfl_xor_sync(0xffffffffu, nfall, o);
-    if (lane == 0 && nfall) atomicAdd(fallback_count, (unsigned long long)nfall);
-  }
+  if (fallback_count && threadIdx.x == 0 && nq) atomicAdd(fallback_count, (unsigned long long)nq);
 }
 
 // ------------------------------------------------------------------------------------------ hysteresis
@@ -685,100 +700,114 @@ __global__ void hyst_emit(const unsigned char *__restrict__ cls, const int *__re
 }
 
 // ------------------------------------------------------------------------------------------ hysteresis, fast path
-// Reachability from the class-2 seeds by synchronous propagation on 1-bit-per-pixel planes.  One warp
-// owns a 32x32 tile: lane r holds the edge word e and the reached word s of row r.  A local step is a
-// 3x3 dilation of s restricted to e followed by an O(1) flood along horizontal runs (carry trick);
-// steps repeat until the tile is stable.  Tiles exchange their boundary bits once per launch, so a
-// launch advances the front by at least one tile; launches repeat until one of them changes nothing
-// (flag protocol below).  The result is the same set as the union-find formulation (connected
-// components of class != 0 that contain a class-2 pixel, rcpp_canny.cpp:184-215) — reached in a
-// different order, and set union does not care.
-__device__ __forceinline__ unsigned run_fill(unsigned e, unsigned x) {
-  // all bits of the runs of e that contain a bit of x (x subset of e)
-  const unsigned up = (e ^ (e + x)) & e;                       // seed .. top of its run
-  const unsigned er = __brev(e), xr = __brev(x);
-  const unsigned dn = __brev((er ^ (er + xr)) & er);           // seed .. bottom of its run
-  return up | dn | x;
-}
+// Breadth-first flood from the class-2 pixels over the class != 0 pixels on 1-bit-per-pixel planes
+// (row-major, 32 pixels per word).  Reached set R starts as the strong set; a frontier pixel tests its
+// 8 neighbours, claims each unreached edge neighbour with one atomicOr on R and appends it to the next
+// frontier.  One persistent cooperative kernel runs all levels (grid-wide barrier between levels), so
+// the whole batch costs  (#levels x barrier) + O(reached pixels)  instead of passes over every tile.
+// Same result as the reference's union-find (rcpp_canny.cpp:184-215): the union of the components
+// that contain a strong pixel.  If a frontier overflows its queue the caller falls back to the
+// two-level union-find below (status = 2).
+}  // namespace b2f
+#include <cooperative_groups.h>
+namespace b2f {
+namespace cg = cooperative_groups;
 
-__global__ void __launch_bounds__(256)
-hyst_prop_kernel(const unsigned *__restrict__ Ebits, unsigned *__restrict__ Sbits, const int *__restrict__ flag_in,
-                 int *__restrict__ flag_out, int TX, int TY, int n_tiles) {
-  if (*flag_in == 0) return;                                   // converged in an earlier launch
+__global__ void hyst_seed_kernel(const unsigned *__restrict__ Sbits, int *__restrict__ queue, int *__restrict__ qcount,
+                                 int cap, size_t n_words, int wpr, int ny) {
+  // every strong pixel is a level-0 frontier entry: value = global pixel id  (f*ny + y)*wpr*32 + x
+  size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned bits = w < n_words ? Sbits[w] : 0u;
+  const int cnt = __popc(bits);
+  // warp-aggregated reservation
+  int incl = cnt;
   const int lane = threadIdx.x & 31;
-  const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (tile >= n_tiles) return;
-  const int tx = tile % TX, ty = (tile / TX) % TY;
-  const size_t base = (size_t)tile * 32;
-  const unsigned e = Ebits[base + lane];
-  if (!__any_sync(0xffffffffu, e != 0)) return;
-  unsigned s = Sbits[base + lane];
-  const unsigned s_in = s;
-  // boundary bits of the 8 neighbouring tiles (tile-major layout: neighbour tile index +-1, +-TX)
-  const bool hasL = tx > 0, hasR = tx + 1 < TX, hasU = ty > 0, hasD = ty + 1 < TY;
-  const unsigned sl = hasL ? Sbits[base - 32 + lane] : 0u, sr = hasR ? Sbits[base + 32 + lane] : 0u;
-  const unsigned lbit = sl >> 31, rbit = sr & 1u;              // my row: left tile's column 31, right tile's column 0
-  unsigned up_row = 0, dn_row = 0, up_l = 0, up_r = 0, dn_l = 0, dn_r = 0;
-  if (hasU) {
-    const size_t u = base - (size_t)TX * 32;
-    up_row = Sbits[u + 31];
-    if (hasL) up_l = Sbits[u - 32 + 31] >> 31;
-    if (hasR) up_r = Sbits[u + 32 + 31] & 1u;
+  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  int base = 0;
+  if (lane == 31 && total) base = atomicAdd(qcount, total);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  int pos = base + incl - cnt;
+  while (bits) {
+    const int b = __ffs(bits) - 1;
+    bits &= bits - 1;
+    if (pos < cap) queue[pos] = (int)(w * 32 + b);
+    pos++;
   }
-  if (hasD) {
-    const size_t d = base + (size_t)TX * 32;
-    dn_row = Sbits[d];
-    if (hasL) dn_l = Sbits[d - 32] >> 31;
-    if (hasR) dn_r = Sbits[d + 32] & 1u;
-  }
-  for (int iter = 0; iter < 96; iter++) {
-    // horizontally spread row words (with the carry-in bits of the side tiles)
-    const unsigned h = s | (s << 1) | (s >> 1) | lbit | (rbit << 31);
-    unsigned hu = __shfl_up_sync(0xffffffffu, h, 1), hd = __shfl_down_sync(0xffffffffu, h, 1);
-    // neighbours' side bits for the rows above / below
-    const unsigned lu = __shfl_up_sync(0xffffffffu, lbit, 1), ru = __shfl_up_sync(0xffffffffu, rbit, 1);
-    const unsigned ld = __shfl_down_sync(0xffffffffu, lbit, 1), rd = __shfl_down_sync(0xffffffffu, rbit, 1);
-    (void)lu; (void)ru; (void)ld; (void)rd;                    // already folded into h of those lanes
-    if (lane == 0) hu = up_row | (up_row << 1) | (up_row >> 1) | up_l | (up_r << 31);
-    if (lane == 31) hd = dn_row | (dn_row << 1) | (dn_row >> 1) | dn_l | (dn_r << 31);
-    const unsigned seeds = e & (h | hu | hd);
-    const unsigned ns = run_fill(e, seeds) | s;
-    const bool ch = ns != s;
-    s = ns;
-    if (!__any_sync(0xffffffffu, ch)) break;
-  }
-  const bool changed = s != s_in;
-  if (changed) Sbits[base + lane] = s;
-  if (__any_sync(0xffffffffu, changed) && lane == 0) *flag_out = 1;
 }
 
-// edges (0/255 bytes) and per-frame counts from the final reached bits
 __global__ void __launch_bounds__(256)
-hyst_emit_bits_kernel(const unsigned *__restrict__ Sbits, unsigned char *__restrict__ edges, int *__restrict__ nonzero,
-                      int nx, int ny, int TX, int TY) {
-  const int tx = blockIdx.x, ty = blockIdx.y, f = blockIdx.z;
-  const int r = threadIdx.x >> 3, part = threadIdx.x & 7;      // 32 rows x 8 groups of 4 pixels
-  const unsigned w = Sbits[(((size_t)f * TY + ty) * TX + tx) * 32 + r];
-  const int gy = ty * 32 + r, gx = tx * 32 + 4 * part;
-  const unsigned nib = (w >> (4 * part)) & 0xfu;
-  int cnt = 0;
-  if (gy < ny && gx < nx) {
-    unsigned char *dst = edges + (size_t)f * nx * ny + (size_t)gy * nx + gx;
-    if ((nx & 3) == 0 && (reinterpret_cast<uintptr_t>(edges) & 3) == 0) {
-      const unsigned v = ((nib & 1u) ? 0xffu : 0u) | ((nib & 2u) ? 0xff00u : 0u) | ((nib & 4u) ? 0xff0000u : 0u) | ((nib & 8u) ? 0xff000000u : 0u);
-      *reinterpret_cast<unsigned *>(dst) = v;
-      cnt = __popc(nib);
-    } else {
-      for (int b = 0; b < 4; b++) if (gx + b < nx) { const bool on = (nib >> b) & 1u; dst[b] = on ? 255 : 0; cnt += on; }
+hyst_bfs_kernel(const unsigned *__restrict__ Ebits, unsigned *__restrict__ Rbits, int *__restrict__ qa, int *__restrict__ qb,
+                int *__restrict__ counts /* [0]=|qa| [1]=|qb| [2]=status */, int cap, int wpr, int nx, int ny) {
+  cg::grid_group grid = cg::this_grid();
+  const int rowpix = wpr * 32;
+  int *cur = qa, *nxt = qb;
+  int ci = 0;
+  volatile int *vc = counts;                                    // counters and queues are re-read every level: bypass L1
+  if (vc[0] > cap) { if (grid.thread_rank() == 0) vc[2] = 2; return; }              // seed overflow (uniform exit)
+  for (int level = 0;; level++) {
+    const int n = vc[ci];
+    if (n == 0) break;
+    for (size_t i = grid.thread_rank(); i < (size_t)n; i += grid.size()) {
+      const int p = __ldcg(cur + i);
+      const int row = p / rowpix, x = p - row * rowpix;             // row = f*ny + y
+      const int y = row % ny;
+#pragma unroll
+      for (int dy = -1; dy <= 1; dy++) {
+        const int yy = y + dy;
+        if (yy < 0 || yy >= ny) continue;
+#pragma unroll
+        for (int dx = -1; dx <= 1; dx++) {
+          if (dx == 0 && dy == 0) continue;
+          const int xx = x + dx;
+          if (xx < 0 || xx >= nx) continue;
+          const size_t w = (size_t)(row + dy) * wpr + (xx >> 5);
+          const unsigned bit = 1u << (xx & 31);
+          if (!(__ldg(Ebits + w) & bit)) continue;
+          if (Rbits[w] & bit) continue;                              // cheap pre-test
+          const unsigned old = atomicOr(&Rbits[w], bit);
+          if (old & bit) continue;
+          const int slot = atomicAdd(&counts[1 - ci], 1);
+          if (slot < cap) nxt[slot] = (row + dy) * rowpix + xx;
+        }
+      }
     }
+    grid.sync();
+    if (vc[1 - ci] > cap) { if (grid.thread_rank() == 0) vc[2] = 2; break; }           // uniform: same value for all
+    if (grid.thread_rank() == 0) vc[ci] = 0;
+    int *t = cur; cur = nxt; nxt = t;
+    ci = 1 - ci;
+    grid.sync();
+  }
+}
+
+// edges (0/255 bytes) and per-frame counts from the reached bits: one thread = one 32-pixel word
+__global__ void hyst_emit_bits_kernel(const unsigned *__restrict__ Rbits, unsigned char *__restrict__ edges,
+                                      int *__restrict__ nonzero, int nx, int ny, int wpr) {
+  const int wx = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
+  int cnt = 0;
+  if (wx < wpr) {
+    const unsigned w = Rbits[((size_t)f * ny + y) * wpr + wx];
+    unsigned char *dst = edges + (size_t)f * nx * ny + (size_t)y * nx + (size_t)wx * 32;
+    const int valid = min(32, nx - wx * 32);
+    if (valid == 32 && (nx & 15) == 0 && (reinterpret_cast<uintptr_t>(edges) & 15) == 0) {
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        unsigned v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const unsigned nib = (w >> (16 * q + 4 * k)) & 0xfu;
+          v[k] = ((nib & 1u) ? 0xffu : 0u) | ((nib & 2u) ? 0xff00u : 0u) | ((nib & 4u) ? 0xff0000u : 0u) | ((nib & 8u) ? 0xff000000u : 0u);
+        }
+        reinterpret_cast<uint4 *>(dst)[q] = make_uint4(v[0], v[1], v[2], v[3]);
+      }
+    } else {
+      for (int b = 0; b < valid; b++) dst[b] = ((w >> b) & 1u) ? 255 : 0;
+    }
+    cnt = __popc(valid == 32 ? w : (w & ((1u << valid) - 1u)));
   }
   for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  __shared__ int tot;
-  if (threadIdx.x == 0) tot = 0;
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&tot, cnt);
-  __syncthreads();
-  if (threadIdx.x == 0 && tot) atomicAdd(&nonzero[f], tot);
+  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&nonzero[f], cnt);
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -824,7 +853,7 @@ int canny_device(b2f_ctx *ctx, const unsigned char *d_frames, int n_frames, int 
   int *L = ctx->arena.get<int>(n);
   unsigned char *strong = ctx->arena.get<unsigned char>(n);
   unsigned char *rinfo = ctx->arena.get<unsigned char>(n);
-  const size_t n_words = (size_t)ceil_div(nx, 32) * ceil_div(ny, 32) * n_frames * 32;
+  const size_t n_words = (size_t)ceil_div(nx, 32) * ny * n_frames;                  // row-major bit planes
   unsigned *Ebits = ctx->arena.get<unsigned>(n_words), *Sbits = ctx->arena.get<unsigned>(n_words);
   int *flags = ctx->arena.get<int>(64);
   std::vector<int> cx, cy; std::vector<double> wx, wy;
@@ -861,7 +890,7 @@ int canny_device(b2f_ctx *ctx, const unsigned char *d_frames, int n_frames, int 
     canny_blur_generic_cols<<<grid, 128, 0, st>>>(tmp, blur, nx, ny, TapList{dcx + cx.size(), dwx + wx.size(), (int)cy.size(), sym ? 1 : 0});
     B2F_LAUNCH_CHECK(ctx);
   }
-  const int TX = ceil_div(nx, CG_T), TY = ceil_div(ny, CG_T), n_tiles = TX * TY * n_frames;
+  const int TX = ceil_div(nx, CG_T), TY = ceil_div(ny, CG_T), wpr = TX;
   static const bool force_exact = getenv("B2F_CANNY_EXACT") != nullptr;
   if (force_exact)
     canny_grad_nms_kernel<<<dim3(TX, TY, n_frames), CG_NT, 0, st>>>(
@@ -871,29 +900,35 @@ int canny_device(b2f_ctx *ctx, const unsigned char *d_frames, int n_frames, int 
         blur, cls, Ebits, Sbits, nx, ny, acc_grad ? 1 : 0, (int)low_thr, (int)high_thr, nullptr);
   B2F_LAUNCH_CHECK(ctx);
   B2F_CUDA(cudaMemsetAsync(d_nonzero, 0, sizeof(int) * n_frames, st));
-  // ---- hysteresis, fast path: bit-plane propagation.  Launch i runs only if launch i-1 changed something.
-  constexpr int MAX_ROUNDS = 48;
-  B2F_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * (MAX_ROUNDS + 2), st));
-  {
-    const int one = 1;
-    B2F_CUDA(cudaMemcpyAsync(flags, &one, sizeof(int), cudaMemcpyHostToDevice, st));
-  }
+  // ---- hysteresis, fast path: cooperative BFS on the bit planes (queues live in the label plane L)
   static const bool force_uf = getenv("B2F_CANNY_UNIONFIND") != nullptr;
-  int still = 1;
-  if (!force_uf) {
-    for (int i = 0; i < MAX_ROUNDS; i++) {
-      hyst_prop_kernel<<<ceil_div(n_tiles, 8), 256, 0, st>>>(Ebits, Sbits, flags + i, flags + i + 1, TX, TY, n_tiles);
-      B2F_LAUNCH_CHECK(ctx);
+  int status = 2;
+  if (!force_uf && (size_t)n_frames * ny * wpr * 32 < ((size_t)1 << 31)) {
+    const size_t words = (size_t)n_frames * ny * wpr;
+    const int cap = (int)std::min<size_t>(n / 2, (size_t)1 << 30);
+    int *qa = L, *qb = L + cap;
+    B2F_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * 4, st));
+    hyst_seed_kernel<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(Sbits, qa, flags, cap, words, wpr, ny);
+    B2F_LAUNCH_CHECK(ctx);
+    static int coop_blocks = 0;
+    if (!coop_blocks) {
+      int per_sm = 0;
+      B2F_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hyst_bfs_kernel, 256, 0));
+      coop_blocks = std::max(1, per_sm) * ctx->sm_count;
     }
-    B2F_CUDA(cudaMemcpyAsync(&still, flags + MAX_ROUNDS, sizeof(int), cudaMemcpyDeviceToHost, st));
-    B2F_CUDA(cudaStreamSynchronize(st));      // one host decision per call: did the propagation converge?
+    const unsigned *Ep = Ebits; unsigned *Rp = Sbits; int *cnts = flags; int capv = cap, wprv = wpr, nxv = nx, nyv = ny;
+    void *args[] = {(void *)&Ep, (void *)&Rp, (void *)&qa, (void *)&qb, (void *)&cnts, (void *)&capv, (void *)&wprv, (void *)&nxv, (void *)&nyv};
+    B2F_CUDA(cudaLaunchCooperativeKernel((const void *)hyst_bfs_kernel, dim3(coop_blocks), dim3(256), args, 0, st));
+    ctx->launches++;
+    B2F_CUDA(cudaMemcpyAsync(&status, flags + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
+    B2F_CUDA(cudaStreamSynchronize(st));      // one host decision per call: did a queue overflow?
   }
-  if (!still) {
-    hyst_emit_bits_kernel<<<dim3(TX, TY, n_frames), 256, 0, st>>>(Sbits, d_edges, d_nonzero, nx, ny, TX, TY);
+  if (status == 0) {
+    hyst_emit_bits_kernel<<<dim3(ceil_div(wpr, 64), ny, n_frames), 64, 0, st>>>(Sbits, d_edges, d_nonzero, nx, ny, wpr);
     B2F_LAUNCH_CHECK(ctx);
     return B2F_OK;
   }
-  // ---- fallback (fronts that need more than MAX_ROUNDS tile hops): two-level union-find, always exact
+  // ---- fallback (queue overflow, or forced): two-level union-find on the class bytes, always exact
   B2F_CUDA(cudaMemsetAsync(strong, 0, n, st));
   dim3 tiles(ceil_div(nx, HT), ceil_div(ny, HT), n_frames);
   hyst_local_kernel<<<tiles, 256, 0, st>>>(cls, L, rinfo, nx, ny);
