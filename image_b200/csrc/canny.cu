@@ -217,8 +217,8 @@ constexpr int CG_DW = CG_GW + 2;         // data tile 38
 // clamped pixel (cx,cy) can be read with plain +-1 offsets around the tile entry of (cx,cy): the
 // neighbour of an edge pixel is again the edge pixel, which is what the tile holds one entry further.
 __global__ void __launch_bounds__(CG_NT)
-canny_grad_nms_kernel(const float *__restrict__ data, unsigned char *__restrict__ cls, unsigned *__restrict__ Ebits,
-                      unsigned *__restrict__ Sbits, int nx, int ny, int accGrad, int low_thr, int high_thr) {
+canny_grad_nms_kernel(const float *__restrict__ data, unsigned char *__restrict__ cls, int nx, int ny, int accGrad,
+                      int low_thr, int high_thr) {
   __shared__ float sd[CG_DW * CG_DW];
   __shared__ double sg[CG_GW * CG_GW], sh[CG_GW * CG_GW], sv[CG_GW * CG_GW];
   const int x0 = blockIdx.x * CG_T, y0 = blockIdx.y * CG_T;
@@ -297,12 +297,6 @@ canny_grad_nms_kernel(const float *__restrict__ data, unsigned char *__restrict_
       else c = 1;
     }
     if (inimg) cls[(size_t)blockIdx.z * nx * ny + (size_t)gy * nx + gx] = c;
-    // one bit per pixel for the propagation kernels: word r of this tile = row y0+r, bit x = column x0+x
-    const unsigned eb = __ballot_sync(0xffffffffu, c != 0), sb = __ballot_sync(0xffffffffu, c == 2);
-    if (lx == 0 && gy < ny) {
-      const size_t w = ((size_t)blockIdx.z * ny + gy) * gridDim.x + blockIdx.x;        // row-major bit planes
-      Ebits[w] = eb; Sbits[w] = sb;
-    }
   }
 }
 
@@ -366,9 +360,8 @@ __device__ __noinline__ unsigned char canny_exact_class(const float *sd, int x0,
 }
 
 __global__ void __launch_bounds__(CG_NT)
-canny_grad_nms_spec_kernel(const float *__restrict__ data, unsigned char *__restrict__ cls, unsigned *__restrict__ Ebits,
-                           unsigned *__restrict__ Sbits, int nx, int ny, int accGrad, int low_thr, int high_thr,
-                           unsigned long long *__restrict__ fallback_count) {
+canny_grad_nms_spec_kernel(const float *__restrict__ data, unsigned char *__restrict__ cls, int nx, int ny, int accGrad,
+                           int low_thr, int high_thr, unsigned long long *__restrict__ fallback_count) {
   __shared__ float sd[CG_DW * CG_DW];
   __shared__ float fg[CG_GW * CG_GW], fh[CG_GW * CG_GW], fv[CG_GW * CG_GW];
   const int x0 = blockIdx.x * CG_T, y0 = blockIdx.y * CG_T;
@@ -411,6 +404,7 @@ canny_grad_nms_spec_kernel(const float *__restrict__ data, unsigned char *__rest
   const float lowf = (float)low_thr, highf = (float)high_thr;
   __shared__ unsigned char scls[CG_T * CG_T];
   __shared__ unsigned short squeue[CG_T * CG_T];
+  __shared__ double sg2[28 * 9];
   __shared__ int qn;
   if (threadIdx.x == 0) qn = 0;
   __syncthreads();
@@ -461,23 +455,65 @@ canny_grad_nms_spec_kernel(const float *__restrict__ data, unsigned char *__rest
     scls[t] = c;
   }
   __syncthreads();
-  // tier 2: the undecided pixels of this tile, one thread each (no divergence against decided lanes)
+  // tier 2: the undecided pixels of this tile.  Their exact magnitudes are needed on the 3x3 block
+  // around each of them (the bilinear corners lie there): one thread per (pixel, block position) does
+  // one glibc-exact hypot, then one thread per pixel finishes the reference's double arithmetic.
   const int nq = qn;
-  for (int i = threadIdx.x; i < nq; i += CG_NT) {
-    const int t = squeue[i], ly = t / CG_T, lx = t - ly * CG_T;
-    scls[t] = canny_exact_class(sd, x0, y0, x0 + lx, y0 + ly, nx, ny, accGrad, low_thr, high_thr);
+  double *eg = sg2;                                              // [chunk][9]
+  for (int qb = 0; qb < nq; qb += 28) {
+    const int nc = min(28, nq - qb);
+    for (int i = threadIdx.x; i < nc * 9; i += CG_NT) {
+      const int qi = i / 9, k = i - qi * 9;
+      const int t = squeue[qb + qi], ly = t / CG_T, lx = t - ly * CG_T;
+      const int px = min(max(x0 + lx + (k % 3) - 1, 0), nx - 1), py = min(max(y0 + ly + (k / 3) - 1, 0), ny - 1);
+      double h, v;
+      exact_hv(sd + (py - (y0 - 3)) * CG_DW + (px - (x0 - 3)), accGrad, h, v);
+      eg[i] = hypot_glibc(h, v);
+    }
+    __syncthreads();
+    for (int qi = threadIdx.x; qi < nc; qi += CG_NT) {
+      const int t = squeue[qb + qi], ly = t / CG_T, lx = t - ly * CG_T;
+      const int gx = x0 + lx, gy = y0 + ly;
+      const double *g9 = eg + qi * 9;
+      double h, v;
+      exact_hv(sd + (gy - (y0 - 3)) * CG_DW + (gx - (x0 - 3)), accGrad, h, v);
+      const double now = g9[4];
+      unsigned char c;
+      if (now <= (double)low_thr) c = 0;
+      else {
+        double sn, cs;
+        if (h == 0.0 || v == 0.0) { const double th = atan2(v, h); sincos(th, &sn, &cs); }
+        else { const double inv = __ddiv_rn(1.0, now); cs = __dmul_rn(h, inv); sn = __dmul_rn(v, inv); }
+        double nb[2];
+        for (int s2 = 0; s2 < 2; s2++) {
+          const double dir = s2 ? 1.0 : -1.0;
+          const double xt = __dmul_rn(dir, cs), yt = __dmul_rn(dir, sn);
+          const double x1 = floor(xt), x2 = __dadd_rn(x1, 1.0), y1 = floor(yt), y2 = __dadd_rn(y1, 1.0);
+          // block index of a corner: offsets are in {-1,0,1}; an offset of 2 only occurs with weight exactly 0
+          auto G = [&](double ox, double oy) -> double {
+            const int ix = (int)ox, iy = (int)oy;
+            if (ix > 1 || iy > 1) return 0.0;                    // multiplied by a zero weight (xt or yt == 1)
+            // value(): the neighbour coordinate is clamped to the image, like the block was built
+            const int cxp = min(max(gx + ix, 0), nx - 1) - gx, cyp = min(max(gy + iy, 0), ny - 1) - gy;
+            return g9[(cyp + 1) * 3 + (cxp + 1)];
+          };
+          const double wa = __dsub_rn(x2, xt), wb = __dsub_rn(xt, x1);
+          const double g1 = __dadd_rn(__dmul_rn(wa, G(x1, y1)), __dmul_rn(wb, G(x2, y1)));
+          const double g2 = __dadd_rn(__dmul_rn(wa, G(x1, y2)), __dmul_rn(wb, G(x2, y2)));
+          nb[s2] = __dadd_rn(__dmul_rn(__dsub_rn(y2, yt), g1), __dmul_rn(__dsub_rn(yt, y1), g2));
+        }
+        if (now <= nb[0] || now <= nb[1]) c = 0;
+        else c = now >= (double)high_thr ? 2 : 1;
+      }
+      scls[t] = c;
+    }
+    __syncthreads();
   }
-  __syncthreads();
   for (int t = threadIdx.x; t < CG_T * CG_T; t += CG_NT) {
     const int ly = t / CG_T, lx = t - ly * CG_T;
     const int gx = x0 + lx, gy = y0 + ly;
     const unsigned char c = scls[t];
     if (gx < nx && gy < ny) cls[(size_t)blockIdx.z * nx * ny + (size_t)gy * nx + gx] = c;
-    const unsigned eb = __ballot_sync(0xffffffffu, c != 0), sb = __ballot_sync(0xffffffffu, c == 2);
-    if (lx == 0 && gy < ny) {
-      const size_t w = ((size_t)blockIdx.z * ny + gy) * gridDim.x + blockIdx.x;      // row-major bit planes
-      Ebits[w] = eb; Sbits[w] = sb;
-    }
   }
   if (fallback_count && threadIdx.x == 0 && nq) atomicAdd(fallback_count, (unsigned long long)nq);
 }
@@ -699,117 +735,6 @@ __global__ void hyst_emit(const unsigned char *__restrict__ cls, const int *__re
   if (threadIdx.x == 0 && cnt) atomicAdd(&nonzero[f], cnt);
 }
 
-// ------------------------------------------------------------------------------------------ hysteresis, fast path
-// Breadth-first flood from the class-2 pixels over the class != 0 pixels on 1-bit-per-pixel planes
-// (row-major, 32 pixels per word).  Reached set R starts as the strong set; a frontier pixel tests its
-// 8 neighbours, claims each unreached edge neighbour with one atomicOr on R and appends it to the next
-// frontier.  One persistent cooperative kernel runs all levels (grid-wide barrier between levels), so
-// the whole batch costs  (#levels x barrier) + O(reached pixels)  instead of passes over every tile.
-// Same result as the reference's union-find (rcpp_canny.cpp:184-215): the union of the components
-// that contain a strong pixel.  If a frontier overflows its queue the caller falls back to the
-// two-level union-find below (status = 2).
-}  // namespace b2f
-#include <cooperative_groups.h>
-namespace b2f {
-namespace cg = cooperative_groups;
-
-__global__ void hyst_seed_kernel(const unsigned *__restrict__ Sbits, int *__restrict__ queue, int *__restrict__ qcount,
-                                 int cap, size_t n_words, int wpr, int ny) {
-  // every strong pixel is a level-0 frontier entry: value = global pixel id  (f*ny + y)*wpr*32 + x
-  size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned bits = w < n_words ? Sbits[w] : 0u;
-  const int cnt = __popc(bits);
-  // warp-aggregated reservation
-  int incl = cnt;
-  const int lane = threadIdx.x & 31;
-  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-  const int total = __shfl_sync(0xffffffffu, incl, 31);
-  int base = 0;
-  if (lane == 31 && total) base = atomicAdd(qcount, total);
-  base = __shfl_sync(0xffffffffu, base, 31);
-  int pos = base + incl - cnt;
-  while (bits) {
-    const int b = __ffs(bits) - 1;
-    bits &= bits - 1;
-    if (pos < cap) queue[pos] = (int)(w * 32 + b);
-    pos++;
-  }
-}
-
-__global__ void __launch_bounds__(256)
-hyst_bfs_kernel(const unsigned *__restrict__ Ebits, unsigned *__restrict__ Rbits, int *__restrict__ qa, int *__restrict__ qb,
-                int *__restrict__ counts /* [0]=|qa| [1]=|qb| [2]=status */, int cap, int wpr, int nx, int ny) {
-  cg::grid_group grid = cg::this_grid();
-  const int rowpix = wpr * 32;
-  int *cur = qa, *nxt = qb;
-  int ci = 0;
-  volatile int *vc = counts;                                    // counters and queues are re-read every level: bypass L1
-  if (vc[0] > cap) { if (grid.thread_rank() == 0) vc[2] = 2; return; }              // seed overflow (uniform exit)
-  for (int level = 0;; level++) {
-    const int n = vc[ci];
-    if (n == 0) break;
-    for (size_t i = grid.thread_rank(); i < (size_t)n; i += grid.size()) {
-      const int p = __ldcg(cur + i);
-      const int row = p / rowpix, x = p - row * rowpix;             // row = f*ny + y
-      const int y = row % ny;
-#pragma unroll
-      for (int dy = -1; dy <= 1; dy++) {
-        const int yy = y + dy;
-        if (yy < 0 || yy >= ny) continue;
-#pragma unroll
-        for (int dx = -1; dx <= 1; dx++) {
-          if (dx == 0 && dy == 0) continue;
-          const int xx = x + dx;
-          if (xx < 0 || xx >= nx) continue;
-          const size_t w = (size_t)(row + dy) * wpr + (xx >> 5);
-          const unsigned bit = 1u << (xx & 31);
-          if (!(__ldg(Ebits + w) & bit)) continue;
-          if (Rbits[w] & bit) continue;                              // cheap pre-test
-          const unsigned old = atomicOr(&Rbits[w], bit);
-          if (old & bit) continue;
-          const int slot = atomicAdd(&counts[1 - ci], 1);
-          if (slot < cap) nxt[slot] = (row + dy) * rowpix + xx;
-        }
-      }
-    }
-    grid.sync();
-    if (vc[1 - ci] > cap) { if (grid.thread_rank() == 0) vc[2] = 2; break; }           // uniform: same value for all
-    if (grid.thread_rank() == 0) vc[ci] = 0;
-    int *t = cur; cur = nxt; nxt = t;
-    ci = 1 - ci;
-    grid.sync();
-  }
-}
-
-// edges (0/255 bytes) and per-frame counts from the reached bits: one thread = one 32-pixel word
-__global__ void hyst_emit_bits_kernel(const unsigned *__restrict__ Rbits, unsigned char *__restrict__ edges,
-                                      int *__restrict__ nonzero, int nx, int ny, int wpr) {
-  const int wx = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
-  int cnt = 0;
-  if (wx < wpr) {
-    const unsigned w = Rbits[((size_t)f * ny + y) * wpr + wx];
-    unsigned char *dst = edges + (size_t)f * nx * ny + (size_t)y * nx + (size_t)wx * 32;
-    const int valid = min(32, nx - wx * 32);
-    if (valid == 32 && (nx & 15) == 0 && (reinterpret_cast<uintptr_t>(edges) & 15) == 0) {
-#pragma unroll
-      for (int q = 0; q < 2; q++) {
-        unsigned v[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const unsigned nib = (w >> (16 * q + 4 * k)) & 0xfu;
-          v[k] = ((nib & 1u) ? 0xffu : 0u) | ((nib & 2u) ? 0xff00u : 0u) | ((nib & 4u) ? 0xff0000u : 0u) | ((nib & 8u) ? 0xff000000u : 0u);
-        }
-        reinterpret_cast<uint4 *>(dst)[q] = make_uint4(v[0], v[1], v[2], v[3]);
-      }
-    } else {
-      for (int b = 0; b < valid; b++) dst[b] = ((w >> b) & 1u) ? 255 : 0;
-    }
-    cnt = __popc(valid == 32 ? w : (w & ((1u << valid) - 1u)));
-  }
-  for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&nonzero[f], cnt);
-}
-
 // ------------------------------------------------------------------------------------------ host
 // tap list of one axis: orc_canny_taps restated (tools.c:146-163): wrap coordinates, exp(-c^2/s^2),
 // unit sum over the full period, taps below 2^-64 dropped.
@@ -853,8 +778,6 @@ int canny_device(b2f_ctx *ctx, const unsigned char *d_frames, int n_frames, int 
   int *L = ctx->arena.get<int>(n);
   unsigned char *strong = ctx->arena.get<unsigned char>(n);
   unsigned char *rinfo = ctx->arena.get<unsigned char>(n);
-  const size_t n_words = (size_t)ceil_div(nx, 32) * ny * n_frames;                  // row-major bit planes
-  unsigned *Ebits = ctx->arena.get<unsigned>(n_words), *Sbits = ctx->arena.get<unsigned>(n_words);
   int *flags = ctx->arena.get<int>(64);
   std::vector<int> cx, cy; std::vector<double> wx, wy;
   make_taps(nx, s, cx, wx); make_taps(ny, s, cy, wy);
@@ -890,45 +813,28 @@ int canny_device(b2f_ctx *ctx, const unsigned char *d_frames, int n_frames, int 
     canny_blur_generic_cols<<<grid, 128, 0, st>>>(tmp, blur, nx, ny, TapList{dcx + cx.size(), dwx + wx.size(), (int)cy.size(), sym ? 1 : 0});
     B2F_LAUNCH_CHECK(ctx);
   }
-  const int TX = ceil_div(nx, CG_T), TY = ceil_div(ny, CG_T), wpr = TX;
+  const int TX = ceil_div(nx, CG_T), TY = ceil_div(ny, CG_T);
   static const bool force_exact = getenv("B2F_CANNY_EXACT") != nullptr;
   if (force_exact)
     canny_grad_nms_kernel<<<dim3(TX, TY, n_frames), CG_NT, 0, st>>>(
-        blur, cls, Ebits, Sbits, nx, ny, acc_grad ? 1 : 0, (int)low_thr, (int)high_thr);   // thresholds truncate like rcpp_canny.cpp:180
+        blur, cls, nx, ny, acc_grad ? 1 : 0, (int)low_thr, (int)high_thr);   // thresholds truncate like rcpp_canny.cpp:180
   else
+  {
+    static const bool stats = getenv("B2F_CANNY_STATS") != nullptr;
+    unsigned long long *fc = stats ? reinterpret_cast<unsigned long long *>(flags + 8) : nullptr;
+    if (stats) B2F_CUDA(cudaMemsetAsync(fc, 0, 8, st));
     canny_grad_nms_spec_kernel<<<dim3(TX, TY, n_frames), CG_NT, 0, st>>>(
-        blur, cls, Ebits, Sbits, nx, ny, acc_grad ? 1 : 0, (int)low_thr, (int)high_thr, nullptr);
+        blur, cls, nx, ny, acc_grad ? 1 : 0, (int)low_thr, (int)high_thr, fc);
+    if (stats) {
+      unsigned long long h = 0;
+      B2F_CUDA(cudaMemcpyAsync(&h, fc, 8, cudaMemcpyDeviceToHost, st));
+      B2F_CUDA(cudaStreamSynchronize(st));
+      fprintf(stderr, "[b2f] canny tier-2 pixels: %llu of %zu (%.3f %%)\n", h, n, 100.0 * (double)h / (double)n);
+    }
+  }
   B2F_LAUNCH_CHECK(ctx);
   B2F_CUDA(cudaMemsetAsync(d_nonzero, 0, sizeof(int) * n_frames, st));
-  // ---- hysteresis, fast path: cooperative BFS on the bit planes (queues live in the label plane L)
-  static const bool force_uf = getenv("B2F_CANNY_UNIONFIND") != nullptr;
-  int status = 2;
-  if (!force_uf && (size_t)n_frames * ny * wpr * 32 < ((size_t)1 << 31)) {
-    const size_t words = (size_t)n_frames * ny * wpr;
-    const int cap = (int)std::min<size_t>(n / 2, (size_t)1 << 30);
-    int *qa = L, *qb = L + cap;
-    B2F_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * 4, st));
-    hyst_seed_kernel<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(Sbits, qa, flags, cap, words, wpr, ny);
-    B2F_LAUNCH_CHECK(ctx);
-    static int coop_blocks = 0;
-    if (!coop_blocks) {
-      int per_sm = 0;
-      B2F_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hyst_bfs_kernel, 256, 0));
-      coop_blocks = std::max(1, per_sm) * ctx->sm_count;
-    }
-    const unsigned *Ep = Ebits; unsigned *Rp = Sbits; int *cnts = flags; int capv = cap, wprv = wpr, nxv = nx, nyv = ny;
-    void *args[] = {(void *)&Ep, (void *)&Rp, (void *)&qa, (void *)&qb, (void *)&cnts, (void *)&capv, (void *)&wprv, (void *)&nxv, (void *)&nyv};
-    B2F_CUDA(cudaLaunchCooperativeKernel((const void *)hyst_bfs_kernel, dim3(coop_blocks), dim3(256), args, 0, st));
-    ctx->launches++;
-    B2F_CUDA(cudaMemcpyAsync(&status, flags + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
-    B2F_CUDA(cudaStreamSynchronize(st));      // one host decision per call: did a queue overflow?
-  }
-  if (status == 0) {
-    hyst_emit_bits_kernel<<<dim3(ceil_div(wpr, 64), ny, n_frames), 64, 0, st>>>(Sbits, d_edges, d_nonzero, nx, ny, wpr);
-    B2F_LAUNCH_CHECK(ctx);
-    return B2F_OK;
-  }
-  // ---- fallback (queue overflow, or forced): two-level union-find on the class bytes, always exact
+  // ---- hysteresis: two-level union-find on the class bytes (tile-local in shared memory, seams with atomicMin)
   B2F_CUDA(cudaMemsetAsync(strong, 0, n, st));
   dim3 tiles(ceil_div(nx, HT), ceil_div(ny, HT), n_frames);
   hyst_local_kernel<<<tiles, 256, 0, st>>>(cls, L, rinfo, nx, ny);
