@@ -27,7 +27,7 @@ struct CannyTaps {
 };
 
 // ------------------------------------------------------------------------------------------ blur
-constexpr int CB_TW = 32, CB_TH = 128, CB_NT = 256;
+constexpr int CB_TW = 32, CB_TH = 64, CB_NT = 256;     // (64+2R) x (32+2R) doubles + row buffer = 65 KB at R=13: 3 CTAs / SM
 
 __device__ __forceinline__ int wrap_index(int p, int n) {   // circular addressing, tools.c:151-155
   while (p < 0) p += n;
@@ -38,7 +38,7 @@ __device__ __forceinline__ int wrap_index(int p, int n) {   // circular addressi
 // Shared memory: the input tile is converted to double ONCE at load time (u8 -> double is exact),
 // so both passes are pure DADD/DMUL streams: pair sum, product, accumulate (40 fp64 ops / output).
 template <int RT>
-__global__ void __launch_bounds__(CB_NT)
+__global__ void __launch_bounds__(CB_NT, 3)
 canny_blur_kernel(const unsigned char *__restrict__ frames, float *__restrict__ out, int nx, int ny,
                   const __grid_constant__ CannyTaps tx, const __grid_constant__ CannyTaps ty) {
   extern __shared__ __align__(16) double smem_d[];
@@ -325,38 +325,6 @@ __device__ __forceinline__ void exact_hv(const float *d, int accGrad, double &h,
     v = __dsub_rn(DD(0, 1), DD(0, -1));
   }
 #undef DD
-}
-
-// exact class of pixel (gx,gy) from the clamped float data tile (tile entry (i,j) <-> pixel
-// (x0-3+i, y0-3+j) clamped) — the reference's arithmetic, operation by operation.
-__device__ __noinline__ unsigned char canny_exact_class(const float *sd, int x0, int y0, int gx, int gy, int nx, int ny,
-                                                        int accGrad, int low_thr, int high_thr) {
-  auto grad_at = [&](int px, int py) -> double {      // magnitude at image pixel (px,py) (already clamped)
-    double h, v;
-    exact_hv(sd + (py - (y0 - 3)) * CG_DW + (px - (x0 - 3)), accGrad, h, v);
-    return hypot_glibc(h, v);
-  };
-  double h, v;
-  exact_hv(sd + (gy - (y0 - 3)) * CG_DW + (gx - (x0 - 3)), accGrad, h, v);
-  const double now = hypot_glibc(h, v);
-  if (now <= (double)low_thr) return 0;
-  double sn, cs;
-  if (h == 0.0 || v == 0.0) { const double th = atan2(v, h); sincos(th, &sn, &cs); }
-  else { const double inv = __ddiv_rn(1.0, now); cs = __dmul_rn(h, inv); sn = __dmul_rn(v, inv); }
-  double nb[2];
-  for (int s = 0; s < 2; s++) {
-    const double dir = s ? 1.0 : -1.0;
-    const double xt = __dmul_rn(dir, cs), yt = __dmul_rn(dir, sn);
-    const double x1 = floor(xt), x2 = __dadd_rn(x1, 1.0), y1 = floor(yt), y2 = __dadd_rn(y1, 1.0);
-    const int ax1 = min(max(gx + (int)x1, 0), nx - 1), ax2 = min(max(gx + (int)x2, 0), nx - 1);
-    const int ay1 = min(max(gy + (int)y1, 0), ny - 1), ay2 = min(max(gy + (int)y2, 0), ny - 1);
-    const double wa = __dsub_rn(x2, xt), wb = __dsub_rn(xt, x1);
-    const double g1 = __dadd_rn(__dmul_rn(wa, grad_at(ax1, ay1)), __dmul_rn(wb, grad_at(ax2, ay1)));
-    const double g2 = __dadd_rn(__dmul_rn(wa, grad_at(ax1, ay2)), __dmul_rn(wb, grad_at(ax2, ay2)));
-    nb[s] = __dadd_rn(__dmul_rn(__dsub_rn(y2, yt), g1), __dmul_rn(__dsub_rn(yt, y1), g2));
-  }
-  if (now <= nb[0] || now <= nb[1]) return 0;
-  return now >= (double)high_thr ? 2 : 1;
 }
 
 __global__ void __launch_bounds__(CG_NT)

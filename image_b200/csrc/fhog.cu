@@ -152,45 +152,57 @@ fhog_cell_kernel(const float *__restrict__ vmag, const unsigned char *__restrict
     const int ya = tb.ylo[R], yb = tb.yhi[R], xa = tb.xlo[C], xb = tb.xhi[C];
     float *h = sh + threadIdx.x;
     float *wxs = swx + threadIdx.x;
+    int *sidx = reinterpret_cast<int *>(swx + (size_t)KW * FC_NT) + threadIdx.x;
     const int nxw = min(xb - xa, KW);
-    // x weight of pixel xa+k for THIS cell; a set sign bit marks the scalar-tail product order
-    for (int k = 0; k < nxw; k++) {
-      const int x = xa + k;
-      const float wx = (__ldg(tb.c0 + x) == C) ? __ldg(tb.vx1 + x) : __ldg(tb.vx0 + x);
-      wxs[k * FC_NT] = (x < g.simd_end) ? wx : -wx;
+    // per-thread tables over the cell's columns: x weight (sign bit = scalar-tail product order) and the
+    // offset of column xa+k inside a de-interleaved plane row
+    {
+      const int NCB = PW / g.cell;
+      int ph = xa % g.cell, q = xa / g.cell;
+      for (int k = 0; k < nxw; k++) {
+        const int x = xa + k;
+        const float wx = (__ldg(tb.c0 + x) == C) ? __ldg(tb.vx1 + x) : __ldg(tb.vx0 + x);
+        wxs[k * FC_NT] = (x < g.simd_end) ? wx : -wx;
+        sidx[k * FC_NT] = ph * NCB + q;
+        if (++ph == g.cell) { ph = 0; q++; }
+      }
     }
-    // column offsets advance incrementally (no dependent table load); the loads of a chunk of 8
-    // pixels are issued together so the sequential adds do not wait on memory one by one
-    const int NCB = PW / g.cell;
-    const int ph0 = xa % g.cell, q0 = xa / g.cell;
+    const int nfull = (xb - xa <= KW) ? nxw : 0;               // table-driven fast loop when the range is cached
     for (int y = ya; y < yb; y++) {
       const float wy = (__ldg(tb.r0 + y) == R) ? __ldg(tb.vy1 + y) : __ldg(tb.vy0 + y);
       const float *vrow = vin + (size_t)y * PW;
       const unsigned char *orow = oin + (size_t)y * PW;
-      int ph = ph0, q = q0;
-      for (int xc = xa; xc < xb; xc += 8) {
+      int k = 0;
+      for (; k + 8 <= nfull; k += 8) {                          // 8 independent loads in flight, then 8 sequential adds
         float v[8]; int o[8];
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-          const int idx = ph * NCB + q;
-          const bool in = xc + j < xb;
-          v[j] = in ? __ldg(vrow + idx) : 0.f;
-          o[j] = in ? (int)__ldg(orow + idx) : 0;
-          if (++ph == g.cell) { ph = 0; q++; }
-        }
+        for (int j = 0; j < 8; j++) { const int idx = sidx[(k + j) * FC_NT]; v[j] = __ldg(vrow + idx); o[j] = (int)__ldg(orow + idx); }
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-          const int x = xc + j;
-          if (x >= xb) break;
-          const int k = x - xa;
-          float wq;
-          if (k < KW) wq = wxs[k * FC_NT];
-          else { const float wx = (__ldg(tb.c0 + x) == C) ? __ldg(tb.vx1 + x) : __ldg(tb.vx0 + x); wq = (x < g.simd_end) ? wx : -wx; }
-          // simd body: vy*(vx*v) (fhog.h:867-874) ; scalar tail: (vy*vx)*v (fhog.h:951-954)
-          const bool tail = __float_as_int(wq) < 0;
+          const float wq = wxs[(k + j) * FC_NT];
           const float wx = fabsf(wq);
-          const float val = tail ? __fmul_rn(__fmul_rn(wy, wx), v[j]) : __fmul_rn(wy, __fmul_rn(wx, v[j]));
+          // simd body: vy*(vx*v) (fhog.h:867-874) ; scalar tail: (vy*vx)*v (fhog.h:951-954)
+          const float val = (__float_as_int(wq) < 0) ? __fmul_rn(__fmul_rn(wy, wx), v[j]) : __fmul_rn(wy, __fmul_rn(wx, v[j]));
           h[o[j] * FC_NT] = __fadd_rn(h[o[j] * FC_NT], val);
+        }
+      }
+      for (; k < nfull; k++) {
+        const int idx = sidx[k * FC_NT];
+        const float v = __ldg(vrow + idx); const int o = (int)__ldg(orow + idx);
+        const float wq = wxs[k * FC_NT], wx = fabsf(wq);
+        const float val = (__float_as_int(wq) < 0) ? __fmul_rn(__fmul_rn(wy, wx), v) : __fmul_rn(wy, __fmul_rn(wx, v));
+        h[o * FC_NT] = __fadd_rn(h[o * FC_NT], val);
+      }
+      if (!nfull) {                                             // very large cells: no tables, direct evaluation
+        const int NCB = PW / g.cell;
+        int ph = xa % g.cell, q = xa / g.cell;
+        for (int x = xa; x < xb; x++) {
+          const float wx = (__ldg(tb.c0 + x) == C) ? __ldg(tb.vx1 + x) : __ldg(tb.vx0 + x);
+          const int idx = ph * NCB + q;
+          const float v = __ldg(vrow + idx); const int o = (int)__ldg(orow + idx);
+          const float val = (x < g.simd_end) ? __fmul_rn(wy, __fmul_rn(wx, v)) : __fmul_rn(__fmul_rn(wy, wx), v);
+          h[o * FC_NT] = __fadd_rn(h[o * FC_NT], val);
+          if (++ph == g.cell) { ph = 0; q++; }
         }
       }
     }
@@ -358,7 +370,7 @@ int fhog_device(b2f_ctx *ctx, const unsigned char *d_frames, int n_frames, const
     int maxw = 1;
     for (int C = 0; C < HC; C++) maxw = std::max(maxw, xhi[C] - xlo[C]);
     const int KW = std::min(maxw, 96);
-    size_t smem = sizeof(float) * (size_t)(18 + KW) * FC_NT;
+    size_t smem = sizeof(float) * (size_t)(18 + 2 * KW) * FC_NT;   // histogram + x weights + column offsets
     B2F_CUDA(cudaFuncSetAttribute(fhog_cell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     fhog_cell_kernel<<<dim3(ceil_div(HC, FC_NT), HR, n_frames), FC_NT, smem, st>>>(vmag, obin, hist, g, tb, d_colidx, PW, KW);
     B2F_LAUNCH_CHECK(ctx);

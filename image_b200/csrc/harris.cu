@@ -168,6 +168,93 @@ nms_bitmask_kernel(const float *__restrict__ R, unsigned *__restrict__ mask, int
   }
 }
 
+// Fast variant for a compile-time radius: separable window maximum first (row pass, column pass in
+// shared memory), so that only pixels equal to their window maximum — a handful per tile — run the
+// exact asymmetric predicate.  Same result as nms_bitmask_kernel.
+template <int RAD>
+__global__ void __launch_bounds__(NMS_NT)
+nms_bitmask_sep_kernel(const float *__restrict__ R, unsigned *__restrict__ mask, int nx, int ny, int words_per_row, float Th) {
+  constexpr int P = NMS_TW + 2 * RAD, TH2 = NMS_TH + 2 * RAD;
+  __shared__ float tile[TH2 * P];
+  __shared__ float rmax[TH2 * NMS_TW];
+  const int x0 = blockIdx.x * NMS_TW, y0 = blockIdx.y * NMS_TH;
+  const float *Rf = R + (size_t)nx * ny * blockIdx.z;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  {   // tile rows are streamed by warps; the loads of several rows are issued before the stores
+    constexpr int NCH = (P + 31) / 32;                          // column chunks per row (5)
+    constexpr int RPW = (TH2 + 7) / 8;                          // rows per warp (4)
+    float v[RPW][NCH];
+#pragma unroll
+    for (int k = 0; k < RPW; k++) {
+      const int r = warp + 8 * k, gy = y0 - RAD + r;
+      const bool rowok = r < TH2 && gy >= 0 && gy < ny;
+      const float *src = Rf + (size_t)(rowok ? gy : 0) * nx;
+#pragma unroll
+      for (int q = 0; q < NCH; q++) {
+        const int c = lane + 32 * q, gx = x0 - RAD + c;
+        v[k][q] = (rowok && c < P && gx >= 0 && gx < nx) ? __ldg(src + gx) : -INFINITY;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < RPW; k++) {
+      const int r = warp + 8 * k;
+      if (r < TH2) {
+#pragma unroll
+        for (int q = 0; q < NCH; q++) { const int c = lane + 32 * q; if (c < P) tile[r * P + c] = v[k][q]; }
+      }
+    }
+  }
+  __syncthreads();
+  // row pass: 4 consecutive outputs per item share the middle of their windows
+  for (int it = threadIdx.x; it < TH2 * (NMS_TW / 4); it += NMS_NT) {
+    const int r = it / (NMS_TW / 4), g = it - r * (NMS_TW / 4);
+    const float *p = tile + r * P + 4 * g;                      // output col j covers tile cols j .. j+2*RAD
+    float v[4 + 2 * RAD];
+#pragma unroll
+    for (int q = 0; q < 4 + 2 * RAD; q++) v[q] = p[q];
+    float mid = v[3];
+#pragma unroll
+    for (int q = 4; q <= 2 * RAD; q++) mid = fmaxf(mid, v[q]);  // cols 3 .. 2*RAD are in all four windows
+    float o0 = fmaxf(fmaxf(mid, v[0]), fmaxf(v[1], v[2]));
+    float o1 = fmaxf(fmaxf(mid, v[1]), fmaxf(v[2], v[2 * RAD + 1]));
+    float o2 = fmaxf(fmaxf(mid, v[2]), fmaxf(v[2 * RAD + 1], v[2 * RAD + 2]));
+    float o3 = fmaxf(fmaxf(mid, v[2 * RAD + 1]), fmaxf(v[2 * RAD + 2], v[2 * RAD + 3]));
+    *reinterpret_cast<float4 *>(rmax + r * NMS_TW + 4 * g) = make_float4(o0, o1, o2, o3);
+  }
+  __syncthreads();
+  // column pass + candidate test: thread = (column, group of 8 rows); lanes of a warp = 32 consecutive columns
+  {
+    const int col = threadIdx.x & (NMS_TW - 1), rg = threadIdx.x / NMS_TW;       // 2 row groups
+    float v[8 + 2 * RAD];
+#pragma unroll
+    for (int q = 0; q < 8 + 2 * RAD; q++) v[q] = rmax[(rg * 8 + q) * NMS_TW + col];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      float m = v[j];
+#pragma unroll
+      for (int q = 1; q <= 2 * RAD; q++) m = fmaxf(m, v[j + q]);
+      const int row = rg * 8 + j, gx = x0 + col, gy = y0 + row;
+      const float *c = tile + (row + RAD) * P + col + RAD;
+      const float val = *c;
+      bool ok = gx >= RAD && gx < nx - RAD && gy >= RAD && gy < ny - RAD && !(val < Th) && val >= m;
+      if (ok) {       // val equals its window maximum: apply the reference's tie rules exactly
+        for (int dy = -RAD; dy <= RAD && ok; dy++) {
+          const float *q = c + dy * P;
+          if (dy < 0) { for (int dx = -RAD; dx <= RAD; dx++) ok = ok && (val > q[dx]); }
+          else if (dy > 0) { for (int dx = -RAD; dx <= RAD; dx++) ok = ok && (val >= q[dx]); }
+          else {
+            for (int dx = -RAD; dx < 0; dx++) ok = ok && (val >= q[dx]);
+            for (int dx = 1; dx <= RAD; dx++) ok = ok && (val > q[dx]);
+          }
+        }
+      }
+      const unsigned bits = __ballot_sync(0xffffffffu, ok);
+      const int word = (x0 >> 5) + (col >> 5);
+      if (lane == 0 && gy < ny && word < words_per_row) mask[((size_t)blockIdx.z * ny + gy) * words_per_row + word] = bits;
+    }
+  }
+}
+
 // one warp per row: number of set bits of that row
 __global__ void row_count_kernel(const unsigned *__restrict__ mask, int *__restrict__ row_cnt, int ny, int words_per_row) {
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -420,7 +507,9 @@ int harris_nms_device(b2f_ctx *ctx, const float *d_R, int n_frames, int nx, int 
   if (smem > 200 * 1024) { set_error("harris: NMS radius %d too large", radius); return B2F_EUNSUP; }
   if (smem > 48 * 1024) B2F_CUDA(cudaFuncSetAttribute(nms_bitmask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(ceil_div(nx, NMS_TW), ceil_div(ny, NMS_TH), n_frames);
-  nms_bitmask_kernel<<<grid, NMS_NT, smem, st>>>(d_R, mask, nx, ny, wpr, Th, radius);
+  if (radius == 5) nms_bitmask_sep_kernel<5><<<grid, NMS_NT, 0, st>>>(d_R, mask, nx, ny, wpr, Th);
+  else if (radius == 3) nms_bitmask_sep_kernel<3><<<grid, NMS_NT, 0, st>>>(d_R, mask, nx, ny, wpr, Th);
+  else nms_bitmask_kernel<<<grid, NMS_NT, smem, st>>>(d_R, mask, nx, ny, wpr, Th, radius);
   B2F_LAUNCH_CHECK(ctx);
   row_count_kernel<<<dim3(ceil_div(ny, 8), n_frames), 256, 0, st>>>(mask, row_off, ny, wpr);
   B2F_LAUNCH_CHECK(ctx);
