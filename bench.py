@@ -294,18 +294,21 @@ def main():
     try:
         np_grey = h_grey.numpy()
         np_rgb = h_rgb.numpy()
+        # results land in pinned host buffers too (what a serving loop would keep allocated)
+        pin_edges = torch.empty((B, NY, NX), dtype=torch.uint8).pin_memory().numpy() if "canny" in dets else None
+        pin_hog = torch.empty((B, hnr, hnc, 31), dtype=torch.float32).pin_memory().numpy() if "fhog" in dets else None
 
         def step_e2e():
             nonlocal h2d, d2h
-            outs = H.harris_batch_u8(np_grey, cap=cap, precision=0, **HARRIS_KW)
+            hx, hy, hs, hc = H.harris_batch_u8(np_grey, cap=cap, raw=True, precision=0, **HARRIS_KW)
             h2d = np_grey.nbytes
-            d2h = sum(o["x"].nbytes * 3 for o in outs) + 4 * B
+            d2h = int(hc.sum()) * 8 + 4 * B
             if "canny" in dets:
-                e, nz = Cn.canny_batch(np_grey, **CANNY_KW)
+                e, nz = Cn.canny_batch(np_grey, out=pin_edges, **CANNY_KW)
                 h2d += np_grey.nbytes
                 d2h += e.nbytes + 4 * B
             if "fhog" in dets:
-                hog = Dl.fhog_batch(np_rgb, **FHOG_KW)
+                hog = Dl.fhog_batch(np_rgb, out=pin_hog, **FHOG_KW)
                 h2d += np_rgb.nbytes
                 d2h += hog.nbytes
         for _ in range(2):

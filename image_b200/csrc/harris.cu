@@ -174,14 +174,15 @@ nms_bitmask_kernel(const float *__restrict__ R, unsigned *__restrict__ mask, int
 template <int RAD>
 __global__ void __launch_bounds__(NMS_NT)
 nms_bitmask_sep_kernel(const float *__restrict__ R, unsigned *__restrict__ mask, int nx, int ny, int words_per_row, float Th) {
-  constexpr int P = NMS_TW + 2 * RAD, TH2 = NMS_TH + 2 * RAD;
-  __shared__ float tile[TH2 * P];
-  __shared__ float rmax[TH2 * NMS_TW];
+  constexpr int PW = NMS_TW + 2 * RAD, P = (PW + 3) & ~3, TH2 = NMS_TH + 2 * RAD;   // pitch multiple of 4: 16-byte row loads
+  __shared__ __align__(16) float tile[TH2 * P];
+
+  __shared__ __align__(16) float rmax[TH2 * NMS_TW];
   const int x0 = blockIdx.x * NMS_TW, y0 = blockIdx.y * NMS_TH;
   const float *Rf = R + (size_t)nx * ny * blockIdx.z;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   {   // tile rows are streamed by warps; the loads of several rows are issued before the stores
-    constexpr int NCH = (P + 31) / 32;                          // column chunks per row (5)
+    constexpr int NCH = (PW + 31) / 32;                         // column chunks per row (5)
     constexpr int RPW = (TH2 + 7) / 8;                          // rows per warp (4)
     float v[RPW][NCH];
 #pragma unroll
@@ -192,7 +193,7 @@ nms_bitmask_sep_kernel(const float *__restrict__ R, unsigned *__restrict__ mask,
 #pragma unroll
       for (int q = 0; q < NCH; q++) {
         const int c = lane + 32 * q, gx = x0 - RAD + c;
-        v[k][q] = (rowok && c < P && gx >= 0 && gx < nx) ? __ldg(src + gx) : -INFINITY;
+        v[k][q] = (rowok && c < PW && gx >= 0 && gx < nx) ? __ldg(src + gx) : -INFINITY;
       }
     }
 #pragma unroll
@@ -200,7 +201,7 @@ nms_bitmask_sep_kernel(const float *__restrict__ R, unsigned *__restrict__ mask,
       const int r = warp + 8 * k;
       if (r < TH2) {
 #pragma unroll
-        for (int q = 0; q < NCH; q++) { const int c = lane + 32 * q; if (c < P) tile[r * P + c] = v[k][q]; }
+        for (int q = 0; q < NCH; q++) { const int c = lane + 32 * q; if (c < PW) tile[r * P + c] = v[k][q]; }
       }
     }
   }
@@ -209,9 +210,13 @@ nms_bitmask_sep_kernel(const float *__restrict__ R, unsigned *__restrict__ mask,
   for (int it = threadIdx.x; it < TH2 * (NMS_TW / 4); it += NMS_NT) {
     const int r = it / (NMS_TW / 4), g = it - r * (NMS_TW / 4);
     const float *p = tile + r * P + 4 * g;                      // output col j covers tile cols j .. j+2*RAD
-    float v[4 + 2 * RAD];
+    constexpr int NV = (4 + 2 * RAD + 3) & ~3;
+    float v[NV];
 #pragma unroll
-    for (int q = 0; q < 4 + 2 * RAD; q++) v[q] = p[q];
+    for (int q = 0; q < NV / 4; q++) {
+      const float4 t = *reinterpret_cast<const float4 *>(p + 4 * q);
+      v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+    }
     float mid = v[3];
 #pragma unroll
     for (int q = 4; q <= 2 * RAD; q++) mid = fmaxf(mid, v[q]);  // cols 3 .. 2*RAD are in all four windows
