@@ -108,7 +108,7 @@ def run_reference(args, dets):
         po._cache.clear()
     kind = "reference" if all(po.have_ref(w) for w in ("harris", "canny", "dlib")) else "port"
     impl = "ref" if kind == "reference" else "oracle"
-    nf = max(1, args.ref_frames)
+    nf = max(1, args.ref_frames if args.ref_frames > 0 else min(cores, 16))
     rgb = [synth.frame_rgb(2000 + i, NY, NX) for i in range(nf)]
     grey = [np.ascontiguousarray(f[..., 1]) for f in rgb]
 
@@ -155,7 +155,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=16, help="4K frames per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--ref-frames", type=int, default=2)
+    ap.add_argument("--ref-frames", type=int, default=0, help="frames per reference step (0 = min(cores, 16))")
     ap.add_argument("--detectors", default="")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -277,14 +277,16 @@ def main():
     peak, peak_src = peaks()
     alg_bytes = 5.0 * B * NX * NY
     achieved = alg_bytes / (th * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "harris_fused_kernel<3,7,u8>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-            "algorithmic_bytes_per_launch": alg_bytes,
-            "note": "fp32-issue bound, not HBM bound: ~170 fp32 instructions per pixel (DESIGN.md §4)"}
+    roof = {"bound": "hbm", "kernel": "harris_fused2_kernel<3,7,u8> (+ border-ring launch of harris_fused_kernel)",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "frac_of_nominal_8000": achieved / 8000.0, "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": th,
+            "note": "this chain is fp32-FMA / shared-memory bound (>= 110 fp32 lane-ops per 5 algorithmic bytes): "
+                    "its HBM fraction cannot exceed ~24 % (DESIGN.md 4.1)"}
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            roof["traffic"] = json.load(open(tp)).get("harris_fused_bytes_per_launch_b%d" % B)
+            roof["traffic"] = json.load(open(tp)).get("harris_fused2_bytes_per_launch_b%d" % B)
         except Exception:
             pass
 
