@@ -90,8 +90,8 @@ def check(rc):
 def context(device=None):
     """One context per (thread, device), created lazily (R_init_<pkg> does the same in the R build)."""
     lib = load()
-    if device is None:
-        device = int(os.environ.get("LOCAL_RANK", "0")) if os.environ.get("B2F_DEVICE_FROM_RANK") else 0
+    if device is None:      # one process per GPU: B2F_DEVICE, else torchrun's LOCAL_RANK, else 0
+        device = int(os.environ.get("B2F_DEVICE", os.environ.get("LOCAL_RANK", "0")))
     key = (threading.get_ident(), device)
     with _lock:
         if key not in _ctx:
