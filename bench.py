@@ -217,13 +217,40 @@ def main():
         hnr, hnc = Dl.fhog_size(NY, NX, **FHOG_KW)
         d_hog = torch.empty((B, hnr, hnc, 31), dtype=torch.float32, device="cuda")
 
+    # The three detectors are independent: each gets its own context (stream + scratch) and they run
+    # concurrently, forked from / joined into the timing stream with events.
+    ctx_c = _lib.new_context(local) if "canny" in dets else None
+    ctx_f = _lib.new_context(local) if "fhog" in dets else None
+    st_c = torch.cuda.Stream() if "canny" in dets else None
+    st_f = torch.cuda.Stream() if "fhog" in dets else None
+    ev_fork = torch.cuda.Event()
+    ev_c, ev_f = torch.cuda.Event(), torch.cuda.Event()
+    serial = bool(os.environ.get("B2F_BENCH_SERIAL"))
+
     def step_dev():
+        if serial:
+            H.harris_response_dev(d_grey, True, B, NX, NY, d_R, stream=sp, **HARRIS_KW)
+            H.harris_nms_dev(d_R, B, NX, NY, HARRIS_KW["threshold"], radius, cap, d_xy, d_st, d_cnt, stream=sp)
+            if "canny" in dets:
+                Cn.canny_dev(d_grey, B, NX, NY, d_edges, d_nz, stream=sp, **CANNY_KW)
+            if "fhog" in dets:
+                Dl.fhog_dev(d_rgb, B, NY, NX, d_hog, stream=sp, **FHOG_KW)
+            return
+        ev_fork.record(stream)
+        if "canny" in dets:
+            st_c.wait_event(ev_fork)
+            Cn.canny_dev(d_grey, B, NX, NY, d_edges, d_nz, stream=st_c.cuda_stream, ctx=ctx_c, **CANNY_KW)
+            ev_c.record(st_c)
+        if "fhog" in dets:
+            st_f.wait_event(ev_fork)
+            Dl.fhog_dev(d_rgb, B, NY, NX, d_hog, stream=st_f.cuda_stream, ctx=ctx_f, **FHOG_KW)
+            ev_f.record(st_f)
         H.harris_response_dev(d_grey, True, B, NX, NY, d_R, stream=sp, **HARRIS_KW)
         H.harris_nms_dev(d_R, B, NX, NY, HARRIS_KW["threshold"], radius, cap, d_xy, d_st, d_cnt, stream=sp)
         if "canny" in dets:
-            Cn.canny_dev(d_grey, B, NX, NY, d_edges, d_nz, stream=sp, **CANNY_KW)
+            stream.wait_event(ev_c)
         if "fhog" in dets:
-            Dl.fhog_dev(d_rgb, B, NY, NX, d_hog, stream=sp, **FHOG_KW)
+            stream.wait_event(ev_f)
 
     def barrier():
         torch.cuda.synchronize()
@@ -249,12 +276,16 @@ def main():
     for _ in range(W):
         step_dev()
     l0 = lib.b2f_launch_count(ctx)
+    l0x = [lib.b2f_launch_count(cx) if cx is not None else 0 for cx in (ctx_c, ctx_f)]
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
     ms_total = timed(step_dev, K)
     launches = int(lib.b2f_launch_count(ctx) - l0)
+    for cx, base in zip((ctx_c, ctx_f), l0x):
+        if cx is not None:
+            launches += int(lib.b2f_launch_count(cx) - base)
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / K
     value = world * B * NX * NY / (ms_step * 1e-3) / 1e6

@@ -101,6 +101,19 @@ def context(device=None):
         return _ctx[key]
 
 
+def new_context(device=None):
+    """An additional context (own stream + scratch arena) on `device`; calls on different contexts may
+    run concurrently (bench.py gives each detector its own).  Released by shutdown()."""
+    lib = load()
+    if device is None:
+        device = int(os.environ.get("B2F_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    h = C.c_void_p()
+    check(lib.b2f_init(int(device), C.byref(h)))
+    with _lock:
+        _ctx[("extra", len(_ctx), device)] = h
+    return h
+
+
 def shutdown():
     lib = load()
     with _lock:

@@ -59,9 +59,9 @@ def canny_batch(frames, s=2.0, low_thr=3.0, high_thr=10.0, accGrad=True, out=Non
     return edges, nz
 
 
-def canny_dev(d_frames, n_frames, nx, ny, d_edges, d_nonzero, s=2.0, low_thr=3.0, high_thr=10.0, accGrad=True, stream=None):
+def canny_dev(d_frames, n_frames, nx, ny, d_edges, d_nonzero, s=2.0, low_thr=3.0, high_thr=10.0, accGrad=True, stream=None, ctx=None):
     lib = _lib.load()
-    _lib.check(lib.b2f_canny_dev(_lib.context(), _lib.ptr(d_frames), n_frames, nx, ny, float(s), float(low_thr),
+    _lib.check(lib.b2f_canny_dev(ctx or _lib.context(), _lib.ptr(d_frames), n_frames, nx, ny, float(s), float(low_thr),
                                  float(high_thr), int(bool(accGrad)), _lib.ptr(d_edges), _lib.ptr(d_nonzero),
                                  _lib.ptr(stream) if stream is not None else None))
 

@@ -65,9 +65,9 @@ def fhog_batch(frames, cell=8, frp=1, fcp=1, out=None):
     return hog
 
 
-def fhog_dev(d_frames, n_frames, rows, cols, d_hog, cell=8, frp=1, fcp=1, stream=None):
+def fhog_dev(d_frames, n_frames, rows, cols, d_hog, cell=8, frp=1, fcp=1, stream=None, ctx=None):
     lib = _lib.load()
-    _lib.check(lib.b2f_fhog_dev(_lib.context(), _lib.ptr(d_frames), n_frames, rows, cols, int(cell), int(frp), int(fcp),
+    _lib.check(lib.b2f_fhog_dev(ctx or _lib.context(), _lib.ptr(d_frames), n_frames, rows, cols, int(cell), int(frp), int(fcp),
                                 _lib.ptr(d_hog), _lib.ptr(stream) if stream is not None else None))
 
 

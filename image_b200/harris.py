@@ -108,7 +108,7 @@ def harris_batch_u8(frames, cap=65536, raw=False, **kw):
     return [HarrisCorners(x=x[i, :cnt[i]].copy(), y=y[i, :cnt[i]].copy(), strength=s[i, :cnt[i]].copy()) for i in range(n)]
 
 
-def harris_response_dev(d_frames, is_u8, n_frames, nx, ny, d_R, stream=None, **kw):
+def harris_response_dev(d_frames, is_u8, n_frames, nx, ny, d_R, stream=None, ctx=None, **kw):
     """Device-resident response map (pointers are ints / torch tensors)."""
     lib = _lib.load()
     d = dict(k=0.06, sigma_d=1.0, sigma_i=2.5, threshold=130.0, gaussian=0, gradient=0, strategy=0, Nselect=1,
@@ -116,12 +116,12 @@ def harris_response_dev(d_frames, is_u8, n_frames, nx, ny, d_R, stream=None, **k
     d.update(kw)
     p = _lib.HarrisParams(*[d[k] for k in ("k", "sigma_d", "sigma_i", "threshold", "gaussian", "gradient", "strategy",
                                            "Nselect", "measure", "Nscales", "precision", "cells", "verbose", "exact")])
-    _lib.check(lib.b2f_harris_response_dev(_lib.context(), _lib.ptr(d_frames), int(bool(is_u8)), n_frames, nx, ny,
+    _lib.check(lib.b2f_harris_response_dev(ctx or _lib.context(), _lib.ptr(d_frames), int(bool(is_u8)), n_frames, nx, ny,
                                            C.byref(p), _lib.ptr(d_R), _lib.ptr(stream) if stream is not None else None))
 
 
-def harris_nms_dev(d_R, n_frames, nx, ny, threshold, radius, cap, d_xy, d_strength, d_counts, stream=None):
+def harris_nms_dev(d_R, n_frames, nx, ny, threshold, radius, cap, d_xy, d_strength, d_counts, stream=None, ctx=None):
     lib = _lib.load()
-    _lib.check(lib.b2f_harris_nms_dev(_lib.context(), _lib.ptr(d_R), n_frames, nx, ny, float(threshold), int(radius),
+    _lib.check(lib.b2f_harris_nms_dev(ctx or _lib.context(), _lib.ptr(d_R), n_frames, nx, ny, float(threshold), int(radius),
                                       int(cap), _lib.ptr(d_xy), _lib.ptr(d_strength), _lib.ptr(d_counts),
                                       _lib.ptr(stream) if stream is not None else None))
