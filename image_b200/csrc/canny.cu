@@ -147,6 +147,101 @@ canny_blur_kernel(const unsigned char *__restrict__ frames, float *__restrict__ 
   }
 }
 
+// ---- two-kernel variant for the default radius (s = 2 -> R = 13) ------------------------------
+// Row pass straight from global memory: a thread produces 4 consecutive outputs of one row from 9
+// aligned 32-bit loads; symmetric pair sums are formed as exact integers and converted with the
+// 2^52 trick, so the pass is 14 DADD(convert) + 14 DMUL + 13 DADD per output.  Column pass: a CTA
+// stages a (128+2R) x 32 tile of the double row sums in shared memory (batched loads) and each thread
+// produces 8 consecutive rows of one column.  Same operation order as the tiled kernel / the oracle.
+__device__ __forceinline__ double u32_to_double(unsigned s) {   // exact: (2^52 + s) - 2^52
+  return __dadd_rn(__hiloint2double(0x43300000, (int)s), -4503599627370496.0);
+}
+
+template <int RR>
+__global__ void __launch_bounds__(256)
+canny_blur_rows_kernel(const unsigned char *__restrict__ frames, double *__restrict__ rowsum, int nx, int ny,
+                       const __grid_constant__ CannyTaps tx) {
+  const int y = blockIdx.y;
+  const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (x4 >= nx) return;
+  const unsigned char *row = frames + ((size_t)blockIdx.z * ny + y) * nx;
+  constexpr int LEAD = (RR + 3) & ~3;                            // 16: first loaded byte is x4 - LEAD
+  constexpr int NW = (LEAD + 4 + RR + 3) / 4;                    // 9 words cover x4-16 .. x4+19
+  unsigned char b[NW * 4];
+  const bool fast = (nx & 3) == 0 && x4 - LEAD >= 0 && x4 - LEAD + NW * 4 <= nx && (reinterpret_cast<uintptr_t>(frames) & 3) == 0;
+  if (fast) {
+    const unsigned *w = reinterpret_cast<const unsigned *>(row + x4 - LEAD);
+    unsigned v[NW];
+#pragma unroll
+    for (int q = 0; q < NW; q++) v[q] = __ldg(w + q);
+#pragma unroll
+    for (int q = 0; q < NW; q++) { b[4 * q] = v[q] & 0xff; b[4 * q + 1] = (v[q] >> 8) & 0xff; b[4 * q + 2] = (v[q] >> 16) & 0xff; b[4 * q + 3] = v[q] >> 24; }
+  } else {
+#pragma unroll
+    for (int q = 0; q < NW * 4; q++) b[q] = __ldg(row + wrap_index(x4 - LEAD + q, nx));
+  }
+  double o[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int c = LEAD + j;
+    double acc = __dmul_rn(tx.w[0], u32_to_double(b[c]));
+#pragma unroll
+    for (int k = 1; k <= RR; k++) acc = __dadd_rn(acc, __dmul_rn(tx.w[k], u32_to_double((unsigned)b[c - k] + (unsigned)b[c + k])));
+    o[j] = acc;
+  }
+  double *d = rowsum + ((size_t)blockIdx.z * ny + y) * nx + x4;
+  if (x4 + 3 < nx && (nx & 1) == 0) {
+    *reinterpret_cast<double2 *>(d) = make_double2(o[0], o[1]);
+    *reinterpret_cast<double2 *>(d + 2) = make_double2(o[2], o[3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; j++) if (x4 + j < nx) d[j] = o[j];
+  }
+}
+
+constexpr int CC_TW = 32, CC_TH = 128;
+template <int RR>
+__global__ void __launch_bounds__(256)
+canny_blur_cols_kernel(const double *__restrict__ rowsum, float *__restrict__ out, int nx, int ny,
+                       const __grid_constant__ CannyTaps ty) {
+  extern __shared__ __align__(16) double smem_d[];              // [CC_TH + 2RR][CC_TW]
+  constexpr int TILE_H = CC_TH + 2 * RR;
+  const int x0 = blockIdx.x * CC_TW, y0 = blockIdx.y * CC_TH;
+  const double *src = rowsum + (size_t)blockIdx.z * nx * ny;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gx = x0 + lane;
+  const int cx = min(gx, nx - 1);
+  {
+    constexpr int RBATCH = 10;                                   // 10 rows in flight per thread
+    for (int r0 = warp; r0 < TILE_H; r0 += 8 * RBATCH) {
+      double v[RBATCH];
+#pragma unroll
+      for (int k = 0; k < RBATCH; k++) {
+        const int r = min(r0 + 8 * k, TILE_H - 1);
+        v[k] = __ldg(src + (size_t)wrap_index(y0 - RR + r, ny) * nx + cx);
+      }
+#pragma unroll
+      for (int k = 0; k < RBATCH; k++) { const int r = r0 + 8 * k; if (r < TILE_H) smem_d[r * CC_TW + lane] = v[k]; }
+    }
+  }
+  __syncthreads();
+  float *dst = out + (size_t)blockIdx.z * nx * ny;
+  constexpr int RB = 8;
+  for (int rg = warp; rg < CC_TH / RB; rg += 8) {
+    double v[RB + 2 * RR];
+#pragma unroll
+    for (int q = 0; q < RB + 2 * RR; q++) v[q] = smem_d[(rg * RB + q) * CC_TW + lane];
+#pragma unroll
+    for (int j = 0; j < RB; j++) {
+      double acc = __dmul_rn(ty.w[0], v[j + RR]);
+#pragma unroll
+      for (int k = 1; k <= RR; k++) acc = __dadd_rn(acc, __dmul_rn(ty.w[k], __dadd_rn(v[j + RR - k], v[j + RR + k])));
+      const int gy = y0 + rg * RB + j;
+      if (gx < nx && gy < ny) dst[(size_t)gy * nx + gx] = __double2float_rn(acc);
+    }
+  }
+}
+
 // Un-tiled fallback (tiny images whose wrapped kernel is not symmetric, or radii too large for the
 // tile): one thread per pixel.  sym != 0: centre tap then symmetric pairs (the order of the tiled
 // kernel and of the oracle); sym == 0: taps in ascending coordinate order (the oracle's order then).
@@ -756,7 +851,18 @@ int canny_device(b2f_ctx *ctx, const unsigned char *d_frames, int n_frames, int 
   if (sym && smem <= 200 * 1024) {
     B2F_ARENA_CHECK(ctx);
     dim3 grid(ceil_div(nx, CB_TW), ceil_div(ny, CB_TH), n_frames);
-    if (tx.R == 13 && ty.R == 13) {
+    static const bool tiled13 = getenv("B2F_CANNY_TILED_BLUR") != nullptr;
+    if (tx.R == 13 && ty.R == 13 && !tiled13 && nx >= 64 && ny >= 64) {
+      // two-kernel variant: row sums (doubles) go through HBM/L2 once, no halo recomputation
+      double *rowsum = ctx->arena.get<double>(n);
+      B2F_ARENA_CHECK(ctx);
+      canny_blur_rows_kernel<13><<<dim3(ceil_div(ceil_div(nx, 4), 256), ny, n_frames), 256, 0, st>>>(d_frames, rowsum, nx, ny, tx);
+      B2F_LAUNCH_CHECK(ctx);
+      const size_t csm = sizeof(double) * (size_t)(CC_TH + 26) * CC_TW;
+      static bool cfg2 = false;
+      if (!cfg2) { B2F_CUDA(cudaFuncSetAttribute(canny_blur_cols_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm)); cfg2 = true; }
+      canny_blur_cols_kernel<13><<<dim3(ceil_div(nx, CC_TW), ceil_div(ny, CC_TH), n_frames), 256, csm, st>>>(rowsum, blur, nx, ny, ty);
+    } else if (tx.R == 13 && ty.R == 13) {
       static bool cfg = false;
       if (!cfg) { B2F_CUDA(cudaFuncSetAttribute(canny_blur_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = true; }
       canny_blur_kernel<13><<<grid, CB_NT, smem, st>>>(d_frames, blur, nx, ny, tx, ty);
