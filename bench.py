@@ -110,7 +110,7 @@ def run_reference(args, dets):
     impl = "ref" if kind == "reference" else "oracle"
     nf = max(1, args.ref_frames if args.ref_frames > 0 else min(cores, 16))
     rgb = [synth.frame_rgb(2000 + i, NY, NX) for i in range(nf)]
-    grey = [np.ascontiguousarray(f[..., 1]) for f in rgb]
+    grey = [(f.astype(np.uint16).sum(axis=2) // 3).astype(np.uint8) for f in rgb]
 
     def step():
         if "harris" in dets:
@@ -192,7 +192,7 @@ def main():
 
     # ---- synthetic frames (seeded per rank: frames are independent units, sharded across ranks)
     rgb = synth.batch(synth.frame_rgb, 2000 + 1000 * rank, B, NY, NX, distinct=2)      # [B, NY, NX, 3] u8
-    grey = np.ascontiguousarray(rgb[..., 1])
+    grey = (rgb.astype(np.uint16).sum(axis=3) // 3).astype(np.uint8)       # dlib's grey rule (r+g+b)/3, pixel.h:775-783
     h_rgb = torch.from_numpy(rgb).pin_memory()
     h_grey = torch.from_numpy(grey).pin_memory()
     d_rgb = h_rgb.cuda()

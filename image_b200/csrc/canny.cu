@@ -404,10 +404,9 @@ canny_grad_nms_kernel(const float *__restrict__ data, unsigned char *__restrict_
 //   tier 2 (the rare undecided pixel): the exact double evaluation of that pixel alone, including
 //           glibc-exact hypot of its up to nine neighbour magnitudes.
 // The output is therefore identical to the all-double kernel; B2F_CANNY_EXACT=1 selects the latter.
-// Error budget of tier 1 (float data are exact inputs): h,v are 6-term sums of floats bounded by
-// 8*255, so |dh|,|dv| <= 8*2^-24*2040 < 1e-3; |d grad| <= sqrt(2)*1e-3 + 2^-22*grad < 2.2e-3; a bilinear
-// value inherits that plus (|d cos| + |d sin|) * (spread of the four corner magnitudes), with
-// |d cos|,|d sin| <= 3.2e-3/now + 2^-21.  The margins used below are at least twice these figures.
+// Error budget of tier 1 (the float data are exact inputs): see the gradient pass — E is a per-tile
+// bound on |d grad|; a bilinear value inherits it plus (|d cos| + |d sin|) * (spread of its four
+// corner magnitudes) with |d cos|,|d sin| <= 2E/now + 2^-21.  The margins below are >= twice that.
 __device__ __forceinline__ void exact_hv(const float *d, int accGrad, double &h, double &v) {
 #define DD(dx, dy) ((double)d[(dy) * CG_DW + (dx)])
   if (accGrad) {
@@ -446,23 +445,39 @@ canny_grad_nms_spec_kernel(const float *__restrict__ data, unsigned char *__rest
     }
   }
   __syncthreads();
-  // tier-1 gradient tile (fp32)
+  // tier-1 gradient tile (fp32).  Differences are formed first (they are exact or nearly so), which
+  // keeps the rounding error proportional to the local contrast S = sum |terms| instead of to the
+  // pixel level:  |dh|,|dv| <= 3*2^-24*S,  |d grad| <= sqrt2*max(|dh|,|dv|) + 2^-23*grad.
+  // E below is twice that; its maximum over the tile is the tolerance unit of this CTA.
+  float emax = 0.f;
   for (int t = threadIdx.x; t < CG_GW * CG_GW; t += CG_NT) {
     const int j = t / CG_GW, i = t - j * CG_GW;
     const int xc = min(max(x0 - 2 + i, 0), nx - 1) - (x0 - 3), yc = min(max(y0 - 2 + j, 0), ny - 1) - (y0 - 3);
     const float *d = sd + yc * CG_DW + xc;
-    float h, v;
+    float h, v, S;
     if (accGrad) {
-      h = 2.f * (d[1] - d[-1]) + d[CG_DW + 1] - d[CG_DW - 1] + d[-CG_DW + 1] - d[-CG_DW - 1];
-      v = 2.f * (d[CG_DW] - d[-CG_DW]) + d[CG_DW + 1] - d[-CG_DW + 1] + d[CG_DW - 1] - d[-CG_DW - 1];
+      const float hx = d[1] - d[-1], hp = d[CG_DW + 1] - d[CG_DW - 1], hm = d[-CG_DW + 1] - d[-CG_DW - 1];
+      const float vy = d[CG_DW] - d[-CG_DW], vp = d[CG_DW + 1] - d[-CG_DW + 1], vm = d[CG_DW - 1] - d[-CG_DW - 1];
+      h = 2.f * hx + (hp + hm);
+      v = 2.f * vy + (vp + vm);
+      S = 2.f * (fabsf(hx) + fabsf(vy)) + fabsf(hp) + fabsf(hm) + fabsf(vp) + fabsf(vm);
     } else {
       h = d[1] - d[-1];
       v = d[CG_DW] - d[-CG_DW];
+      S = fabsf(h) + fabsf(v);
     }
-    fh[t] = h; fv[t] = v;
-    fg[t] = sqrtf(h * h + v * v);
+    const float gmag = sqrtf(h * h + v * v);
+    fh[t] = h; fv[t] = v; fg[t] = gmag;
+    emax = fmaxf(emax, 6e-7f * S + 3e-7f * gmag);
   }
+  __shared__ float s_emax[CG_NT / 32];
+  for (int o = 16; o; o >>= 1) emax = fmaxf(emax, __shfl_xor_sync(0xffffffffu, emax, o));
+  if (lane == 0) s_emax[warp] = emax;
   __syncthreads();
+  float E = s_emax[0];
+#pragma unroll
+  for (int w = 1; w < CG_NT / 32; w++) E = fmaxf(E, s_emax[w]);
+  E = fmaxf(E, 1e-7f);
   const bool interior = x0 >= 2 && y0 >= 2 && x0 + CG_T + 2 <= nx && y0 + CG_T + 2 <= ny;
   const float lowf = (float)low_thr, highf = (float)high_thr;
   __shared__ unsigned char scls[CG_T * CG_T];
@@ -479,7 +494,7 @@ canny_grad_nms_spec_kernel(const float *__restrict__ data, unsigned char *__rest
     unsigned char c = 0;
     if (inimg) {
       const float now = fg[ci];
-      const float T0 = 4.5e-3f;                                  // 2 x bound on |d grad|
+      const float T0 = 2.f * E;                                  // 2 x bound on |d grad| anywhere in this tile
       bool undecided = false;
       if (now < lowf - T0) c = 0;                                // certainly now <= low
       else if (now <= lowf + T0) undecided = true;
@@ -501,10 +516,10 @@ canny_grad_nms_spec_kernel(const float *__restrict__ data, unsigned char *__rest
           const float wb = xt - x1, wa = 1.f - wb, wd = yt - y1, wc = 1.f - wd;
           nbv[s] = wc * (wa * g11 + wb * g12) + wd * (wa * g21 + wb * g22);
           const float spread = fmaxf(fmaxf(g11, g12), fmaxf(g21, g22)) - fminf(fminf(g11, g12), fminf(g21, g22));
-          tol[s] = 2.f * T0 + 8.f * (1e-3f * inv + 5e-7f) * spread;
+          tol[s] = 2.f * T0 + 8.f * (E * inv + 5e-7f) * spread;
         }
         // the direction is ambiguous for the reference's floor() when a cosine is within its error of 0
-        const float dcs = 8.f * (1e-3f * inv + 5e-7f);
+        const float dcs = 8.f * (E * inv + 5e-7f);
         if (fabsf(cs) <= dcs || fabsf(sn) <= dcs) undecided = true;
         else if (now < nbv[0] - tol[0] || now < nbv[1] - tol[1]) c = 0;      // certainly suppressed
         else if (now > nbv[0] + tol[0] && now > nbv[1] + tol[1]) {           // certainly a maximum
