@@ -294,6 +294,8 @@ def main():
     detail = {}
 
     def t_of(fn, k=5):
+        fn()                                   # first call may grow the context's scratch arena
+        torch.cuda.synchronize()
         return timed(fn, k) / k
     th = t_of(lambda: H.harris_response_dev(d_grey, True, B, NX, NY, d_R, stream=sp, **HARRIS_KW))
     tn = t_of(lambda: H.harris_nms_dev(d_R, B, NX, NY, HARRIS_KW["threshold"], radius, cap, d_xy, d_st, d_cnt, stream=sp))

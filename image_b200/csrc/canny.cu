@@ -628,92 +628,110 @@ __device__ __forceinline__ int run_start(unsigned bits, int x) {
   return x - __clz(~(bits << (31 - x))) + 1;
 }
 
-// Level 1.  One CTA per 32x32 tile, a warp works on whole rows.  Horizontal runs are found with
-// ballots (no atomics): every pixel of a run is labelled with the run's first pixel.  Only run
-// heads take part in the shared-memory union-find, and a pair of vertically adjacent runs is
-// linked once (at the first column where they touch).  Output per edge pixel: L[p] = GLOBAL index
-// of the tile-local root; rinfo[p] = bit0 "p is a tile root", bit1 "its tile component holds a
-// class-2 pixel".
+// Level 1.  ONE WARP per 32x32 tile (8 tiles per CTA), working on RUNS, not pixels:
+//   * lane r fetches row r of the tile (32 bytes) and derives its edge / strong bit masks;
+//   * lane r walks the horizontal runs of its row with bit operations; only run heads carry a label;
+//   * each run is linked (lock-free union, atomicMin on shared memory) to every run of the row above that
+//     touches it 8-connectedly -- all 32 rows concurrently;
+//   * heads are flattened, the per-component "holds a class-2 pixel" flag is set per run;
+//   * the output pass (lane = column) writes one root index per edge pixel.
+// Output per edge pixel: L[p] = GLOBAL index of the tile-local root; rinfo[p] (pre-zeroed by a memset) =
+// bit0 "p is a tile root", bit1 "its tile component holds a class-2 pixel".
+__device__ __forceinline__ unsigned nonzero_bytes_mask(unsigned m) {   // m has 0xff / 0x00 per byte -> 4 bits
+  return ((m >> 7) & 1u) | ((m >> 14) & 2u) | ((m >> 21) & 4u) | ((m >> 28) & 8u);
+}
+__device__ __forceinline__ unsigned run_mask_from(unsigned bits, int s) {   // the run of set bits of `bits` that starts at bit s
+  const unsigned t = ~(bits >> s);                                         // first zero above s ...
+  const int len = t ? __ffs(t) - 1 : 32;                                   // (bits >> s) shifts zeros in, so t != 0 unless s == 0 && bits == ~0
+  return (len >= 32 ? 0xffffffffu : ((1u << len) - 1u)) << s;
+}
+
 __global__ void __launch_bounds__(256)
-hyst_local_kernel(const unsigned char *__restrict__ cls, int *__restrict__ L, unsigned char *__restrict__ rinfo, int nx, int ny) {
-  __shared__ int lab[HT * HT];
-  __shared__ unsigned rowmask[HT], strongmask[HT];
-  __shared__ unsigned char cstrong[HT * HT];
-  const int x0 = blockIdx.x * HT, y0 = blockIdx.y * HT;
-  const size_t base = (size_t)blockIdx.z * nx * ny;
-  int root_dummy[4];
+hyst_local_kernel(const unsigned char *__restrict__ cls, int *__restrict__ L, unsigned char *__restrict__ rinfo, int nx, int ny,
+                  int TX, int TY, int n_tiles) {
+  __shared__ int lab_all[8][HT * HT];
+  __shared__ unsigned char cst_all[8][HT * HT];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int gx = x0 + lane;
-  {   // stage the tile: one 32-bit load per thread (4 pixels) when rows are word aligned
-    __shared__ __align__(4) unsigned char sc[HT * HT];
-    const int r = threadIdx.x >> 3, w = threadIdx.x & 7, gy = y0 + r, wx = x0 + 4 * w;
-    unsigned v = 0;
+  const int tile = blockIdx.x * 8 + warp;
+  if (tile >= n_tiles) return;
+  int *lab = lab_all[warp];
+  unsigned char *cstrong = cst_all[warp];
+  const int tx = tile % TX, ty = (tile / TX) % TY, f = tile / (TX * TY);
+  const int x0 = tx * HT, y0 = ty * HT;
+  const size_t base = (size_t)f * nx * ny;
+  // ---- row `lane` of the tile -> bit masks
+  unsigned emask = 0, smask = 0;
+  {
+    const int gy = y0 + lane;
     if (gy < ny) {
-      const unsigned char *row = cls + base + (size_t)gy * nx;
-      if ((nx & 3) == 0 && wx + 3 < nx) v = *reinterpret_cast<const unsigned *>(row + wx);
-      else { for (int b = 0; b < 4; b++) if (wx + b < nx) v |= (unsigned)row[wx + b] << (8 * b); }
-    }
-    reinterpret_cast<unsigned *>(sc)[threadIdx.x] = v;
-    __syncthreads();
-    // hand the staged bytes to the row loop below through registers
+      const unsigned char *row = cls + base + (size_t)gy * nx + x0;
+      if ((nx & 15) == 0 && x0 + 32 <= nx) {
+        const uint4 a = *reinterpret_cast<const uint4 *>(row), b = *reinterpret_cast<const uint4 *>(row + 16);
+        const unsigned w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-    for (int k = 0; k < 4; k++) root_dummy[k] = sc[(4 * warp + k) * HT + lane];
-  }
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const int r = 4 * warp + k;
-    const unsigned char c = (unsigned char)root_dummy[k];
-    const unsigned bits = __ballot_sync(0xffffffffu, c != 0), sb = __ballot_sync(0xffffffffu, c == 2);
-    if (lane == 0) { rowmask[r] = bits; strongmask[r] = sb; }
-    lab[r * HT + lane] = c ? r * HT + run_start(bits, lane) : r * HT + lane;
-    cstrong[r * HT + lane] = 0;
-  }
-  __syncthreads();
-  // vertical links.  Pass 0: every warp links rows 4w+1..4w+3 of its own strip top-down (short
-  // chains, no contention between warps); pass 1: the 7 strip seams (row 4w against row 4w-1).
-  for (int pass = 0; pass < 2; pass++) {
-    for (int k = (pass ? 0 : 1); k < (pass ? 1 : 4); k++) {
-      const int r = 4 * warp + k;
-      if (r == 0) continue;
-      const unsigned bits = rowmask[r], up = rowmask[r - 1];
-      if (((bits >> lane) & 1u) && up) {
-        const int st = run_start(bits, lane);
-        const bool isStart = st == lane, isEnd = lane == 31 || !((bits >> (lane + 1)) & 1u);
-        const bool N = (up >> lane) & 1u, NW = lane > 0 && ((up >> (lane - 1)) & 1u), NE = lane < 31 && ((up >> (lane + 1)) & 1u);
-        const int me = r * HT + st;
-        if (N) {
-          if (isStart || !NW) uf_union(lab, me, (r - 1) * HT + run_start(up, lane));
-        } else {
-          if (NW && isStart) uf_union(lab, me, (r - 1) * HT + run_start(up, lane - 1));
-          if (NE && isEnd) uf_union(lab, me, (r - 1) * HT + run_start(up, lane + 1));
+        for (int q = 0; q < 8; q++) {
+          emask |= nonzero_bytes_mask(__vcmpne4(w[q], 0u)) << (4 * q);
+          smask |= nonzero_bytes_mask(__vcmpeq4(w[q], 0x02020202u)) << (4 * q);
         }
+      } else {
+        for (int x = 0; x < 32; x++)
+          if (x0 + x < nx) { const unsigned char c = row[x]; emask |= (unsigned)(c != 0) << x; smask |= (unsigned)(c == 2) << x; }
       }
-      __syncwarp();
-    }
-    __syncthreads();
-  }
-  int root[4];
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const int r = 4 * warp + k, i = r * HT + lane;
-    root[k] = -1;
-    if ((rowmask[r] >> lane) & 1u) {
-      root[k] = uf_find(lab, i);
-      if ((strongmask[r] >> lane) & 1u) cstrong[root[k]] = 1;
     }
   }
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const int r = 4 * warp + k, i = r * HT + lane, gy = y0 + r;
-    if (gx >= nx || gy >= ny) continue;
-    const size_t p = base + (size_t)gy * nx + gx;
-    if (root[k] < 0) { rinfo[p] = 0; continue; }
-    const int ry = root[k] / HT, rx = root[k] - ry * HT;
+  if (!__any_sync(0xffffffffu, emask != 0)) return;             // empty tile
+  const unsigned up = __shfl_up_sync(0xffffffffu, emask, 1);
+  // ---- heads
+  for (unsigned rem = emask; rem;) {
+    const int s = __ffs(rem) - 1;
+    rem &= ~run_mask_from(emask, s);
+    lab[lane * HT + s] = lane * HT + s;
+    cstrong[lane * HT + s] = 0;
+  }
+  __syncwarp();
+  // ---- link every run to the touching runs of the row above
+  if (lane > 0 && up) {
+    for (unsigned rem = emask; rem;) {
+      const int s = __ffs(rem) - 1;
+      const unsigned rm = run_mask_from(emask, s);
+      rem &= ~rm;
+      unsigned touch = up & (rm | (rm << 1) | (rm >> 1));
+      while (touch) {
+        const int b = __ffs(touch) - 1, us = run_start(up, b);
+        touch &= ~run_mask_from(up, us);
+        uf_union(lab, lane * HT + s, (lane - 1) * HT + us);
+      }
+    }
+  }
+  __syncwarp();
+  // ---- flatten heads; afterwards every head holds its root
+  for (unsigned rem = emask; rem;) {
+    const int s = __ffs(rem) - 1;
+    rem &= ~run_mask_from(emask, s);
+    lab[lane * HT + s] = uf_find(lab, lane * HT + s);
+  }
+  __syncwarp();
+  for (unsigned rem = emask; rem;) {
+    const int s = __ffs(rem) - 1;
+    const unsigned rm = run_mask_from(emask, s);
+    rem &= ~rm;
+    if (smask & rm) cstrong[uf_find(lab, lane * HT + s)] = 1;
+  }
+  __syncwarp();
+  // ---- output (lane = column)
+  const int gx = x0 + lane;
+  for (int r = 0; r < HT; r++) {
+    const unsigned bits = __shfl_sync(0xffffffffu, emask, r);
+    if (!((bits >> lane) & 1u)) continue;                       // (no shuffles below: divergence is fine)
+    const int h = r * HT + run_start(bits, lane);
+    const int rt = uf_find(lab, h);
+    const int ry = rt / HT, rx = rt - ry * HT;
+    const size_t p = base + (size_t)(y0 + r) * nx + gx;
     L[p] = (int)(base + (size_t)(y0 + ry) * nx + (x0 + rx));
-    rinfo[p] = (root[k] == i) ? (unsigned char)(1 | (cstrong[i] << 1)) : (unsigned char)0;
+    if (rt == r * HT + lane) rinfo[p] = (unsigned char)(1 | (cstrong[rt] << 1));
   }
 }
+
 // Level 2: seams.  A pixel on the right / bottom / left edge of its tile unions with its forward
 // neighbours (E, SW, S, SE) that live in another tile.  3*HT slots per tile.
 __global__ void hyst_seam_kernel(const unsigned char *__restrict__ cls, int *__restrict__ L, int nx, int ny) {
@@ -926,7 +944,11 @@ int canny_device(b2f_ctx *ctx, const unsigned char *d_frames, int n_frames, int 
   // ---- hysteresis: two-level union-find on the class bytes (tile-local in shared memory, seams with atomicMin)
   B2F_CUDA(cudaMemsetAsync(strong, 0, n, st));
   dim3 tiles(ceil_div(nx, HT), ceil_div(ny, HT), n_frames);
-  hyst_local_kernel<<<tiles, 256, 0, st>>>(cls, L, rinfo, nx, ny);
+  B2F_CUDA(cudaMemsetAsync(rinfo, 0, n, st));
+  {
+    const int HTX = ceil_div(nx, HT), HTY = ceil_div(ny, HT), htn = HTX * HTY * n_frames;
+    hyst_local_kernel<<<ceil_div(htn, 8), 256, 0, st>>>(cls, L, rinfo, nx, ny, HTX, HTY, htn);
+  }
   B2F_LAUNCH_CHECK(ctx);
   hyst_seam_kernel<<<tiles, 3 * HT, 0, st>>>(cls, L, nx, ny);
   B2F_LAUNCH_CHECK(ctx);

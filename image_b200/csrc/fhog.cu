@@ -1,15 +1,17 @@
 // fhog.cu — Felzenszwalb HOG of dlib 19.20 as reached from image.dlib::image_fhog
 // (reference: dlib/image_transforms/fhog.h:698-1046).
 //
-//   fhog_hist_kernel     one CTA = a tile of CT x CT histogram cells.  Phase 1: the RGB pixels
-//                        that vote into the tile (+1 ring for the gradient) are staged in shared
-//                        memory and every pixel's (orientation bin, magnitude) is computed once:
-//                        max-length colour channel with the reference's position-dependent
-//                        tie-break (SIMD body vs scalar tail, fhog.h:48-58 / :133-141), 18-way
-//                        snap with un-fused float ops, correctly rounded sqrt.  Phase 2: ONE thread
-//                        per cell replays that cell's votes in raster order (the order of the
-//                        reference's sequential `hist += v` statements, fhog.h:879-917, :951-954),
-//                        accumulating in a private shared-memory histogram -> the 18-bin
+//   fhog_lut_kernel      (once per context) 511 x 511 table of the 18-way orientation snap for every
+//                        possible integer gradient (gx, gy in -255..255), computed with the reference's
+//                        un-fused float ops (fhog.h:864-877) -> the per-pixel snap is one table load.
+//   fhog_pixel_kernel    one CTA = a 64 x 16 pixel tile (+1 ring, word-aligned staging of the RGB bytes).
+//                        Per pixel: max-length colour channel with the reference's position-dependent
+//                        tie-break (SIMD body vs scalar tail, fhog.h:48-58 / :133-141), LUT snap,
+//                        correctly rounded sqrt.  Writes a magnitude plane and an orientation plane in a
+//                        cell-phase de-interleaved column order, so the next kernel's loads coalesce.
+//   fhog_cell_kernel     ONE thread per histogram cell replays that cell's votes in raster order (the
+//                        order of the reference's sequential `hist += v` statements, fhog.h:879-917,
+//                        :951-954), accumulating in a private shared-memory histogram -> the 18-bin
 //                        histograms are BIT-IDENTICAL to the reference, no atomics.
 //   fhog_norm_kernel     per-cell energy (fhog.h:959-968), sequential over the 9 orientations.
 //   fhog_feature_kernel  4-block normalisation, clipping and the 31 features (fhog.h:972-1045)
@@ -226,54 +228,66 @@ __global__ void fhog_norm_kernel(const float *__restrict__ hist, float *__restri
   norm[((size_t)blockIdx.z * g.cells_nr + r) * g.cells_nc + c] = n;
 }
 
-__global__ void fhog_feature_kernel(const float *__restrict__ hist, const float *__restrict__ norm, float *__restrict__ out,
-                                    FhogGeom g) {
-  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-  if (x >= g.hog_nc) return;
+constexpr int FF_NT = 64;   // hog cells (consecutive columns of one row) per CTA
+__global__ void __launch_bounds__(FF_NT)
+fhog_feature_kernel(const float *__restrict__ hist, const float *__restrict__ norm, float *__restrict__ out, FhogGeom g) {
+  // histograms in and features out are staged through shared memory so that both global streams are
+  // contiguous (a row segment of 64 cells = 1152 floats in, 1984 floats out)
+  __shared__ float sh[FF_NT * 18];
+  __shared__ float so[FF_NT * 31];
+  const int xb = blockIdx.x * FF_NT, y = blockIdx.y;
+  const int ncell = min(FF_NT, g.hog_nc - xb);
   const int HC = g.cells_nc + 2;
-  const float *N = norm + (size_t)blockIdx.z * g.cells_nr * g.cells_nc;
-#define NN(r, c) N[(size_t)(r) * g.cells_nc + (c)]
-  const float z1[4] = {NN(y + 1, x + 1), NN(y, x + 1), NN(y + 1, x), NN(y, x)};
-  const float z2[4] = {NN(y + 1, x + 2), NN(y, x + 2), NN(y + 1, x + 1), NN(y, x + 1)};
-  const float z3[4] = {NN(y + 2, x + 1), NN(y + 1, x + 1), NN(y + 2, x), NN(y + 1, x)};
-  const float z4[4] = {NN(y + 2, x + 2), NN(y + 1, x + 2), NN(y + 2, x + 1), NN(y + 1, x + 1)};
+  const float *hsrc = hist + ((size_t)blockIdx.z * (g.cells_nr + 2) * HC + (size_t)(y + 2) * HC + (xb + 2)) * 18;
+  for (int i = threadIdx.x; i < ncell * 18; i += FF_NT) sh[i] = __ldg(hsrc + i);
+  __syncthreads();
+  const int t = threadIdx.x, x = xb + t;
+  if (t < ncell) {
+    const float *N = norm + (size_t)blockIdx.z * g.cells_nr * g.cells_nc;
+#define NN(r, c) __ldg(N + (size_t)(r) * g.cells_nc + (c))
+    const float n00 = NN(y, x), n01 = NN(y, x + 1), n02 = NN(y, x + 2), n10 = NN(y + 1, x), n11 = NN(y + 1, x + 1), n12 = NN(y + 1, x + 2),
+                n20 = NN(y + 2, x), n21 = NN(y + 2, x + 1), n22 = NN(y + 2, x + 2);
 #undef NN
-  float nn[4], n[4], tt[4] = {0.f, 0.f, 0.f, 0.f};
+    const float z1[4] = {n11, n01, n10, n00}, z2[4] = {n12, n02, n11, n01}, z3[4] = {n21, n11, n20, n10}, z4[4] = {n22, n12, n21, n11};
+    float nn[4], n[4], tt[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    float s = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(z1[k], z2[k]), z3[k]), z4[k]), 0.0001f);
-    nn[k] = __fmul_rn(0.2f, __fsqrt_rn(s));
-    n[k] = __fdiv_rn(0.1f, nn[k]);
-  }
-  const float *h = hist + ((size_t)blockIdx.z * (g.cells_nr + 2) * HC + (size_t)(y + 2) * HC + (x + 2)) * 18;
-  float hv[18];
+    for (int k = 0; k < 4; k++) {
+      float s = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(z1[k], z2[k]), z3[k]), z4[k]), 0.0001f);
+      nn[k] = __fmul_rn(0.2f, __fsqrt_rn(s));
+      n[k] = __fdiv_rn(0.1f, nn[k]);
+    }
+    float hv[18];
 #pragma unroll
-  for (int o = 0; o < 18; o++) hv[o] = h[o];
-  float *o31 = out + (((size_t)blockIdx.z * g.out_nr + (y + g.pad_r)) * g.out_nc + (x + g.pad_c)) * 31;
+    for (int o = 0; o < 18; o++) hv[o] = sh[t * 18 + o];
+    float *o31 = so + t * 31;
 #pragma unroll
-  for (int o = 0; o < 18; o += 3) {
-    float hh[3][4];
+    for (int o = 0; o < 18; o += 3) {
+      float hh[3][4];
 #pragma unroll
-    for (int j = 0; j < 3; j++) {
+      for (int j = 0; j < 3; j++) {
 #pragma unroll
-      for (int k = 0; k < 4; k++) hh[j][k] = __fmul_rn(hv[o + j] < nn[k] ? hv[o + j] : nn[k], n[k]);
-      o31[o + j] = __fadd_rn(__fadd_rn(hh[j][0], hh[j][2]), __fadd_rn(hh[j][1], hh[j][3]));
+        for (int k = 0; k < 4; k++) hh[j][k] = __fmul_rn(hv[o + j] < nn[k] ? hv[o + j] : nn[k], n[k]);
+        o31[o + j] = __fadd_rn(__fadd_rn(hh[j][0], hh[j][2]), __fadd_rn(hh[j][1], hh[j][3]));
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) tt[k] = __fadd_rn(tt[k], __fadd_rn(__fadd_rn(hh[0][k], hh[1][k]), hh[2][k]));
+    }
+    const float tscale = (float)(2 * 0.2357);
+#pragma unroll
+    for (int k = 0; k < 4; k++) tt[k] = __fmul_rn(tt[k], tscale);
+#pragma unroll
+    for (int o = 0; o < 9; o++) {
+      float tmp = __fadd_rn(hv[o], hv[o + 9]), hk[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) hk[k] = __fmul_rn(tmp < nn[k] ? tmp : nn[k], n[k]);
+      o31[18 + o] = __fadd_rn(__fadd_rn(hk[0], hk[2]), __fadd_rn(hk[1], hk[3]));
     }
 #pragma unroll
-    for (int k = 0; k < 4; k++) tt[k] = __fadd_rn(tt[k], __fadd_rn(__fadd_rn(hh[0][k], hh[1][k]), hh[2][k]));
+    for (int k = 0; k < 4; k++) o31[27 + k] = tt[k];
   }
-  const float tscale = (float)(2 * 0.2357);
-#pragma unroll
-  for (int k = 0; k < 4; k++) tt[k] = __fmul_rn(tt[k], tscale);
-#pragma unroll
-  for (int o = 0; o < 9; o++) {
-    float tmp = __fadd_rn(hv[o], hv[o + 9]), hk[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) hk[k] = __fmul_rn(tmp < nn[k] ? tmp : nn[k], n[k]);
-    o31[18 + o] = __fadd_rn(__fadd_rn(hk[0], hk[2]), __fadd_rn(hk[1], hk[3]));
-  }
-#pragma unroll
-  for (int k = 0; k < 4; k++) o31[27 + k] = tt[k];
+  __syncthreads();
+  float *dst = out + (((size_t)blockIdx.z * g.out_nr + (y + g.pad_r)) * g.out_nc + (xb + g.pad_c)) * 31;
+  for (int i = threadIdx.x; i < ncell * 31; i += FF_NT) dst[i] = so[i];
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -379,7 +393,7 @@ int fhog_device(b2f_ctx *ctx, const unsigned char *d_frames, int n_frames, const
   B2F_LAUNCH_CHECK(ctx);
   if (g.out_nr != g.hog_nr || g.out_nc != g.hog_nc)   // zero border of init_hog (fhog.h:459-470)
     B2F_CUDA(cudaMemsetAsync(d_out, 0, sizeof(float) * (size_t)n_frames * g.out_nr * g.out_nc * 31, st));
-  fhog_feature_kernel<<<dim3(ceil_div(g.hog_nc, 64), g.hog_nr, n_frames), 64, 0, st>>>(hist, norm, d_out, g);
+  fhog_feature_kernel<<<dim3(ceil_div(g.hog_nc, FF_NT), g.hog_nr, n_frames), FF_NT, 0, st>>>(hist, norm, d_out, g);
   B2F_LAUNCH_CHECK(ctx);
   return B2F_OK;
 }
