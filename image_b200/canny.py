@@ -46,7 +46,7 @@ def image_canny_edge_detector(x, s=2, low_thr=3, high_thr=10, accGrad=True):
     return canny_edge_detector(a.ravel(order="F"), a.shape[0], a.shape[1], s, low_thr, high_thr, accGrad)
 
 
-def canny_batch(frames, s=2.0, low_thr=3.0, high_thr=10.0, accGrad=True, out=None):
+def canny_batch(frames, s=2.0, low_thr=3.0, high_thr=10.0, accGrad=True, out=None, ctx=None):
     """Batch form (new surface): uint8 [n, ny, nx] host frames -> (edges uint8 [n, ny, nx], nonzero int32 [n]).
     `out` may be a preallocated (e.g. pinned) uint8 array of the same shape."""
     lib = _lib.load()
@@ -54,7 +54,7 @@ def canny_batch(frames, s=2.0, low_thr=3.0, high_thr=10.0, accGrad=True, out=Non
     n, ny, nx = f.shape
     edges = out if out is not None else np.empty_like(f)
     nz = np.zeros(n, np.int32)
-    _lib.check(lib.b2f_canny_batch(_lib.context(), _lib.ptr(f), n, nx, ny, float(s), float(low_thr), float(high_thr),
+    _lib.check(lib.b2f_canny_batch(ctx or _lib.context(), _lib.ptr(f), n, nx, ny, float(s), float(low_thr), float(high_thr),
                                    int(bool(accGrad)), _lib.ptr(edges), _lib.ptr(nz)))
     return edges, nz
 

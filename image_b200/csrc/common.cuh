@@ -60,6 +60,15 @@ struct b2f_ctx {
   size_t pinned_cap = 0;
   long long launches = 0;
   void *fhog_lut = nullptr;   // 511x511 orientation-snap table (fhog.cu), built on first use
+  // FHOG vote tables of the last geometry (fhog.cu): one device block, rebuilt when (rows, cols, cell) changes
+  void *fhog_tab = nullptr;
+  size_t fhog_tab_cap = 0;
+  int fhog_tab_key[3] = {0, 0, 0};
+  int fhog_tab_kw = 0;
+  // chunked host batches (*_batch): copy-in / copy-out streams beside `stream`, and their events
+  size_t chunk_bytes = (size_t)24 << 20;   // input bytes per chunk (b2f_set_chunk_bytes)
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  std::vector<cudaEvent_t> events;
 };
 
 namespace b2f {
@@ -68,6 +77,18 @@ namespace b2f {
 // upper bound of its scratch need, then carves buffers with ctx->arena.get<T>(n).
 int arena_reserve(b2f_ctx *ctx, size_t bytes);
 int pinned_reserve(b2f_ctx *ctx, size_t bytes);
+// Host batches are cut into chunks of frames so that the upload of chunk c+1, the kernels of chunk c and
+// the download of chunk c-1 overlap (three streams, events between them).  pipe_prepare makes sure the two
+// copy streams and `n_events` events exist and orders the copy-in stream behind whatever the context
+// stream still has in flight.
+int pipe_prepare(b2f_ctx *ctx, int n_events);
+int pipe_drain(b2f_ctx *ctx);                       // wait for all three streams (also used on error paths)
+inline int frames_per_chunk(const b2f_ctx *ctx, size_t frame_bytes, int n_frames) {
+  const size_t target = ctx->chunk_bytes;
+  size_t c = target / (frame_bytes ? frame_bytes : 1);
+  if (c < 1) c = 1;
+  return c > (size_t)n_frames ? n_frames : (int)c;
+}
 #define B2F_ARENA_CHECK(ctx)                                                                \
   do {                                                                                     \
     if ((ctx)->arena.overflow) {                                                           \

@@ -50,6 +50,30 @@ int pinned_reserve(b2f_ctx *ctx, size_t bytes) {
   ctx->pinned_cap = bytes;
   return B2F_OK;
 }
+
+int pipe_prepare(b2f_ctx *ctx, int n_events) {
+  if (!ctx->s_in) B2F_CUDA(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+  if (!ctx->s_out) B2F_CUDA(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+  n_events += 1;
+  while ((int)ctx->events.size() < n_events) {
+    cudaEvent_t e;
+    B2F_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->events.push_back(e);
+  }
+  cudaEvent_t e0 = ctx->events[n_events - 1];
+  B2F_CUDA(cudaEventRecord(e0, ctx->stream));
+  B2F_CUDA(cudaStreamWaitEvent(ctx->s_in, e0, 0));
+  return B2F_OK;
+}
+
+int pipe_drain(b2f_ctx *ctx) {
+  cudaError_t a = ctx->s_in ? cudaStreamSynchronize(ctx->s_in) : cudaSuccess;
+  cudaError_t b = cudaStreamSynchronize(ctx->stream);
+  cudaError_t c = ctx->s_out ? cudaStreamSynchronize(ctx->s_out) : cudaSuccess;
+  cudaError_t e = a != cudaSuccess ? a : (b != cudaSuccess ? b : c);
+  if (e != cudaSuccess) { cudaGetLastError(); set_error("CUDA error while draining a batch: %s", cudaGetErrorString(e)); return B2F_ECUDA; }
+  return B2F_OK;
+}
 }  // namespace b2f
 
 extern "C" {
@@ -98,11 +122,20 @@ void b2f_shutdown(b2f_ctx *c) {
   if (c->arena.base) cudaFree(c->arena.base);
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->fhog_lut) cudaFree(c->fhog_lut);
+  if (c->fhog_tab) cudaFree(c->fhog_tab);
+  if (c->s_in) { cudaStreamSynchronize(c->s_in); cudaStreamDestroy(c->s_in); }
+  if (c->s_out) { cudaStreamSynchronize(c->s_out); cudaStreamDestroy(c->s_out); }
+  for (cudaEvent_t e : c->events) cudaEventDestroy(e);
   cudaStreamDestroy(c->stream);
   delete c;
 }
 
 void b2f_free(void *p) { free(p); }
+int b2f_set_chunk_bytes(b2f_ctx *c, size_t bytes) {
+  if (!c || bytes == 0) { b2f::set_error("b2f_set_chunk_bytes: bad argument"); return B2F_EINVAL; }
+  c->chunk_bytes = bytes;
+  return B2F_OK;
+}
 void *b2f_stream(b2f_ctx *c) { return c ? (void *)c->stream : nullptr; }
 long long b2f_launch_count(b2f_ctx *c) { return c ? c->launches : 0; }
 

@@ -299,9 +299,29 @@ size_t fhog_scratch_bytes(int n_frames, const FhogGeom &g) {
   return align256(hist) + align256(norm) + align256(vplane * 4) + align256(vplane) + 12 * align256(tabs) + (1 << 16);
 }
 
-int fhog_device(b2f_ctx *ctx, const unsigned char *d_frames, int n_frames, const FhogGeom &g, float *d_out, cudaStream_t st) {
+// Vote tables for one geometry, built with the reference's float expressions and cached in the context
+// (one device block; rebuilt only when rows / cols / cell change, so steady-state calls upload nothing
+// and never synchronise).
+struct FhogTabDev { FhogTables tb; const int *colidx; int KW; };
+
+static int fhog_tables(b2f_ctx *ctx, const FhogGeom &g, cudaStream_t st, FhogTabDev &out) {
   const int cell = g.cell, HR = g.cells_nr + 2, HC = g.cells_nc + 2;
-  // ---- vote tables, reference float expressions
+  const size_t o_r0 = 0, o_c0 = align256(o_r0 + 2 * (size_t)g.rows), o_vy0 = align256(o_c0 + 2 * (size_t)g.cols),
+               o_vy1 = align256(o_vy0 + 4 * (size_t)g.rows), o_vx0 = align256(o_vy1 + 4 * (size_t)g.rows),
+               o_vx1 = align256(o_vx0 + 4 * (size_t)g.cols), o_ylo = align256(o_vx1 + 4 * (size_t)g.cols),
+               o_yhi = align256(o_ylo + 4 * (size_t)HR), o_xlo = align256(o_yhi + 4 * (size_t)HR), o_xhi = align256(o_xlo + 4 * (size_t)HC),
+               o_col = align256(o_xhi + 4 * (size_t)HC), total = align256(o_col + 4 * (size_t)g.cols);
+  auto bind = [&](char *base) {
+    out.tb = FhogTables{(const short *)(base + o_r0), (const short *)(base + o_c0), (const float *)(base + o_vy0), (const float *)(base + o_vy1),
+                        (const float *)(base + o_vx0), (const float *)(base + o_vx1), (const int *)(base + o_ylo), (const int *)(base + o_yhi),
+                        (const int *)(base + o_xlo), (const int *)(base + o_xhi)};
+    out.colidx = (const int *)(base + o_col);
+  };
+  if (ctx->fhog_tab && ctx->fhog_tab_key[0] == g.rows && ctx->fhog_tab_key[1] == g.cols && ctx->fhog_tab_key[2] == cell) {
+    bind((char *)ctx->fhog_tab);
+    out.KW = ctx->fhog_tab_kw;
+    return B2F_OK;
+  }
   std::vector<short> r0(g.rows, 0), c0(g.cols, 0);
   std::vector<float> vy0(g.rows, 0), vy1(g.rows, 0), vx0(g.cols, 0), vx1(g.cols, 0);
   for (int y = 1; y < g.visible_nr; y++) {                                   // fhog.h:823-826
@@ -345,6 +365,44 @@ int fhog_device(b2f_ctx *ctx, const unsigned char *d_frames, int n_frames, const
   };
   ranges(r0, 1, std::max(g.visible_nr, 1), ylo, yhi);
   ranges(c0, 1, std::max(g.visible_nc, 1), xlo, xhi);
+  const int NCB0 = g.cols / cell + 2;
+  std::vector<int> colidx(g.cols);
+  for (int x = 0; x < g.cols; x++) colidx[x] = (x % cell) * NCB0 + x / cell;      // cell-phase de-interleaved column
+  int maxw = 1;
+  for (int C = 0; C < HC; C++) maxw = std::max(maxw, xhi[C] - xlo[C]);
+
+  // the previous block may still be read by kernels in flight: wait before replacing it
+  B2F_CUDA(cudaStreamSynchronize(st));
+  if (ctx->stream != st) B2F_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->fhog_tab_key[0] = ctx->fhog_tab_key[1] = ctx->fhog_tab_key[2] = 0;
+  if (total > ctx->fhog_tab_cap) {
+    if (ctx->fhog_tab) B2F_CUDA(cudaFree(ctx->fhog_tab));
+    ctx->fhog_tab = nullptr; ctx->fhog_tab_cap = 0;
+    void *pnew = nullptr;
+    cudaError_t e = cudaMalloc(&pnew, total);
+    if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc(%zu bytes of FHOG tables) failed: %s", total, cudaGetErrorString(e)); return B2F_ENOMEM; }
+    ctx->fhog_tab = pnew; ctx->fhog_tab_cap = total;
+  }
+  char *base = (char *)ctx->fhog_tab;
+#define UP(off, v) B2F_CUDA(cudaMemcpyAsync(base + off, v.data(), v.size() * sizeof(v[0]), cudaMemcpyHostToDevice, st))
+  UP(o_r0, r0); UP(o_c0, c0); UP(o_vy0, vy0); UP(o_vy1, vy1); UP(o_vx0, vx0); UP(o_vx1, vx1);
+  UP(o_ylo, ylo); UP(o_yhi, yhi); UP(o_xlo, xlo); UP(o_xhi, xhi); UP(o_col, colidx);
+#undef UP
+  B2F_CUDA(cudaStreamSynchronize(st));   // host tables go out of scope at return
+  ctx->fhog_tab_key[0] = g.rows; ctx->fhog_tab_key[1] = g.cols; ctx->fhog_tab_key[2] = cell;
+  ctx->fhog_tab_kw = std::min(maxw, 96);
+  bind(base);
+  out.KW = ctx->fhog_tab_kw;
+  return B2F_OK;
+}
+
+int fhog_device(b2f_ctx *ctx, const unsigned char *d_frames, int n_frames, const FhogGeom &g, float *d_out, cudaStream_t st) {
+  const int cell = g.cell, HR = g.cells_nr + 2, HC = g.cells_nc + 2;
+  FhogTabDev td;
+  int trc = fhog_tables(ctx, g, st, td);
+  if (trc != B2F_OK) return trc;
+  const FhogTables tb = td.tb;
+  const int *d_colidx = td.colidx;
 
   // ---- device buffers
   float *hist = ctx->arena.get<float>((size_t)n_frames * HR * HC * 18);
@@ -352,21 +410,7 @@ int fhog_device(b2f_ctx *ctx, const unsigned char *d_frames, int n_frames, const
   const size_t vplane = (size_t)g.rows * (size_t)(cell * (g.cols / cell + 2));
   float *vmag = ctx->arena.get<float>((size_t)n_frames * vplane);
   unsigned char *obin = ctx->arena.get<unsigned char>((size_t)n_frames * vplane);
-  short *d_r0 = ctx->arena.get<short>(g.rows), *d_c0 = ctx->arena.get<short>(g.cols);
-  float *d_vy0 = ctx->arena.get<float>(g.rows), *d_vy1 = ctx->arena.get<float>(g.rows);
-  float *d_vx0 = ctx->arena.get<float>(g.cols), *d_vx1 = ctx->arena.get<float>(g.cols);
-  const int NCB0 = g.cols / cell + 2;
-  std::vector<int> colidx(g.cols);
-  for (int x = 0; x < g.cols; x++) colidx[x] = (x % cell) * NCB0 + x / cell;      // cell-phase de-interleaved column
-  int *d_colidx = ctx->arena.get<int>(g.cols);
-  int *d_ylo = ctx->arena.get<int>(HR), *d_yhi = ctx->arena.get<int>(HR), *d_xlo = ctx->arena.get<int>(HC), *d_xhi = ctx->arena.get<int>(HC);
   B2F_ARENA_CHECK(ctx);
-#define UP(d, v) B2F_CUDA(cudaMemcpyAsync(d, v.data(), v.size() * sizeof(v[0]), cudaMemcpyHostToDevice, st))
-  UP(d_r0, r0); UP(d_c0, c0); UP(d_vy0, vy0); UP(d_vy1, vy1); UP(d_vx0, vx0); UP(d_vx1, vx1);
-  UP(d_ylo, ylo); UP(d_yhi, yhi); UP(d_xlo, xlo); UP(d_xhi, xhi); UP(d_colidx, colidx);
-#undef UP
-  B2F_CUDA(cudaStreamSynchronize(st));   // host tables go out of scope at return
-  FhogTables tb{d_r0, d_c0, d_vy0, d_vy1, d_vx0, d_vx1, d_ylo, d_yhi, d_xlo, d_xhi};
 
   const int NCB = g.cols / cell + 2, PW = cell * NCB;
   if (!ctx->fhog_lut) {       // one-time 256 KB orientation table
@@ -381,9 +425,7 @@ int fhog_device(b2f_ctx *ctx, const unsigned char *d_frames, int n_frames, const
       (g.cols % 4 == 0 && (reinterpret_cast<uintptr_t>(d_frames) & 3) == 0) ? 1 : 0);
   B2F_LAUNCH_CHECK(ctx);
   {
-    int maxw = 1;
-    for (int C = 0; C < HC; C++) maxw = std::max(maxw, xhi[C] - xlo[C]);
-    const int KW = std::min(maxw, 96);
+    const int KW = td.KW;
     size_t smem = sizeof(float) * (size_t)(18 + 2 * KW) * FC_NT;   // histogram + x weights + column offsets
     B2F_CUDA(cudaFuncSetAttribute(fhog_cell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     fhog_cell_kernel<<<dim3(ceil_div(HC, FC_NT), HR, n_frames), FC_NT, smem, st>>>(vmag, obin, hist, g, tb, d_colidx, PW, KW);
@@ -443,17 +485,32 @@ int b2f_fhog_batch(b2f_ctx *ctx, const uint8_t *frames, int n_frames, int rows, 
   if (!fhog_geometry(rows, cols, cell_size, frp, fcp, g)) return B2F_OK;
   if (!hog) { set_error("b2f_fhog_batch: NULL output"); return B2F_EINVAL; }
   B2F_CUDA(cudaSetDevice(ctx->device));
-  size_t in_bytes = (size_t)n_frames * rows * cols * 3, out_n = (size_t)n_frames * g.out_nr * g.out_nc * 31;
-  if ((rc = arena_reserve(ctx, fhog_scratch_bytes(n_frames, g) + align256(in_bytes) + align256(out_n * 4))) != B2F_OK) return rc;
-  unsigned char *d_in = ctx->arena.get<unsigned char>(in_bytes);
-  float *d_out = ctx->arena.get<float>(out_n);
+  const size_t fin = (size_t)rows * cols * 3, fout = (size_t)g.out_nr * g.out_nc * 31;
+  const int C = frames_per_chunk(ctx, fin, n_frames), NCH = ceil_div(n_frames, C);
+  if ((rc = arena_reserve(ctx, fhog_scratch_bytes(C, g) + align256(fin * n_frames) + align256(fout * n_frames * 4))) != B2F_OK) return rc;
+  unsigned char *d_in = ctx->arena.get<unsigned char>(fin * n_frames);
+  float *d_out = ctx->arena.get<float>(fout * n_frames);
   B2F_ARENA_CHECK(ctx);
+  const size_t mark = ctx->arena.off;
   cudaStream_t st = ctx->stream;
-  B2F_CUDA(cudaMemcpyAsync(d_in, frames, in_bytes, cudaMemcpyHostToDevice, st));
-  if ((rc = fhog_device(ctx, d_in, n_frames, g, d_out, st)) != B2F_OK) return rc;
-  B2F_CUDA(cudaMemcpyAsync(hog, d_out, out_n * 4, cudaMemcpyDeviceToHost, st));
-  B2F_CUDA(cudaStreamSynchronize(st));
-  return B2F_OK;
+  if ((rc = pipe_prepare(ctx, 2 * NCH)) != B2F_OK) return rc;
+  for (int c = 0; c < NCH; c++) {          // upload c+1 | kernels c | download c-1 overlap
+    const int f0 = c * C, nf = std::min(C, n_frames - f0);
+    cudaEvent_t e_in = ctx->events[2 * c], e_done = ctx->events[2 * c + 1];
+    rc = B2F_OK;
+    if (cudaMemcpyAsync(d_in + fin * f0, frames + fin * f0, fin * nf, cudaMemcpyHostToDevice, ctx->s_in) != cudaSuccess ||
+        cudaEventRecord(e_in, ctx->s_in) != cudaSuccess || cudaStreamWaitEvent(st, e_in, 0) != cudaSuccess) rc = B2F_ECUDA;
+    ctx->arena.off = mark;
+    if (rc == B2F_OK) rc = fhog_device(ctx, d_in + fin * f0, nf, g, d_out + fout * f0, st);
+    if (rc == B2F_OK && (cudaEventRecord(e_done, st) != cudaSuccess || cudaStreamWaitEvent(ctx->s_out, e_done, 0) != cudaSuccess ||
+                         cudaMemcpyAsync(hog + fout * f0, d_out + fout * f0, fout * nf * 4, cudaMemcpyDeviceToHost, ctx->s_out) != cudaSuccess)) rc = B2F_ECUDA;
+    if (rc != B2F_OK) {
+      if (rc == B2F_ECUDA) set_error("b2f_fhog_batch: CUDA error in chunk %d: %s", c, cudaGetErrorString(cudaGetLastError()));
+      pipe_drain(ctx);
+      return rc;
+    }
+  }
+  return pipe_drain(ctx);
 }
 
 int b2f_fhog_host(b2f_ctx *ctx, const uint8_t *rgb, int rows, int cols, int cell_size, int frp, int fcp, float *hog) {

@@ -275,20 +275,35 @@ int b2f_harris_batch_u8(b2f_ctx *ctx, const uint8_t *frames, int n_frames, int n
   B2F_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   size_t plane = (size_t)nx * ny;
-  int rc = arena_reserve(ctx, harris_scratch_bytes(n_frames, nx, ny, p, cap) + align256(plane * n_frames));
+  const int C = frames_per_chunk(ctx, plane, n_frames), NCH = ceil_div(n_frames, C);
+  int rc = arena_reserve(ctx, harris_scratch_bytes(C, nx, ny, p, cap) + align256(plane * n_frames) +
+                                  2 * align256((size_t)n_frames * cap * 4) + align256(n_frames * 4));
   if (rc != B2F_OK) return rc;
   unsigned char *d_f = ctx->arena.get<unsigned char>(plane * n_frames);
-  float *d_R = ctx->arena.get<float>(plane * n_frames);
   int *d_xy = ctx->arena.get<int>((size_t)n_frames * cap);
   float *d_s = ctx->arena.get<float>((size_t)n_frames * cap);
   int *d_cnt = ctx->arena.get<int>(n_frames);
   B2F_ARENA_CHECK(ctx);
-  B2F_CUDA(cudaMemcpyAsync(d_f, frames, plane * n_frames, cudaMemcpyHostToDevice, st));
-  if (nx < 3 || ny < 3) { for (int f = 0; f < n_frames; f++) counts[f] = 0; return B2F_OK; }
-  if ((rc = harris_response_device(ctx, d_f, true, n_frames, nx, ny, p, harris_exact_flag(p), d_R, st)) != B2F_OK) return rc;
+  const size_t mark = ctx->arena.off;
   const int radius = 2 * p->sigma_i + 0.5;
-  if (ny <= 2 * radius + 1 || nx <= 2 * radius + 1) { for (int f = 0; f < n_frames; f++) counts[f] = 0; B2F_CUDA(cudaStreamSynchronize(st)); return B2F_OK; }
-  if ((rc = harris_nms_device(ctx, d_R, n_frames, nx, ny, p->threshold, radius, cap, d_xy, d_s, d_cnt, st)) != B2F_OK) return rc;
+  const bool tiny = nx < 3 || ny < 3 || ny <= 2 * radius + 1 || nx <= 2 * radius + 1;   // harris.cpp:493 / no pixel has a full window
+  if (tiny) { for (int f = 0; f < n_frames; f++) counts[f] = 0; return B2F_OK; }
+  if ((rc = pipe_prepare(ctx, NCH)) != B2F_OK) return rc;
+  for (int c = 0; c < NCH; c++) {          // upload c+1 overlaps the kernels of chunk c
+    const int f0 = c * C, nf = std::min(C, n_frames - f0);
+    rc = B2F_OK;
+    if (cudaMemcpyAsync(d_f + plane * f0, frames + plane * f0, plane * nf, cudaMemcpyHostToDevice, ctx->s_in) != cudaSuccess ||
+        cudaEventRecord(ctx->events[c], ctx->s_in) != cudaSuccess || cudaStreamWaitEvent(st, ctx->events[c], 0) != cudaSuccess) {
+      set_error("b2f_harris_batch_u8: CUDA error in chunk %d: %s", c, cudaGetErrorString(cudaGetLastError()));
+      rc = B2F_ECUDA;
+    }
+    ctx->arena.off = mark;
+    float *d_R = ctx->arena.get<float>(plane * nf);
+    if (rc == B2F_OK && !d_R) { set_error("internal: scratch arena under-reserved in b2f_harris_batch_u8"); rc = B2F_ENOMEM; }
+    if (rc == B2F_OK) rc = harris_response_device(ctx, d_f + plane * f0, true, nf, nx, ny, p, harris_exact_flag(p), d_R, st);
+    if (rc == B2F_OK) rc = harris_nms_device(ctx, d_R, nf, nx, ny, p->threshold, radius, cap, d_xy + (size_t)f0 * cap, d_s + (size_t)f0 * cap, d_cnt + f0, st);
+    if (rc != B2F_OK) { pipe_drain(ctx); return rc; }
+  }
   if ((rc = pinned_reserve(ctx, (size_t)n_frames * cap * 8 + n_frames * 4)) != B2F_OK) return rc;
   int *h_xy = (int *)ctx->pinned;
   float *h_s = (float *)(h_xy + (size_t)n_frames * cap);

@@ -52,7 +52,7 @@ def image_fhog(x, cell_size=8, filter_rows_padding=1, filter_cols_padding=1):
     return out
 
 
-def fhog_batch(frames, cell=8, frp=1, fcp=1, out=None):
+def fhog_batch(frames, cell=8, frp=1, fcp=1, out=None, ctx=None):
     """Batch form (new surface): uint8 [n, rows, cols, 3] -> float32 [n, hog_nr, hog_nc, 31].
     `out` may be a preallocated (e.g. pinned) float32 array of that shape."""
     lib = _lib.load()
@@ -61,7 +61,7 @@ def fhog_batch(frames, cell=8, frp=1, fcp=1, out=None):
     nr, nc = fhog_size(rows, cols, cell, frp, fcp)
     hog = out if out is not None else np.zeros((n, nr, nc, 31), np.float32)
     if nr * nc:
-        _lib.check(lib.b2f_fhog_batch(_lib.context(), _lib.ptr(f), n, rows, cols, int(cell), int(frp), int(fcp), _lib.ptr(hog)))
+        _lib.check(lib.b2f_fhog_batch(ctx or _lib.context(), _lib.ptr(f), n, rows, cols, int(cell), int(frp), int(fcp), _lib.ptr(hog)))
     return hog
 
 

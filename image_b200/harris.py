@@ -88,7 +88,7 @@ def image_harris(x, k=0.06, sigma_d=1.0, sigma_i=2.5, threshold=130, gaussian=GA
                           cells=cells, verbose=verbose, exact=exact)
 
 
-def harris_batch_u8(frames, cap=65536, raw=False, **kw):
+def harris_batch_u8(frames, cap=65536, raw=False, ctx=None, **kw):
     """Batch form (new surface): frames uint8 [n, ny, nx] in host memory -> list of dict(x,y,strength)
     in raster order.  Keyword arguments as detect_corners (C++ integer meaning)."""
     lib = _lib.load()
@@ -101,7 +101,7 @@ def harris_batch_u8(frames, cap=65536, raw=False, **kw):
                                            "Nselect", "measure", "Nscales", "precision", "cells", "verbose", "exact")])
     x = np.zeros((n, cap), np.float32); y = np.zeros((n, cap), np.float32); s = np.zeros((n, cap), np.float32)
     cnt = np.zeros(n, np.int32)
-    _lib.check(lib.b2f_harris_batch_u8(_lib.context(), _lib.ptr(f), n, nx, ny, C.byref(p), int(cap),
+    _lib.check(lib.b2f_harris_batch_u8(ctx or _lib.context(), _lib.ptr(f), n, nx, ny, C.byref(p), int(cap),
                                        _lib.ptr(x), _lib.ptr(y), _lib.ptr(s), _lib.ptr(cnt)))
     if raw:     # padded [n, cap] arrays + counts, no per-frame copies
         return x, y, s, cnt

@@ -49,6 +49,9 @@ void b2f_free(void *p);
 void *b2f_stream(b2f_ctx *ctx);
 /* kernels launched by this context since creation (bench.py reports it as gpu_launches) */
 long long b2f_launch_count(b2f_ctx *ctx);
+/* The host batch calls (*_batch) cut their frames into chunks of about `bytes` input bytes (default 24 MiB)
+ * so that the upload of chunk c+1, the kernels of chunk c and the download of chunk c-1 overlap. */
+int b2f_set_chunk_bytes(b2f_ctx *ctx, size_t bytes);
 
 /* ------------------------------------------------------------------------------ Harris ----
  * Integer fields carry the C++ meaning seen at the .Call boundary (gaussian.h:14-16,

@@ -1,0 +1,103 @@
+"""Chunked / pipelined host batches (b2f_*_batch): cutting a batch into several chunks that overlap
+upload, kernels and download must not change a single byte, and concurrent calls on separate
+contexts from separate host threads must not disturb each other."""
+import threading
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def small_chunks():
+    from image_b200 import _lib
+    lib = _lib.load()
+    ctx = _lib.new_context()
+    _lib.check(lib.b2f_set_chunk_bytes(ctx, 3 * 150 * 210))       # 3 grey frames (1 RGB frame) per chunk
+    yield ctx
+    lib.b2f_shutdown(ctx)
+
+
+def _frames(n, ny=150, nx=210):
+    from image_b200 import synth
+    return np.stack([synth.frame_shapes(900 + i, ny, nx) for i in range(n)])
+
+
+def test_canny_batch_chunked_equals_oracle(oracle, small_chunks):
+    from image_b200.canny import canny_batch
+    f = _frames(8)
+    edges, nz = canny_batch(f, ctx=small_chunks)                   # chunks of 3, 3, 2 frames
+    one, nz1 = canny_batch(f)                                       # default context: a single chunk
+    assert np.array_equal(edges, one) and np.array_equal(nz, nz1)
+    for i in (0, 3, 7):
+        e, cnt = oracle.canny(f[i])
+        assert int(nz[i]) == cnt and np.array_equal(edges[i], e)
+
+
+def test_harris_batch_chunked_equals_single_chunk(small_chunks):
+    from image_b200.harris import harris_batch_u8
+    f = _frames(7)
+    a = harris_batch_u8(f, cap=4096, raw=True, ctx=small_chunks, threshold=10.0)
+    b = harris_batch_u8(f, cap=4096, raw=True, threshold=10.0)
+    assert np.array_equal(a[3], b[3]) and a[3].sum() > 0
+    for q in range(3):
+        assert np.array_equal(a[q], b[q])
+
+
+def test_fhog_batch_chunked_equals_oracle(oracle, small_chunks):
+    from image_b200 import synth
+    from image_b200.dlib import fhog_batch
+    f = np.stack([synth.frame_rgb(950 + i, 150, 210) for i in range(5)])
+    a = fhog_batch(f, ctx=small_chunks)                             # 5 chunks of one frame
+    b = fhog_batch(f)
+    assert np.array_equal(a, b)
+    for i in (0, 4):
+        assert np.array_equal(a[i], oracle.fhog(f[i]))
+
+
+def test_fhog_tables_follow_the_geometry(oracle):
+    """The vote tables are cached per (rows, cols, cell): alternate geometries on one context."""
+    from image_b200 import synth
+    from image_b200.dlib import fhog_batch
+    for (ny, nx, cell) in [(96, 128, 8), (97, 131, 8), (96, 128, 4), (96, 128, 8), (64, 200, 6)]:
+        f = synth.frame_rgb(7, ny, nx)[None]
+        assert np.array_equal(fhog_batch(f, cell=cell)[0], oracle.fhog(f[0], cell=cell)), (ny, nx, cell)
+
+
+def test_three_detectors_from_three_threads(oracle):
+    from image_b200 import _lib, synth
+    from image_b200.canny import canny_batch
+    from image_b200.dlib import fhog_batch
+    from image_b200.harris import harris_batch_u8
+    lib = _lib.load()
+    rgb = np.stack([synth.frame_rgb(980 + i, 270, 480) for i in range(6)])
+    grey = (rgb.astype(np.uint16).sum(axis=3) // 3).astype(np.uint8)
+    ctxs = [_lib.new_context() for _ in range(3)]
+    for c in ctxs:
+        _lib.check(lib.b2f_set_chunk_bytes(c, 2 * 270 * 480))
+    out = {}
+    errs = []
+
+    def run(name, fn):
+        try:
+            for _ in range(3):
+                out[name] = fn()
+        except Exception as ex:      # surfaced below
+            errs.append((name, ex))
+    th = [threading.Thread(target=run, args=("harris", lambda: harris_batch_u8(grey, cap=8192, raw=True, ctx=ctxs[0], threshold=10.0))),
+          threading.Thread(target=run, args=("canny", lambda: canny_batch(grey, ctx=ctxs[1]))),
+          threading.Thread(target=run, args=("fhog", lambda: fhog_batch(rgb, ctx=ctxs[2])))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    ref_h = harris_batch_u8(grey, cap=8192, raw=True, threshold=10.0)
+    for q in range(4):
+        assert np.array_equal(out["harris"][q], ref_h[q])
+    e, cnt = oracle.canny(grey[2])
+    assert np.array_equal(out["canny"][0][2], e) and int(out["canny"][1][2]) == cnt
+    assert np.array_equal(out["fhog"][5], oracle.fhog(rgb[5]))
+    for c in ctxs:
+        lib.b2f_shutdown(c)

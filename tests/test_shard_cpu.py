@@ -59,3 +59,18 @@ def test_rshim_sources_compile_against_rcpp_interface():
         if f.endswith(".cpp"):
             subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-I" + os.path.join(ROOT, "oracle", "stubs"),
                                    "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "image_b200", "rshim", f)])
+
+
+def test_gpu_numa_cpus_from_a_fake_sysfs(tmp_path):
+    from image_b200.shard import gpu_numa_cpus, _parse_cpulist
+    assert _parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    dev = tmp_path / "bus/pci/devices/0000:1b:00.0"
+    dev.mkdir(parents=True)
+    (dev / "numa_node").write_text("1\n")
+    node = tmp_path / "devices/system/node/node1"
+    node.mkdir(parents=True)
+    (node / "cpulist").write_text("32-63\n")
+    assert gpu_numa_cpus("00000000:1B:00.0", sysfs=str(tmp_path)) == set(range(32, 64))
+    (dev / "numa_node").write_text("-1\n")
+    assert gpu_numa_cpus("0000:1b:00.0", sysfs=str(tmp_path)) is None
+    assert gpu_numa_cpus("0000:ff:00.0", sysfs=str(tmp_path)) is None
