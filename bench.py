@@ -310,6 +310,27 @@ def main():
     if "fhog" in dets:
         detail["fhog_ms"] = t_of(lambda: Dl.fhog_dev(d_rgb, B, NY, NX, d_hog, stream=sp, **FHOG_KW))
 
+    per_det = {"harris": {"device_ms_per_frame": (th + tn) / B, "device_mpix_s": B * NX * NY / ((th + tn) * 1e-3) / 1e6}}
+    if "canny" in dets:
+        per_det["canny"] = {"device_ms_per_frame": detail["canny_ms"] / B, "device_mpix_s": B * NX * NY / (detail["canny_ms"] * 1e-3) / 1e6}
+    if "fhog" in dets:
+        per_det["fhog"] = {"device_ms_per_frame": detail["fhog_ms"] / B, "device_mpix_s": B * NX * NY / (detail["fhog_ms"] * 1e-3) / 1e6}
+    if "fhog" in dets and rank == 0 and not os.environ.get("B2F_BENCH_NO_SURF"):
+        # SURF (SURVEY.md 8d, config C4 recipe: Gaussian blobs) is reported beside the headline, not inside it:
+        # host API, pinned frames in, key points + descriptors back on the host.
+        try:
+            nsf = 4
+            blobs = np.stack([synth.frame_blobs(3000 + (i % 2), NY, NX) for i in range(nsf)])
+            h_blobs = torch.from_numpy(blobs).pin_memory().numpy()
+            Dl.surf_batch(h_blobs)
+            t0 = time.perf_counter()
+            so = Dl.surf_batch(h_blobs)
+            dts = time.perf_counter() - t0
+            per_det["surf"] = {"e2e_ms_per_frame": dts / nsf * 1e3, "e2e_mpix_s": nsf * NX * NY / dts / 1e6, "frames": nsf,
+                               "points_per_frame": int(np.mean([o["points"] for o in so])), "max_points": 10000, "detection_threshold": 30.0}
+        except Exception as ex:
+            per_det["surf"] = {"error": str(ex)}
+
     # ---- roofline of the dominant target kernel: fused Harris gradient+response, 5 B/px algorithmic
     peak, peak_src = peaks()
     alg_bytes = 5.0 * B * NX * NY
@@ -423,7 +444,7 @@ def main():
                        "parallelism": "frames sharded over %d GPU(s), no data-path collective" % world,
                        "host_affinity": ("GPU NUMA node, %d cpus" % len(aff_new)) if aff_new else "unchanged (NUMA node of the GPU unknown)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
-            "detail_ms_per_step": detail,
+            "detail_ms_per_step": detail, "per_detector": per_det,
         }
         print(json.dumps(line))
     if world > 1:

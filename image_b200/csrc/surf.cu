@@ -85,13 +85,43 @@ __global__ void surf_grey_rowscan(const unsigned char *__restrict__ rgb, int *__
     carry += __shfl_sync(0xffffffffu, incl, 31);
   }
 }
-// one thread per column: running sum down the rows (coalesced across the warp)
-__global__ void surf_colscan(int *__restrict__ sat, int rows, int cols) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// Column pass of the SAT in two sweeps over row segments of SEG_ROWS rows (all columns of a segment in
+// parallel, loads batched 8 rows deep): segment sums first, then every (column, segment) thread adds up the
+// sums of the segments above it and scans its own rows.  Integer adds: the result does not depend on the split.
+constexpr int SEG_ROWS = 96;
+__global__ void surf_colsum_kernel(const int *__restrict__ sat, int *__restrict__ segsum, int rows, int cols, int nseg) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, sgm = blockIdx.y, f = blockIdx.z;
   if (c >= cols) return;
-  int *p = sat + (size_t)blockIdx.y * rows * (size_t)cols + c;
+  const int r0 = sgm * SEG_ROWS, r1 = min(r0 + SEG_ROWS, rows);
+  const int *p = sat + (size_t)f * rows * (size_t)cols + c;
   int acc = 0;
-  for (int r = 0; r < rows; r++) { acc += p[(size_t)r * cols]; p[(size_t)r * cols] = acc; }
+  int r = r0;
+  for (; r + 8 <= r1; r += 8) {
+    int v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = __ldg(p + (size_t)(r + k) * cols);
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc += v[k];
+  }
+  for (; r < r1; r++) acc += __ldg(p + (size_t)r * cols);
+  segsum[((size_t)f * nseg + sgm) * cols + c] = acc;
+}
+__global__ void surf_colscan(int *__restrict__ sat, const int *__restrict__ segsum, int rows, int cols, int nseg) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, sgm = blockIdx.y, f = blockIdx.z;
+  if (c >= cols) return;
+  int acc = 0;
+  for (int k = 0; k < sgm; k++) acc += __ldg(segsum + ((size_t)f * nseg + k) * cols + c);
+  const int r0 = sgm * SEG_ROWS, r1 = min(r0 + SEG_ROWS, rows);
+  int *p = sat + (size_t)f * rows * (size_t)cols + c;
+  int r = r0;
+  for (; r + 8 <= r1; r += 8) {
+    int v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = p[(size_t)(r + k) * cols];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { acc += v[k]; p[(size_t)(r + k) * cols] = acc; }
+  }
+  for (; r < r1; r++) { acc += p[(size_t)r * cols]; p[(size_t)r * cols] = acc; }
 }
 
 __device__ __forceinline__ int sat_box(const int *__restrict__ S, int nc, int l, int t, int r, int b) {
@@ -344,7 +374,7 @@ static bool rect_inside(int rows, int cols, double cx, double cy, unsigned long 
 
 size_t surf_scratch_bytes(int n_frames, const SurfGeom &g, int cand_cap, size_t max_keys) {
   size_t px = (size_t)n_frames * g.rows * g.cols;
-  return align256(px * 4) + align256((size_t)n_frames * g.pyr_per_frame * 8) + align256((size_t)n_frames * cand_cap * sizeof(SurfCand)) +
+  return align256(px * 4) + align256((size_t)n_frames * (g.rows / 96 + 1) * g.cols * 4) /*SAT segment sums*/ + align256((size_t)n_frames * g.pyr_per_frame * 8) + align256((size_t)n_frames * cand_cap * sizeof(SurfCand)) +
          align256(n_frames * 4) + align256(max_keys * sizeof(SurfKey)) + align256(max_keys * 8) + align256(max_keys * 64 * 8) + (1 << 16);
 }
 
@@ -360,8 +390,15 @@ int surf_device(b2f_ctx *ctx, const unsigned char *d_rgb, int n_frames, const Su
   B2F_ARENA_CHECK(ctx);
   surf_grey_rowscan<<<dim3(ceil_div(rows, 8), n_frames), 256, 0, st>>>(d_rgb, sat, rows, cols);
   B2F_LAUNCH_CHECK(ctx);
-  surf_colscan<<<dim3(ceil_div(cols, 128), n_frames), 128, 0, st>>>(sat, rows, cols);
-  B2F_LAUNCH_CHECK(ctx);
+  {
+    const int nseg = ceil_div(rows, SEG_ROWS);
+    int *segsum = ctx->arena.get<int>((size_t)n_frames * nseg * cols);
+    B2F_ARENA_CHECK(ctx);
+    surf_colsum_kernel<<<dim3(ceil_div(cols, 128), nseg, n_frames), 128, 0, st>>>(sat, segsum, rows, cols, nseg);
+    B2F_LAUNCH_CHECK(ctx);
+    surf_colscan<<<dim3(ceil_div(cols, 128), nseg, n_frames), 128, 0, st>>>(sat, segsum, rows, cols, nseg);
+    B2F_LAUNCH_CHECK(ctx);
+  }
   B2F_CUDA(cudaMemsetAsync(pyr, 0, sizeof(double) * (size_t)n_frames * g.pyr_per_frame, st));   // the unread rim
   B2F_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * n_frames, st));
   {
