@@ -596,6 +596,236 @@ canny_grad_nms_spec_kernel(const float *__restrict__ data, unsigned char *__rest
   if (fallback_count && threadIdx.x == 0 && nq) atomicAdd(fallback_count, (unsigned long long)nq);
 }
 
+// ------------------------------------------------------------------------------------------ gradient + NMS, speculative (v2)
+// Same two tiers and the same certification as canny_grad_nms_spec_kernel, with about a third of the
+// instructions (that kernel is issue-bound):
+//   * data tile 36x36 (clamped coordinates at load, so the gradient needs no clamping at all), gradient
+//     tile 34x34;
+//   * gradient: one thread per (column, strip of 5 rows) slides down its strip with the three columns of
+//     the two previous rows in registers: 3 shared loads per pixel instead of 8, row differences reused;
+//   * direction: xt, yt lie in [-1, 1], so floor() is a sign test; the opposite neighbour mirrors the
+//     cell and swaps the bilinear weights; approximate reciprocal / square root, their error is part of
+//     the bound (4e-7*g instead of 3e-7*g; 5e-7 on the cosines as before).
+constexpr int SG_DW = CG_T + 4;   // data tile, origin (x0-2, y0-2)
+constexpr int SG_GW = CG_T + 2;   // gradient tile, origin (x0-1, y0-1)
+constexpr int SG_K = 5;           // rows per gradient strip: 7 strips x 34 columns = 238 work items
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+__device__ __forceinline__ void exact_hv2(const float *d, int accGrad, double &h, double &v) {   // pitch SG_DW
+#define DD(dx, dy) ((double)d[(dy) * SG_DW + (dx)])
+  if (accGrad) {
+    h = __dmul_rn(2.0, __dsub_rn(DD(1, 0), DD(-1, 0)));
+    h = __dadd_rn(h, DD(1, 1)); h = __dsub_rn(h, DD(-1, 1)); h = __dadd_rn(h, DD(1, -1)); h = __dsub_rn(h, DD(-1, -1));
+    v = __dmul_rn(2.0, __dsub_rn(DD(0, 1), DD(0, -1)));
+    v = __dadd_rn(v, DD(1, 1)); v = __dsub_rn(v, DD(1, -1)); v = __dadd_rn(v, DD(-1, 1)); v = __dsub_rn(v, DD(-1, -1));
+  } else {
+    h = __dsub_rn(DD(1, 0), DD(-1, 0));
+    v = __dsub_rn(DD(0, 1), DD(0, -1));
+  }
+#undef DD
+}
+
+template <bool ACC>
+__global__ void __launch_bounds__(CG_NT)
+canny_grad_nms_spec2_kernel(const float *__restrict__ data, unsigned char *__restrict__ cls, int nx, int ny,
+                            int low_thr, int high_thr, unsigned long long *__restrict__ fallback_count) {
+  __shared__ float sd[SG_DW * SG_DW];
+  __shared__ float fg[SG_GW * SG_GW];
+  __shared__ float2 fhv[SG_GW * SG_GW];
+  __shared__ float s_emax[CG_NT / 32];
+  __shared__ unsigned char scls[CG_T * CG_T];
+  __shared__ unsigned short squeue[CG_T * CG_T];
+  __shared__ double sg2[28 * 9];
+  __shared__ int qn;
+  const int x0 = blockIdx.x * CG_T, y0 = blockIdx.y * CG_T;
+  const float *src = data + (size_t)blockIdx.z * nx * ny;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) qn = 0;
+  {   // data tile, clamped coordinates; all loads of a thread are issued before its stores
+    const int c0 = min(max(x0 - 2 + lane, 0), nx - 1), c1 = min(max(x0 - 2 + lane + 32, 0), nx - 1);
+    float a[5], b[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+      const int j = min(warp + 8 * k, SG_DW - 1);
+      const float *row = src + (size_t)min(max(y0 - 2 + j, 0), ny - 1) * nx;
+      a[k] = __ldg(row + c0);
+      b[k] = lane < SG_DW - 32 ? __ldg(row + c1) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+      const int j = warp + 8 * k;
+      if (j < SG_DW) { sd[j * SG_DW + lane] = a[k]; if (lane < SG_DW - 32) sd[j * SG_DW + lane + 32] = b[k]; }
+    }
+  }
+  __syncthreads();
+  // ---- tier-1 gradient tile.  Differences first (exact or nearly so): the rounding error then scales with
+  // the local contrast S = sum |terms|:  |dh|,|dv| <= 3*2^-24*S,  |d grad| <= sqrt2*max(|dh|,|dv|) + 1.8e-7*grad
+  // (h*h+v*v and the approximate root).  E is about twice that; its tile maximum is this CTA's tolerance unit.
+  float emax = 0.f;
+  if (threadIdx.x < 7 * SG_GW) {
+    const int strip = threadIdx.x / SG_GW, c = threadIdx.x - strip * SG_GW;
+    const int r0 = strip * SG_K, r1 = min(r0 + SG_K, SG_GW);
+    const float *d = sd + r0 * SG_DW + c;          // data (row r0, col c) = gradient pixel (r0, c) shifted by (-1, -1)
+    float l0 = d[0], m0 = d[1], q0 = d[2];
+    float l1 = d[SG_DW], q1 = d[SG_DW + 2];
+    float dh0 = q0 - l0, dh1 = q1 - l1;
+    d += 2 * SG_DW;
+#pragma unroll
+    for (int k = 0; k < SG_K; k++) {
+      if (r0 + k < r1) {
+        const float l2 = d[0], m2 = d[1], q2 = d[2];
+        const float dh2 = q2 - l2;
+        float h, v, S;
+        const float vy = m2 - m0;
+        if (ACC) {
+          const float vp = q2 - q0, vm = l2 - l0;
+          h = fmaf(2.f, dh1, dh2 + dh0);
+          v = fmaf(2.f, vy, vp + vm);
+          S = fmaf(2.f, fabsf(dh1) + fabsf(vy), (fabsf(dh2) + fabsf(dh0)) + (fabsf(vp) + fabsf(vm)));
+        } else {
+          h = dh1; v = vy;
+          S = fabsf(h) + fabsf(v);
+        }
+        const float g = sqrt_approx(fmaf(h, h, v * v));
+        const int gi = (r0 + k) * SG_GW + c;
+        fg[gi] = g;
+        fhv[gi] = make_float2(h, v);
+        emax = fmaxf(emax, fmaf(6e-7f, S, 4e-7f * g));
+        l0 = l1; q0 = q1; dh0 = dh1;
+        m0 = d[1 - SG_DW];                          // centre of the row that becomes "previous"
+        l1 = l2; q1 = q2; dh1 = dh2;
+        d += SG_DW;
+      }
+    }
+  }
+  for (int o = 16; o; o >>= 1) emax = fmaxf(emax, __shfl_xor_sync(0xffffffffu, emax, o));
+  if (lane == 0) s_emax[warp] = emax;
+  __syncthreads();
+  float E = s_emax[0];
+#pragma unroll
+  for (int w = 1; w < CG_NT / 32; w++) E = fmaxf(E, s_emax[w]);
+  E = fmaxf(E, 1e-7f);
+  const bool interior = x0 >= 1 && y0 >= 1 && x0 + CG_T + 1 <= nx && y0 + CG_T + 1 <= ny;
+  const float lowf = (float)low_thr, highf = (float)high_thr;
+  const float T0 = 2.f * E;                                      // 2 x bound on |d grad| anywhere in this tile
+#pragma unroll
+  for (int k = 0; k < CG_T * CG_T / CG_NT; k++) {
+    const int t = threadIdx.x + k * CG_NT;
+    const int ly = t >> 5, lx = t & 31;
+    const int gx = x0 + lx, gy = y0 + ly;
+    unsigned char c = 0;
+    if (gx < nx && gy < ny) {
+      const int ci = (ly + 1) * SG_GW + lx + 1;
+      const float now = fg[ci];
+      bool undecided = false;
+      if (now < lowf - T0) c = 0;                                // certainly now <= low
+      else if (now <= lowf + T0) undecided = true;
+      else {
+        const float inv = rcp_approx(now);
+        const float2 hv = fhv[ci];
+        const float cs = hv.x * inv, sn = hv.y * inv;
+        const float dcs = 8.f * fmaf(E, inv, 5e-7f);             // bound on |d cos|, |d sin| (x4 margin)
+        // "+" neighbour at (cs, sn): cell corner and weights; the "-" neighbour mirrors the cell and swaps the weights
+        const int ngx = cs < 0.f, ngy = sn < 0.f;
+        const float wbx = cs + (float)ngx, wax = 1.f - wbx, wby = sn + (float)ngy, way = 1.f - wby;
+        float p11, p12, p21, p22, m11, m12, m21, m22;
+        if (interior) {
+          const float *gp = fg + (ly + 1 - ngy) * SG_GW + (lx + 1 - ngx);
+          const float *gm = fg + (ly + ngy) * SG_GW + (lx + ngx);
+          p11 = gp[0]; p12 = gp[1]; p21 = gp[SG_GW]; p22 = gp[SG_GW + 1];
+          m11 = gm[0]; m12 = gm[1]; m21 = gm[SG_GW]; m22 = gm[SG_GW + 1];
+        } else {     // value(): neighbour coordinates clamp to the image
+          const int ox = x0 - 1, oy = y0 - 1;
+          const int px1 = min(max(gx - ngx, 0), nx - 1) - ox, px2 = min(max(gx - ngx + 1, 0), nx - 1) - ox;
+          const int py1 = min(max(gy - ngy, 0), ny - 1) - oy, py2 = min(max(gy - ngy + 1, 0), ny - 1) - oy;
+          const int mx1 = min(max(gx + ngx - 1, 0), nx - 1) - ox, mx2 = min(max(gx + ngx, 0), nx - 1) - ox;
+          const int my1 = min(max(gy + ngy - 1, 0), ny - 1) - oy, my2 = min(max(gy + ngy, 0), ny - 1) - oy;
+          p11 = fg[py1 * SG_GW + px1]; p12 = fg[py1 * SG_GW + px2]; p21 = fg[py2 * SG_GW + px1]; p22 = fg[py2 * SG_GW + px2];
+          m11 = fg[my1 * SG_GW + mx1]; m12 = fg[my1 * SG_GW + mx2]; m21 = fg[my2 * SG_GW + mx1]; m22 = fg[my2 * SG_GW + mx2];
+        }
+        const float nbp = way * fmaf(wax, p11, wbx * p12) + wby * fmaf(wax, p21, wbx * p22);
+        const float nbm = wby * fmaf(wbx, m11, wax * m12) + way * fmaf(wbx, m21, wax * m22);
+        const float spp = fmaxf(fmaxf(p11, p12), fmaxf(p21, p22)) - fminf(fminf(p11, p12), fminf(p21, p22));
+        const float spm = fmaxf(fmaxf(m11, m12), fmaxf(m21, m22)) - fminf(fminf(m11, m12), fminf(m21, m22));
+        const float tolp = fmaf(dcs, spp, 2.f * T0), tolm = fmaf(dcs, spm, 2.f * T0);
+        // the direction is ambiguous for the reference's floor() when a cosine is within its error of 0
+        if (fabsf(cs) <= dcs || fabsf(sn) <= dcs) undecided = true;
+        else if (now < nbp - tolp || now < nbm - tolm) c = 0;       // certainly suppressed
+        else if (now > nbp + tolp && now > nbm + tolm) {            // certainly a maximum
+          if (now >= highf + T0) c = 2;
+          else if (now < highf - T0) c = 1;
+          else undecided = true;
+        } else undecided = true;
+      }
+      if (undecided) squeue[atomicAdd(&qn, 1)] = (unsigned short)t;
+    }
+    scls[t] = c;
+  }
+  __syncthreads();
+  // ---- tier 2: the undecided pixels of this tile, exactly as in canny_grad_nms_spec_kernel
+  const int nq = qn;
+  double *eg = sg2;                                              // [chunk][9]
+  for (int qb = 0; qb < nq; qb += 28) {
+    const int nc = min(28, nq - qb);
+    for (int i = threadIdx.x; i < nc * 9; i += CG_NT) {
+      const int qi = i / 9, k = i - qi * 9;
+      const int t = squeue[qb + qi], ly = t >> 5, lx = t & 31;
+      const int px = min(max(x0 + lx + (k % 3) - 1, 0), nx - 1), py = min(max(y0 + ly + (k / 3) - 1, 0), ny - 1);
+      double h, v;
+      exact_hv2(sd + (py - (y0 - 2)) * SG_DW + (px - (x0 - 2)), ACC, h, v);
+      eg[i] = hypot_glibc(h, v);
+    }
+    __syncthreads();
+    for (int qi = threadIdx.x; qi < nc; qi += CG_NT) {
+      const int t = squeue[qb + qi], ly = t >> 5, lx = t & 31;
+      const int gx = x0 + lx, gy = y0 + ly;
+      const double *g9 = eg + qi * 9;
+      double h, v;
+      exact_hv2(sd + (gy - (y0 - 2)) * SG_DW + (gx - (x0 - 2)), ACC, h, v);
+      const double now = g9[4];
+      unsigned char c;
+      if (now <= (double)low_thr) c = 0;
+      else {
+        double sn, cs;
+        if (h == 0.0 || v == 0.0) { const double th = atan2(v, h); sincos(th, &sn, &cs); }
+        else { const double inv = __ddiv_rn(1.0, now); cs = __dmul_rn(h, inv); sn = __dmul_rn(v, inv); }
+        double nb[2];
+        for (int s2 = 0; s2 < 2; s2++) {
+          const double dir = s2 ? 1.0 : -1.0;
+          const double xt = __dmul_rn(dir, cs), yt = __dmul_rn(dir, sn);
+          const double x1 = floor(xt), x2 = __dadd_rn(x1, 1.0), y1 = floor(yt), y2 = __dadd_rn(y1, 1.0);
+          auto G = [&](double ox, double oy) -> double {
+            const int ix = (int)ox, iy = (int)oy;
+            if (ix > 1 || iy > 1) return 0.0;                    // multiplied by a zero weight (xt or yt == 1)
+            const int cxp = min(max(gx + ix, 0), nx - 1) - gx, cyp = min(max(gy + iy, 0), ny - 1) - gy;
+            return g9[(cyp + 1) * 3 + (cxp + 1)];
+          };
+          const double wa = __dsub_rn(x2, xt), wb = __dsub_rn(xt, x1);
+          const double g1 = __dadd_rn(__dmul_rn(wa, G(x1, y1)), __dmul_rn(wb, G(x2, y1)));
+          const double g2 = __dadd_rn(__dmul_rn(wa, G(x1, y2)), __dmul_rn(wb, G(x2, y2)));
+          nb[s2] = __dadd_rn(__dmul_rn(__dsub_rn(y2, yt), g1), __dmul_rn(__dsub_rn(yt, y1), g2));
+        }
+        if (now <= nb[0] || now <= nb[1]) c = 0;
+        else c = now >= (double)high_thr ? 2 : 1;
+      }
+      scls[t] = c;
+    }
+    __syncthreads();
+  }
+  // ---- class bytes out, one 32-bit word per thread
+  {
+    const int ly = threadIdx.x >> 3, wq = threadIdx.x & 7;
+    const int gy = y0 + ly, gx = x0 + 4 * wq;
+    unsigned char *dst = cls + (size_t)blockIdx.z * nx * ny + (size_t)gy * nx + gx;
+    if (gy < ny) {
+      if ((nx & 3) == 0 && gx + 3 < nx) *reinterpret_cast<unsigned *>(dst) = *reinterpret_cast<const unsigned *>(scls + ly * CG_T + 4 * wq);
+      else for (int q = 0; q < 4; q++) if (gx + q < nx) dst[q] = scls[ly * CG_T + 4 * wq + q];
+    }
+  }
+  if (fallback_count && threadIdx.x == 0 && nq) atomicAdd(fallback_count, (unsigned long long)nq);
+}
+
 // ------------------------------------------------------------------------------------------ hysteresis
 // Two-level union-find.  Level 1: every 32x32 tile resolves its own connectivity in shared memory
 // (no global atomics) and publishes, for each edge pixel, the GLOBAL index of its tile-local root.
@@ -930,8 +1160,14 @@ int canny_device(b2f_ctx *ctx, const unsigned char *d_frames, int n_frames, int 
     static const bool stats = getenv("B2F_CANNY_STATS") != nullptr;
     unsigned long long *fc = stats ? reinterpret_cast<unsigned long long *>(flags + 8) : nullptr;
     if (stats) B2F_CUDA(cudaMemsetAsync(fc, 0, 8, st));
-    canny_grad_nms_spec_kernel<<<dim3(TX, TY, n_frames), CG_NT, 0, st>>>(
-        blur, cls, nx, ny, acc_grad ? 1 : 0, (int)low_thr, (int)high_thr, fc);
+    static const bool spec1 = getenv("B2F_CANNY_SPEC1") != nullptr;
+    if (spec1)
+      canny_grad_nms_spec_kernel<<<dim3(TX, TY, n_frames), CG_NT, 0, st>>>(
+          blur, cls, nx, ny, acc_grad ? 1 : 0, (int)low_thr, (int)high_thr, fc);
+    else if (acc_grad)
+      canny_grad_nms_spec2_kernel<true><<<dim3(TX, TY, n_frames), CG_NT, 0, st>>>(blur, cls, nx, ny, (int)low_thr, (int)high_thr, fc);
+    else
+      canny_grad_nms_spec2_kernel<false><<<dim3(TX, TY, n_frames), CG_NT, 0, st>>>(blur, cls, nx, ny, (int)low_thr, (int)high_thr, fc);
     if (stats) {
       unsigned long long h = 0;
       B2F_CUDA(cudaMemcpyAsync(&h, fc, 8, cudaMemcpyDeviceToHost, st));
