@@ -606,8 +606,10 @@ canny_grad_nms_spec_kernel(const float *__restrict__ data, unsigned char *__rest
 //   * direction: xt, yt lie in [-1, 1], so floor() is a sign test; the opposite neighbour mirrors the
 //     cell and swaps the bilinear weights; approximate reciprocal / square root, their error is part of
 //     the bound (4e-7*g instead of 3e-7*g; 5e-7 on the cosines as before).
-constexpr int SG_DW = CG_T + 4;   // data tile, origin (x0-2, y0-2)
-constexpr int SG_GW = CG_T + 2;   // gradient tile, origin (x0-1, y0-1)
+constexpr int SG_DW = CG_T + 4;   // data tile columns, origin (x0-2, y0-2)
+constexpr int SG_DH = CG_T + 5;   // data tile rows (one more than needed: the 7 gradient strips are all 5 rows tall)
+constexpr int SG_GW = CG_T + 2;   // gradient tile columns, origin (x0-1, y0-1)
+constexpr int SG_GH = CG_T + 3;   // gradient tile rows (34 used + 1 never read)
 constexpr int SG_K = 5;           // rows per gradient strip: 7 strips x 34 columns = 238 work items
 __device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
@@ -630,11 +632,11 @@ template <bool ACC>
 __global__ void __launch_bounds__(CG_NT)
 canny_grad_nms_spec2_kernel(const float *__restrict__ data, unsigned char *__restrict__ cls, int nx, int ny,
                             int low_thr, int high_thr, unsigned long long *__restrict__ fallback_count) {
-  __shared__ float sd[SG_DW * SG_DW];
-  __shared__ float fg[SG_GW * SG_GW];
-  __shared__ float2 fhv[SG_GW * SG_GW];
+  __shared__ __align__(16) float sd[SG_DH * SG_DW];
+  __shared__ float fg[SG_GH * SG_GW];
+  __shared__ float2 fhv[SG_GH * SG_GW];
   __shared__ float s_emax[CG_NT / 32];
-  __shared__ unsigned char scls[CG_T * CG_T];
+  __shared__ __align__(4) unsigned char scls[CG_T * CG_T];
   __shared__ unsigned short squeue[CG_T * CG_T];
   __shared__ double sg2[28 * 9];
   __shared__ int qn;
@@ -642,12 +644,27 @@ canny_grad_nms_spec2_kernel(const float *__restrict__ data, unsigned char *__res
   const float *src = data + (size_t)blockIdx.z * nx * ny;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) qn = 0;
-  {   // data tile, clamped coordinates; all loads of a thread are issued before its stores
+  if (x0 >= 2 && y0 >= 2 && x0 + SG_DW - 2 <= nx && y0 + SG_DH - 2 <= ny && (nx & 1) == 0) {
+    // data tile inside the image: 18 float2 per row, three per thread, all loads before the stores
+    const float *org = src + (size_t)(y0 - 2) * nx + (x0 - 2);
+    float2 v[3];
+    int so[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const int u = threadIdx.x + k * CG_NT;
+      const int row = u / (SG_DW / 2), cu = u - row * (SG_DW / 2);
+      so[k] = row * SG_DW + 2 * cu;
+      v[k] = u < SG_DH * (SG_DW / 2) ? __ldg(reinterpret_cast<const float2 *>(org + (size_t)row * nx + 2 * cu)) : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+      if (threadIdx.x + k * CG_NT < SG_DH * (SG_DW / 2)) *reinterpret_cast<float2 *>(sd + so[k]) = v[k];
+  } else {   // clamped coordinates
     const int c0 = min(max(x0 - 2 + lane, 0), nx - 1), c1 = min(max(x0 - 2 + lane + 32, 0), nx - 1);
     float a[5], b[5];
 #pragma unroll
     for (int k = 0; k < 5; k++) {
-      const int j = min(warp + 8 * k, SG_DW - 1);
+      const int j = min(warp + 8 * k, SG_DH - 1);
       const float *row = src + (size_t)min(max(y0 - 2 + j, 0), ny - 1) * nx;
       a[k] = __ldg(row + c0);
       b[k] = lane < SG_DW - 32 ? __ldg(row + c1) : 0.f;
@@ -655,7 +672,7 @@ canny_grad_nms_spec2_kernel(const float *__restrict__ data, unsigned char *__res
 #pragma unroll
     for (int k = 0; k < 5; k++) {
       const int j = warp + 8 * k;
-      if (j < SG_DW) { sd[j * SG_DW + lane] = a[k]; if (lane < SG_DW - 32) sd[j * SG_DW + lane + 32] = b[k]; }
+      if (j < SG_DH) { sd[j * SG_DW + lane] = a[k]; if (lane < SG_DW - 32) sd[j * SG_DW + lane + 32] = b[k]; }
     }
   }
   __syncthreads();
@@ -665,38 +682,32 @@ canny_grad_nms_spec2_kernel(const float *__restrict__ data, unsigned char *__res
   float emax = 0.f;
   if (threadIdx.x < 7 * SG_GW) {
     const int strip = threadIdx.x / SG_GW, c = threadIdx.x - strip * SG_GW;
-    const int r0 = strip * SG_K, r1 = min(r0 + SG_K, SG_GW);
-    const float *d = sd + r0 * SG_DW + c;          // data (row r0, col c) = gradient pixel (r0, c) shifted by (-1, -1)
+    const float *d = sd + strip * SG_K * SG_DW + c;   // data (row, col) = gradient pixel (row, col) shifted by (-1, -1)
     float l0 = d[0], m0 = d[1], q0 = d[2];
-    float l1 = d[SG_DW], q1 = d[SG_DW + 2];
+    float l1 = d[SG_DW], m1 = d[SG_DW + 1], q1 = d[SG_DW + 2];
     float dh0 = q0 - l0, dh1 = q1 - l1;
-    d += 2 * SG_DW;
+    int gi = strip * SG_K * SG_GW + c;
 #pragma unroll
     for (int k = 0; k < SG_K; k++) {
-      if (r0 + k < r1) {
-        const float l2 = d[0], m2 = d[1], q2 = d[2];
-        const float dh2 = q2 - l2;
-        float h, v, S;
-        const float vy = m2 - m0;
-        if (ACC) {
-          const float vp = q2 - q0, vm = l2 - l0;
-          h = fmaf(2.f, dh1, dh2 + dh0);
-          v = fmaf(2.f, vy, vp + vm);
-          S = fmaf(2.f, fabsf(dh1) + fabsf(vy), (fabsf(dh2) + fabsf(dh0)) + (fabsf(vp) + fabsf(vm)));
-        } else {
-          h = dh1; v = vy;
-          S = fabsf(h) + fabsf(v);
-        }
-        const float g = sqrt_approx(fmaf(h, h, v * v));
-        const int gi = (r0 + k) * SG_GW + c;
-        fg[gi] = g;
-        fhv[gi] = make_float2(h, v);
-        emax = fmaxf(emax, fmaf(6e-7f, S, 4e-7f * g));
-        l0 = l1; q0 = q1; dh0 = dh1;
-        m0 = d[1 - SG_DW];                          // centre of the row that becomes "previous"
-        l1 = l2; q1 = q2; dh1 = dh2;
-        d += SG_DW;
+      const float l2 = d[(k + 2) * SG_DW], m2 = d[(k + 2) * SG_DW + 1], q2 = d[(k + 2) * SG_DW + 2];
+      const float dh2 = q2 - l2;
+      float h, v, S;
+      const float vy = m2 - m0;
+      if (ACC) {
+        const float vp = q2 - q0, vm = l2 - l0;
+        h = fmaf(2.f, dh1, dh2 + dh0);
+        v = fmaf(2.f, vy, vp + vm);
+        S = fmaf(2.f, fabsf(dh1) + fabsf(vy), (fabsf(dh2) + fabsf(dh0)) + (fabsf(vp) + fabsf(vm)));
+      } else {
+        h = dh1; v = vy;
+        S = fabsf(h) + fabsf(v);
       }
+      const float g = sqrt_approx(fmaf(h, h, v * v));
+      fg[gi + k * SG_GW] = g;
+      fhv[gi + k * SG_GW] = make_float2(h, v);
+      if (strip * SG_K + k < SG_GW) emax = fmaxf(emax, fmaf(6e-7f, S, 4e-7f * g));   // (row 34 is never read)
+      l0 = l1; m0 = m1; q0 = q1; dh0 = dh1;
+      l1 = l2; m1 = m2; q1 = q2; dh1 = dh2;
     }
   }
   for (int o = 16; o; o >>= 1) emax = fmaxf(emax, __shfl_xor_sync(0xffffffffu, emax, o));
@@ -715,49 +726,44 @@ canny_grad_nms_spec2_kernel(const float *__restrict__ data, unsigned char *__res
     const int ly = t >> 5, lx = t & 31;
     const int gx = x0 + lx, gy = y0 + ly;
     unsigned char c = 0;
-    if (gx < nx && gy < ny) {
-      const int ci = (ly + 1) * SG_GW + lx + 1;
-      const float now = fg[ci];
-      bool undecided = false;
-      if (now < lowf - T0) c = 0;                                // certainly now <= low
-      else if (now <= lowf + T0) undecided = true;
-      else {
-        const float inv = rcp_approx(now);
-        const float2 hv = fhv[ci];
-        const float cs = hv.x * inv, sn = hv.y * inv;
-        const float dcs = 8.f * fmaf(E, inv, 5e-7f);             // bound on |d cos|, |d sin| (x4 margin)
-        // "+" neighbour at (cs, sn): cell corner and weights; the "-" neighbour mirrors the cell and swaps the weights
-        const int ngx = cs < 0.f, ngy = sn < 0.f;
-        const float wbx = cs + (float)ngx, wax = 1.f - wbx, wby = sn + (float)ngy, way = 1.f - wby;
-        float p11, p12, p21, p22, m11, m12, m21, m22;
-        if (interior) {
-          const float *gp = fg + (ly + 1 - ngy) * SG_GW + (lx + 1 - ngx);
-          const float *gm = fg + (ly + ngy) * SG_GW + (lx + ngx);
-          p11 = gp[0]; p12 = gp[1]; p21 = gp[SG_GW]; p22 = gp[SG_GW + 1];
-          m11 = gm[0]; m12 = gm[1]; m21 = gm[SG_GW]; m22 = gm[SG_GW + 1];
-        } else {     // value(): neighbour coordinates clamp to the image
-          const int ox = x0 - 1, oy = y0 - 1;
-          const int px1 = min(max(gx - ngx, 0), nx - 1) - ox, px2 = min(max(gx - ngx + 1, 0), nx - 1) - ox;
-          const int py1 = min(max(gy - ngy, 0), ny - 1) - oy, py2 = min(max(gy - ngy + 1, 0), ny - 1) - oy;
-          const int mx1 = min(max(gx + ngx - 1, 0), nx - 1) - ox, mx2 = min(max(gx + ngx, 0), nx - 1) - ox;
-          const int my1 = min(max(gy + ngy - 1, 0), ny - 1) - oy, my2 = min(max(gy + ngy, 0), ny - 1) - oy;
-          p11 = fg[py1 * SG_GW + px1]; p12 = fg[py1 * SG_GW + px2]; p21 = fg[py2 * SG_GW + px1]; p22 = fg[py2 * SG_GW + px2];
-          m11 = fg[my1 * SG_GW + mx1]; m12 = fg[my1 * SG_GW + mx2]; m21 = fg[my2 * SG_GW + mx1]; m22 = fg[my2 * SG_GW + mx2];
-        }
-        const float nbp = way * fmaf(wax, p11, wbx * p12) + wby * fmaf(wax, p21, wbx * p22);
-        const float nbm = wby * fmaf(wbx, m11, wax * m12) + way * fmaf(wbx, m21, wax * m22);
-        const float spp = fmaxf(fmaxf(p11, p12), fmaxf(p21, p22)) - fminf(fminf(p11, p12), fminf(p21, p22));
-        const float spm = fmaxf(fmaxf(m11, m12), fmaxf(m21, m22)) - fminf(fminf(m11, m12), fminf(m21, m22));
-        const float tolp = fmaf(dcs, spp, 2.f * T0), tolm = fmaf(dcs, spm, 2.f * T0);
-        // the direction is ambiguous for the reference's floor() when a cosine is within its error of 0
-        if (fabsf(cs) <= dcs || fabsf(sn) <= dcs) undecided = true;
-        else if (now < nbp - tolp || now < nbm - tolm) c = 0;       // certainly suppressed
-        else if (now > nbp + tolp && now > nbm + tolm) {            // certainly a maximum
-          if (now >= highf + T0) c = 2;
-          else if (now < highf - T0) c = 1;
-          else undecided = true;
-        } else undecided = true;
+    const int ci = (ly + 1) * SG_GW + lx + 1;
+    const float now = fg[ci];
+    if (gx < nx && gy < ny && now >= lowf - T0) {                // below: certainly now <= low, class 0
+      const float inv = rcp_approx(now);
+      const float2 hv = fhv[ci];
+      const float cs = hv.x * inv, sn = hv.y * inv;
+      const float dcs = 8.f * fmaf(E, inv, 5e-7f);               // bound on |d cos|, |d sin| (x4 margin)
+      // "+" neighbour at (cs, sn): cell corner and weights; the "-" neighbour mirrors the cell and swaps the weights
+      const int ngx = cs < 0.f, ngy = sn < 0.f;
+      const float wbx = cs + (float)ngx, wax = 1.f - wbx, wby = sn + (float)ngy, way = 1.f - wby;
+      float p11, p12, p21, p22, m11, m12, m21, m22;
+      if (interior) {
+        const float *gp = fg + ci - ngy * SG_GW - ngx;
+        const float *gm = fg + ci + (ngy - 1) * SG_GW + (ngx - 1);
+        p11 = gp[0]; p12 = gp[1]; p21 = gp[SG_GW]; p22 = gp[SG_GW + 1];
+        m11 = gm[0]; m12 = gm[1]; m21 = gm[SG_GW]; m22 = gm[SG_GW + 1];
+      } else {     // value(): neighbour coordinates clamp to the image
+        const int ox = x0 - 1, oy = y0 - 1;
+        const int px1 = min(max(gx - ngx, 0), nx - 1) - ox, px2 = min(max(gx - ngx + 1, 0), nx - 1) - ox;
+        const int py1 = min(max(gy - ngy, 0), ny - 1) - oy, py2 = min(max(gy - ngy + 1, 0), ny - 1) - oy;
+        const int mx1 = min(max(gx + ngx - 1, 0), nx - 1) - ox, mx2 = min(max(gx + ngx, 0), nx - 1) - ox;
+        const int my1 = min(max(gy + ngy - 1, 0), ny - 1) - oy, my2 = min(max(gy + ngy, 0), ny - 1) - oy;
+        p11 = fg[py1 * SG_GW + px1]; p12 = fg[py1 * SG_GW + px2]; p21 = fg[py2 * SG_GW + px1]; p22 = fg[py2 * SG_GW + px2];
+        m11 = fg[my1 * SG_GW + mx1]; m12 = fg[my1 * SG_GW + mx2]; m21 = fg[my2 * SG_GW + mx1]; m22 = fg[my2 * SG_GW + mx2];
       }
+      const float nbp = way * fmaf(wax, p11, wbx * p12) + wby * fmaf(wax, p21, wbx * p22);
+      const float nbm = wby * fmaf(wbx, m11, wax * m12) + way * fmaf(wbx, m21, wax * m22);
+      const float spp = fmaxf(fmaxf(p11, p12), fmaxf(p21, p22)) - fminf(fminf(p11, p12), fminf(p21, p22));
+      const float spm = fmaxf(fmaxf(m11, m12), fmaxf(m21, m22)) - fminf(fminf(m11, m12), fminf(m21, m22));
+      const float tolp = fmaf(dcs, spp, 2.f * T0), tolm = fmaf(dcs, spm, 2.f * T0);
+      // undecided: now within the bound of `low`; a cosine within its error of 0 (the reference's floor() is
+      // ambiguous there); a comparison with a neighbour or with `high` inside the bound
+      const bool amb = now <= lowf + T0 || fminf(fabsf(cs), fabsf(sn)) <= dcs;
+      const bool sup = now < fmaxf(nbp - tolp, nbm - tolm);      // certainly suppressed
+      const bool top = now > fmaxf(nbp + tolp, nbm + tolm);      // certainly a maximum
+      const bool hi2 = now >= highf + T0, hi1 = now < highf - T0;
+      const bool undecided = amb || (!sup && (!top || (!hi2 && !hi1)));
+      c = (!undecided && !sup) ? (hi2 ? 2 : 1) : 0;
       if (undecided) squeue[atomicAdd(&qn, 1)] = (unsigned short)t;
     }
     scls[t] = c;
