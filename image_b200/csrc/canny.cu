@@ -98,7 +98,7 @@ canny_blur_kernel(const unsigned char *__restrict__ frames, float *__restrict__ 
       for (int j = 0; j < 4; j++) {
         double acc = __dmul_rn(tx.w[0], v[j + RR]);
 #pragma unroll
-        for (int k = 1; k <= RR; k++) acc = __dadd_rn(acc, __dmul_rn(tx.w[k], __dadd_rn(v[j + RR - k], v[j + RR + k])));
+        for (int k = 1; k <= RR; k++) acc = __fma_rn(tx.w[k], __dadd_rn(v[j + RR - k], v[j + RR + k]), acc);
         o[j] = acc;
       }
       double *d = rowbuf + r * CB_TW + 4 * g;
@@ -109,7 +109,7 @@ canny_blur_kernel(const unsigned char *__restrict__ frames, float *__restrict__ 
     for (int r = warp; r < TILE_H; r += CB_NT / 32) {
       const double *p = tile + r * TP + lane + RX;
       double acc = __dmul_rn(tx.w[0], p[0]);
-      for (int k = 1; k <= RX; k++) acc = __dadd_rn(acc, __dmul_rn(tx.w[k], __dadd_rn(p[-k], p[k])));
+      for (int k = 1; k <= RX; k++) acc = __fma_rn(tx.w[k], __dadd_rn(p[-k], p[k]), acc);
       rowbuf[r * CB_TW + lane] = acc;
     }
   }
@@ -130,7 +130,7 @@ canny_blur_kernel(const unsigned char *__restrict__ frames, float *__restrict__ 
         for (int j = 0; j < RB; j++) {
           double acc = __dmul_rn(ty.w[0], v[j + RR]);
 #pragma unroll
-          for (int k = 1; k <= RR; k++) acc = __dadd_rn(acc, __dmul_rn(ty.w[k], __dadd_rn(v[j + RR - k], v[j + RR + k])));
+          for (int k = 1; k <= RR; k++) acc = __fma_rn(ty.w[k], __dadd_rn(v[j + RR - k], v[j + RR + k]), acc);
           int gy = y0 + rg * RB + j;
           if (gx < nx && gy < ny) dst[(size_t)gy * nx + gx] = __double2float_rn(acc);
         }
@@ -139,7 +139,7 @@ canny_blur_kernel(const unsigned char *__restrict__ frames, float *__restrict__ 
       for (int r = warp; r < CB_TH; r += CB_NT / 32) {
         const double *p = rowbuf + (r + RY) * CB_TW + c;
         double acc = __dmul_rn(ty.w[0], p[0]);
-        for (int k = 1; k <= RY; k++) acc = __dadd_rn(acc, __dmul_rn(ty.w[k], __dadd_rn(p[-k * CB_TW], p[k * CB_TW])));
+        for (int k = 1; k <= RY; k++) acc = __fma_rn(ty.w[k], __dadd_rn(p[-k * CB_TW], p[k * CB_TW]), acc);
         int gy = y0 + r;
         if (gx < nx && gy < ny) dst[(size_t)gy * nx + gx] = __double2float_rn(acc);
       }
@@ -186,7 +186,7 @@ canny_blur_rows_kernel(const unsigned char *__restrict__ frames, double *__restr
     const int c = LEAD + j;
     double acc = __dmul_rn(tx.w[0], u32_to_double(b[c]));
 #pragma unroll
-    for (int k = 1; k <= RR; k++) acc = __dadd_rn(acc, __dmul_rn(tx.w[k], u32_to_double((unsigned)b[c - k] + (unsigned)b[c + k])));
+    for (int k = 1; k <= RR; k++) acc = __fma_rn(tx.w[k], u32_to_double((unsigned)b[c - k] + (unsigned)b[c + k]), acc);
     o[j] = acc;
   }
   double *d = rowsum + ((size_t)blockIdx.z * ny + y) * nx + x4;
@@ -235,7 +235,7 @@ canny_blur_cols_kernel(const double *__restrict__ rowsum, float *__restrict__ ou
     for (int j = 0; j < RB; j++) {
       double acc = __dmul_rn(ty.w[0], v[j + RR]);
 #pragma unroll
-      for (int k = 1; k <= RR; k++) acc = __dadd_rn(acc, __dmul_rn(ty.w[k], __dadd_rn(v[j + RR - k], v[j + RR + k])));
+      for (int k = 1; k <= RR; k++) acc = __fma_rn(ty.w[k], __dadd_rn(v[j + RR - k], v[j + RR + k]), acc);
       const int gy = y0 + rg * RB + j;
       if (gx < nx && gy < ny) dst[(size_t)gy * nx + gx] = __double2float_rn(acc);
     }
@@ -256,10 +256,10 @@ __global__ void canny_blur_generic_rows(const unsigned char *__restrict__ frames
     const int R = t.n / 2;
     acc = __dmul_rn(t.weight[R], (double)src[x]);
     for (int k = 1; k <= R; k++)
-      acc = __dadd_rn(acc, __dmul_rn(t.weight[R + k], __dadd_rn((double)src[wrap_index(x - k, nx)], (double)src[wrap_index(x + k, nx)])));
+      acc = __fma_rn(t.weight[R + k], __dadd_rn((double)src[wrap_index(x - k, nx)], (double)src[wrap_index(x + k, nx)]), acc);
   } else {
     acc = 0;
-    for (int i = 0; i < t.n; i++) acc = __dadd_rn(acc, __dmul_rn(t.weight[i], (double)src[wrap_index(x - t.coord[i], nx)]));
+    for (int i = 0; i < t.n; i++) acc = __fma_rn(t.weight[i], (double)src[wrap_index(x - t.coord[i], nx)], acc);
   }
   tmp[(size_t)blockIdx.z * nx * ny + (size_t)y * nx + x] = acc;
 }
@@ -272,10 +272,10 @@ __global__ void canny_blur_generic_cols(const double *__restrict__ tmp, float *_
     const int R = t.n / 2;
     acc = __dmul_rn(t.weight[R], src[(size_t)y * nx]);
     for (int k = 1; k <= R; k++)
-      acc = __dadd_rn(acc, __dmul_rn(t.weight[R + k], __dadd_rn(src[(size_t)wrap_index(y - k, ny) * nx], src[(size_t)wrap_index(y + k, ny) * nx])));
+      acc = __fma_rn(t.weight[R + k], __dadd_rn(src[(size_t)wrap_index(y - k, ny) * nx], src[(size_t)wrap_index(y + k, ny) * nx]), acc);
   } else {
     acc = 0;
-    for (int i = 0; i < t.n; i++) acc = __dadd_rn(acc, __dmul_rn(t.weight[i], src[(size_t)wrap_index(y - t.coord[i], ny) * nx]));
+    for (int i = 0; i < t.n; i++) acc = __fma_rn(t.weight[i], src[(size_t)wrap_index(y - t.coord[i], ny) * nx], acc);
   }
   out[(size_t)blockIdx.z * nx * ny + (size_t)y * nx + x] = __double2float_rn(acc);
 }

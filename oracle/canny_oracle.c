@@ -58,9 +58,12 @@ static int taps_symmetric(const int *c, const double *w, int n) {
  * float (tools.c:129 `crealf`).  Summation order (part of this restatement's definition, chosen
  * once and shared with the CUDA kernel so that the two agree bit for bit):
  *   symmetric tap list (every image at least 2R+2 wide/high):  acc = w0*v0, then for k = 1..R
- *       acc += wk * (v[-k] + v[+k])        (for u8 rows the pair sum is an exact integer)
+ *       acc = fma(wk, v[-k] + v[+k], acc)  (for u8 rows the pair sum is an exact integer)
  *   otherwise (tiny images, where the wrap-around coordinates of tools.c:152-153 make the
- *   kernel asymmetric): acc = 0, then acc += w_t * v[x - c_t] for t ascending. */
+ *   kernel asymmetric): acc = 0, then acc = fma(w_t, v[x - c_t], acc) for t ascending.
+ * fma() is C99's correctly rounded fused multiply-add (one rounding per tap): the reference's own sum
+ * is an FFT (no tap order at all), so either choice restates it equally well; the fused form is the
+ * more accurate one and maps to one DFMA per tap on the GPU. */
 static double conv_at(const int *c, const double *w, int n, int sym, int pos, int len, const void *base,
                       long stride, int is_u8) {
 #define AT(q) (is_u8 ? (double)((const uint8_t *)base)[(long)(q) * stride] : ((const double *)base)[(long)(q) * stride])
@@ -71,14 +74,14 @@ static double conv_at(const int *c, const double *w, int n, int sym, int pos, in
       int a = pos - k, b = pos + k;
       a %= len; if (a < 0) a += len;
       b %= len; if (b < 0) b += len;
-      acc += w[R + k] * (AT(a) + AT(b));
+      acc = fma(w[R + k], AT(a) + AT(b), acc);
     }
     return acc;
   }
   double acc = 0;
   for (int t = 0; t < n; t++) {
     int q = pos - c[t]; q %= len; if (q < 0) q += len;
-    acc += w[t] * AT(q);
+    acc = fma(w[t], AT(q), acc);
   }
   return acc;
 #undef AT
