@@ -168,12 +168,18 @@ canny_blur_rows_kernel(const unsigned char *__restrict__ frames, double *__restr
   constexpr int LEAD = (RR + 3) & ~3;                            // 16: first loaded byte is x4 - LEAD
   constexpr int NW = (LEAD + 4 + RR + 3) / 4;                    // 9 words cover x4-16 .. x4+19
   unsigned char b[NW * 4];
-  const bool fast = (nx & 3) == 0 && x4 - LEAD >= 0 && x4 - LEAD + NW * 4 <= nx && (reinterpret_cast<uintptr_t>(frames) & 3) == 0;
-  if (fast) {
-    const unsigned *w = reinterpret_cast<const unsigned *>(row + x4 - LEAD);
+  const bool fast = (nx & 3) == 0 && NW * 4 <= nx && (reinterpret_cast<uintptr_t>(frames) & 3) == 0;
+  if (fast) {     // nx % 4 == 0: the circular wrap keeps word alignment, so row ends need no byte path
+    const unsigned *w = reinterpret_cast<const unsigned *>(row);
+    const int nw = nx >> 2, w0 = (x4 - LEAD) >> 2;              // (arithmetic shift: x4 - LEAD may be negative)
     unsigned v[NW];
 #pragma unroll
-    for (int q = 0; q < NW; q++) v[q] = __ldg(w + q);
+    for (int q = 0; q < NW; q++) {
+      int wi = w0 + q;
+      wi += wi < 0 ? nw : 0;
+      wi -= wi >= nw ? nw : 0;
+      v[q] = __ldg(w + wi);
+    }
 #pragma unroll
     for (int q = 0; q < NW; q++) { b[4 * q] = v[q] & 0xff; b[4 * q + 1] = (v[q] >> 8) & 0xff; b[4 * q + 2] = (v[q] >> 16) & 0xff; b[4 * q + 3] = v[q] >> 24; }
   } else {
