@@ -188,116 +188,72 @@ harris_fused2_kernel(const void *__restrict__ frames, float *__restrict__ Rout, 
   __syncthreads();
 
   // ---- stage D: gradient + products + row blur sigma_i, streamed -> sAR (plain) ---------------
-  // One item = 4 AR rows x 4 output columns.  AR rows (4k .. 4k+3) <-> Is rows (4k+1 .. 4k+4); with Is
-  // rows paired (even, odd) the three pair lines P0=(4k,4k+1), P1=(4k+2,4k+3), P2=(4k+4,4k+5) hold
-  // everything: for the row pair (4k+1, 4k+2)   gy = (Is[4k+2]-Is[4k], Is[4k+3]-Is[4k+1]) = P1 - P0 (packed),
-  //                                              gx from P0.y and P1.x;
-  //             for the row pair (4k+3, 4k+4)   gy = P2 - P1,  gx from P1.y and P2.x.
+  // One item = one AR row pair x 4 output columns.  AR rows (2r, 2r+1) <-> Is rows (2r+1, 2r+2); with Is
+  // rows paired (even, odd), the two pair lines L0 = (2r, 2r+1) and L1 = (2r+2, 2r+3) hold everything:
+  //     gy = (Is[2r+2] - Is[2r], Is[2r+3] - Is[2r+1]) = L1 - L0 (packed),   gx from L0.y and L1.x.
+  // Consecutive threads take consecutive row pairs (line stride = 4 banks: a quarter warp of 16-byte loads
+  // covers all 32 banks); 39 row pairs are padded to 40 so that quarter warps never straddle two column groups.
   {
     constexpr int GROUPS = C::TW / 4;                          // 16
     constexpr int NPOS = 4 + 2 * RI;                           // 18 product positions per item
-    constexpr int NL = (NPOS + 2 + 1) / 2 * 2;                 // 20 Is columns loaded per line
-    constexpr int QS = (C::AR_H + 3) / 4;                      // 20 row quads (the last one is half empty)
+    constexpr int RPS = C::AR_H / 2, RPS_PAD = (RPS + 7) & ~7; // 39 -> 40
     constexpr int PL = C::AR_H * C::AR_P;                      // plane stride (multiple of 4 floats)
     static_assert(PL % 4 == 0, "plane stride keeps 16-byte alignment");
+    static_assert(C::AR_H % 2 == 0 && RPS + 1 <= C::IS_H / 2, "row pairs and their two pair lines");
     float2 w2[RI + 1];
 #pragma unroll
     for (int t = 0; t <= RI; t++) w2[t] = f2s(kc.wir[t]);
-    for (int it = tid; it < QS * GROUPS; it += C::NT) {
-      const int g = it / QS, k = it - g * QS;                  // consecutive threads = consecutive row quads
-      const float2 *l0 = sISp + (2 * k) * C::IS_P + 4 * g;     // pair line 2k   = Is rows 4k, 4k+1
-      const float2 *l1 = l0 + C::IS_P;                         // pair line 2k+1 = Is rows 4k+2, 4k+3
-      const float2 *l2 = sISp + min(2 * k + 2, C::IS_H / 2 - 1) * C::IS_P + 4 * g;   // rows 4k+4, 4k+5 (clamped for the half-empty last quad)
-      float2 a0[4], b0[4], c0[4], a1[4], b1[4], c1[4];
+    for (int it = tid; it < RPS_PAD * GROUPS; it += C::NT) {
+      const int g = it / RPS_PAD, r = it - g * RPS_PAD;
+      if (r >= RPS) continue;
+      const float2 *l0 = sISp + r * C::IS_P + 4 * g;           // pair line r   = Is rows 2r,   2r+1
+      const float2 *l1 = l0 + C::IS_P;                         // pair line r+1 = Is rows 2r+2, 2r+3
+      float2 a0[4], b0[4], c0[4];
 #pragma unroll
-      for (int j = 0; j < 4; j++) { a0[j] = b0[j] = c0[j] = a1[j] = b1[j] = c1[j] = f2s(0.f); }
-      float2 p0[3], p1[3], p2[3];                              // sliding window of Is columns q, q+1, q+2
+      for (int j = 0; j < 4; j++) { a0[j] = b0[j] = c0[j] = f2s(0.f); }
+      float2 p0[3], p1[3];                                     // sliding window of Is columns q, q+1, q+2
       {
-        float4 t0 = *reinterpret_cast<const float4 *>(l0), t1 = *reinterpret_cast<const float4 *>(l1), t2 = *reinterpret_cast<const float4 *>(l2);
-        p0[0] = f2(t0.x, t0.y); p0[1] = f2(t0.z, t0.w); p1[0] = f2(t1.x, t1.y); p1[1] = f2(t1.z, t1.w); p2[0] = f2(t2.x, t2.y); p2[1] = f2(t2.z, t2.w);
+        const float4 t0 = *reinterpret_cast<const float4 *>(l0), t1 = *reinterpret_cast<const float4 *>(l1);
+        p0[0] = f2(t0.x, t0.y); p0[1] = f2(t0.z, t0.w); p1[0] = f2(t1.x, t1.y); p1[1] = f2(t1.z, t1.w);
       }
 #pragma unroll
       for (int q = 0; q < NPOS; q++) {
-        // bring in column q+2 (pairs of columns are fetched as one 16-byte load on even q)
-        if ((q & 1) == 0) {
-          float4 t0 = *reinterpret_cast<const float4 *>(l0 + q + 2), t1 = *reinterpret_cast<const float4 *>(l1 + q + 2), t2 = *reinterpret_cast<const float4 *>(l2 + q + 2);
-          p0[2] = f2(t0.x, t0.y); p1[2] = f2(t1.x, t1.y); p2[2] = f2(t2.x, t2.y);
-          // stash column q+3 in slot 0 AFTER it has been consumed below: keep it in temporaries
-          float2 n0 = f2(t0.z, t0.w), n1 = f2(t1.z, t1.w), n2 = f2(t2.z, t2.w);
-          // ---- products at column q+1 for both row pairs
-          float2 gxA, gyA, gxB, gyB;
-          if (GRAD == 0) {
-            gyA = sub2(p1[1], p0[1]);                                            // rows 4k+1, 4k+2
-            gxA = f2(p0[2].y - p0[0].y, p1[2].x - p1[0].x);
-            gyB = sub2(p2[1], p1[1]);                                            // rows 4k+3, 4k+4
-            gxB = f2(p1[2].y - p1[0].y, p2[2].x - p2[0].x);
-          } else {
-            gxA = f2(fmaf(0.25f, p0[2].y - p0[0].y, 0.125f * (p0[2].x + p1[2].x - p0[0].x - p1[0].x)),
-                     fmaf(0.25f, p1[2].x - p1[0].x, 0.125f * (p0[2].y + p1[2].y - p0[0].y - p1[0].y)));
-            gyA = f2(fmaf(0.25f, p1[1].x - p0[1].x, 0.125f * (p1[2].x + p1[0].x - p0[2].x - p0[0].x)),
-                     fmaf(0.25f, p1[1].y - p0[1].y, 0.125f * (p1[2].y + p1[0].y - p0[2].y - p0[0].y)));
-            gxB = f2(fmaf(0.25f, p1[2].y - p1[0].y, 0.125f * (p1[2].x + p2[2].x - p1[0].x - p2[0].x)),
-                     fmaf(0.25f, p2[2].x - p2[0].x, 0.125f * (p1[2].y + p2[2].y - p1[0].y - p2[0].y)));
-            gyB = f2(fmaf(0.25f, p2[1].x - p1[1].x, 0.125f * (p2[2].x + p2[0].x - p1[2].x - p1[0].x)),
-                     fmaf(0.25f, p2[1].y - p1[1].y, 0.125f * (p2[2].y + p2[0].y - p1[2].y - p1[0].y)));
-          }
-          {
-            const float2 pa = __fmul2_rn(gxA, gxA), pb = __fmul2_rn(gxA, gyA), pc = __fmul2_rn(gyA, gyA);
-            const float2 qa = __fmul2_rn(gxB, gxB), qb = __fmul2_rn(gxB, gyB), qc = __fmul2_rn(gyB, gyB);
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-              const int t = q - j - RI;
-              if (t >= -RI && t <= RI) {
-                const float2 w = w2[t < 0 ? -t : t];
-                a0[j] = __ffma2_rn(w, pa, a0[j]); b0[j] = __ffma2_rn(w, pb, b0[j]); c0[j] = __ffma2_rn(w, pc, c0[j]);
-                a1[j] = __ffma2_rn(w, qa, a1[j]); b1[j] = __ffma2_rn(w, qb, b1[j]); c1[j] = __ffma2_rn(w, qc, c1[j]);
-              }
-            }
-          }
-          // slide: (q, q+1, q+2) -> (q+1, q+2, q+3)
-          p0[0] = p0[1]; p0[1] = p0[2]; p0[2] = n0; p1[0] = p1[1]; p1[1] = p1[2]; p1[2] = n1; p2[0] = p2[1]; p2[1] = p2[2]; p2[2] = n2;
-        } else {
-          float2 gxA, gyA, gxB, gyB;
-          if (GRAD == 0) {
-            gyA = sub2(p1[1], p0[1]);
-            gxA = f2(p0[2].y - p0[0].y, p1[2].x - p1[0].x);
-            gyB = sub2(p2[1], p1[1]);
-            gxB = f2(p1[2].y - p1[0].y, p2[2].x - p2[0].x);
-          } else {
-            gxA = f2(fmaf(0.25f, p0[2].y - p0[0].y, 0.125f * (p0[2].x + p1[2].x - p0[0].x - p1[0].x)),
-                     fmaf(0.25f, p1[2].x - p1[0].x, 0.125f * (p0[2].y + p1[2].y - p0[0].y - p1[0].y)));
-            gyA = f2(fmaf(0.25f, p1[1].x - p0[1].x, 0.125f * (p1[2].x + p1[0].x - p0[2].x - p0[0].x)),
-                     fmaf(0.25f, p1[1].y - p0[1].y, 0.125f * (p1[2].y + p1[0].y - p0[2].y - p0[0].y)));
-            gxB = f2(fmaf(0.25f, p1[2].y - p1[0].y, 0.125f * (p1[2].x + p2[2].x - p1[0].x - p2[0].x)),
-                     fmaf(0.25f, p2[2].x - p2[0].x, 0.125f * (p1[2].y + p2[2].y - p1[0].y - p2[0].y)));
-            gyB = f2(fmaf(0.25f, p2[1].x - p1[1].x, 0.125f * (p2[2].x + p2[0].x - p1[2].x - p1[0].x)),
-                     fmaf(0.25f, p2[1].y - p1[1].y, 0.125f * (p2[2].y + p2[0].y - p1[2].y - p1[0].y)));
-          }
-          const float2 pa = __fmul2_rn(gxA, gxA), pb = __fmul2_rn(gxA, gyA), pc = __fmul2_rn(gyA, gyA);
-          const float2 qa = __fmul2_rn(gxB, gxB), qb = __fmul2_rn(gxB, gyB), qc = __fmul2_rn(gyB, gyB);
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            const int t = q - j - RI;
-            if (t >= -RI && t <= RI) {
-              const float2 w = w2[t < 0 ? -t : t];
-              a0[j] = __ffma2_rn(w, pa, a0[j]); b0[j] = __ffma2_rn(w, pb, b0[j]); c0[j] = __ffma2_rn(w, pc, c0[j]);
-              a1[j] = __ffma2_rn(w, qa, a1[j]); b1[j] = __ffma2_rn(w, qb, b1[j]); c1[j] = __ffma2_rn(w, qc, c1[j]);
-            }
-          }
-          p0[0] = p0[1]; p0[1] = p0[2]; p1[0] = p1[1]; p1[1] = p1[2]; p2[0] = p2[1]; p2[1] = p2[2];
+        float2 n0 = f2s(0.f), n1 = f2s(0.f);
+        if ((q & 1) == 0) {                                    // columns q+2, q+3 arrive as one 16-byte load per line
+          const float4 t0 = *reinterpret_cast<const float4 *>(l0 + q + 2), t1 = *reinterpret_cast<const float4 *>(l1 + q + 2);
+          p0[2] = f2(t0.x, t0.y); p1[2] = f2(t1.x, t1.y);
+          n0 = f2(t0.z, t0.w); n1 = f2(t1.z, t1.w);
         }
+        // ---- products at column q+1
+        float2 gx, gy;
+        if (GRAD == 0) {
+          gy = sub2(p1[1], p0[1]);
+          gx = f2(p0[2].y - p0[0].y, p1[2].x - p1[0].x);
+        } else {
+          gx = f2(fmaf(0.25f, p0[2].y - p0[0].y, 0.125f * (p0[2].x + p1[2].x - p0[0].x - p1[0].x)),
+                  fmaf(0.25f, p1[2].x - p1[0].x, 0.125f * (p0[2].y + p1[2].y - p0[0].y - p1[0].y)));
+          gy = f2(fmaf(0.25f, p1[1].x - p0[1].x, 0.125f * (p1[2].x + p1[0].x - p0[2].x - p0[0].x)),
+                  fmaf(0.25f, p1[1].y - p0[1].y, 0.125f * (p1[2].y + p1[0].y - p0[2].y - p0[0].y)));
+        }
+        const float2 pa = __fmul2_rn(gx, gx), pb = __fmul2_rn(gx, gy), pc = __fmul2_rn(gy, gy);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int t = q - j - RI;
+          if (t >= -RI && t <= RI) {
+            const float2 w = w2[t < 0 ? -t : t];
+            a0[j] = __ffma2_rn(w, pa, a0[j]); b0[j] = __ffma2_rn(w, pb, b0[j]); c0[j] = __ffma2_rn(w, pc, c0[j]);
+          }
+        }
+        // slide: (q, q+1, q+2) -> (q+1, q+2, q+3)
+        p0[0] = p0[1]; p0[1] = p0[2]; p1[0] = p1[1]; p1[1] = p1[2];
+        if ((q & 1) == 0) { p0[2] = n0; p1[2] = n1; }
       }
-      // AR rows 4k, 4k+1 (pair A) and 4k+2, 4k+3 (pair B); the last quad only has pair A
-      float *o = sAR + (4 * k) * C::AR_P + 4 * g;
+      float *o = sAR + (2 * r) * C::AR_P + 4 * g;
 #define ST_ROWPAIR(dst, v)                                                                   \
       *reinterpret_cast<float4 *>(dst) = make_float4(v[0].x, v[1].x, v[2].x, v[3].x);            \
       *reinterpret_cast<float2 *>((dst) + C::AR_P) = make_float2(v[0].y, v[1].y);                \
       *reinterpret_cast<float2 *>((dst) + C::AR_P + 2) = make_float2(v[2].y, v[3].y);
       ST_ROWPAIR(o, a0) ST_ROWPAIR(o + PL, b0) ST_ROWPAIR(o + 2 * PL, c0)
-      if (4 * k + 2 < C::AR_H) {
-        float *o2 = o + 2 * C::AR_P;
-        ST_ROWPAIR(o2, a1) ST_ROWPAIR(o2 + PL, b1) ST_ROWPAIR(o2 + 2 * PL, c1)
-      }
 #undef ST_ROWPAIR
     }
   }
