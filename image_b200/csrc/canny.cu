@@ -864,6 +864,7 @@ __device__ __forceinline__ void uf_union(int *L, int a, int b) {
 }
 
 constexpr int HT = 32;   // hysteresis tile edge (one warp lane per column)
+constexpr int HYST_MAX_ROOTS = (HT / 2) * (HT / 2);   // isolated pixels on a 2-pixel lattice
 
 __device__ __forceinline__ int run_start(unsigned bits, int x) {
   // first column of the run of set bits that contains bit x (bit x must be set)
@@ -877,8 +878,8 @@ __device__ __forceinline__ int run_start(unsigned bits, int x) {
 //     touches it 8-connectedly -- all 32 rows concurrently;
 //   * heads are flattened, the per-component "holds a class-2 pixel" flag is set per run;
 //   * the output pass (lane = column) writes one root index per edge pixel.
-// Output per edge pixel: L[p] = GLOBAL index of the tile-local root; rinfo[p] (pre-zeroed by a memset) =
-// bit0 "p is a tile root", bit1 "its tile component holds a class-2 pixel".
+// Output: L[p] = GLOBAL index of the tile-local root for every edge pixel; per tile a compact list of its
+// roots (global index, bit 31 = "the tile component holds a class-2 pixel") and their count.
 __device__ __forceinline__ unsigned nonzero_bytes_mask(unsigned m) {   // m has 0xff / 0x00 per byte -> 4 bits
   return ((m >> 7) & 1u) | ((m >> 14) & 2u) | ((m >> 21) & 4u) | ((m >> 28) & 8u);
 }
@@ -889,8 +890,8 @@ __device__ __forceinline__ unsigned run_mask_from(unsigned bits, int s) {   // t
 }
 
 __global__ void __launch_bounds__(256)
-hyst_local_kernel(const unsigned char *__restrict__ cls, int *__restrict__ L, unsigned char *__restrict__ rinfo, int nx, int ny,
-                  int TX, int TY, int n_tiles) {
+hyst_local_kernel(const unsigned char *__restrict__ cls, int *__restrict__ L, unsigned char *__restrict__ strong,
+                  int *__restrict__ rootlist, int *__restrict__ rootcnt, int nx, int ny, int TX, int TY, int n_tiles) {
   __shared__ int lab_all[8][HT * HT];
   __shared__ unsigned char cst_all[8][HT * HT];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -921,7 +922,7 @@ hyst_local_kernel(const unsigned char *__restrict__ cls, int *__restrict__ L, un
       }
     }
   }
-  if (!__any_sync(0xffffffffu, emask != 0)) return;             // empty tile
+  if (!__any_sync(0xffffffffu, emask != 0)) { if (lane == 0) rootcnt[tile] = 0; return; }   // empty tile
   const unsigned up = __shfl_up_sync(0xffffffffu, emask, 1);
   // ---- heads
   for (unsigned rem = emask; rem;) {
@@ -960,18 +961,33 @@ hyst_local_kernel(const unsigned char *__restrict__ cls, int *__restrict__ L, un
     if (smask & rm) cstrong[uf_find(lab, lane * HT + s)] = 1;
   }
   __syncwarp();
-  // ---- output (lane = column)
+  // ---- output (lane = column): root index per edge pixel; the tile's roots are appended to its slot list
+  // (<= 256 per tile: 8-connected components are at least two pixels apart) with the strong flag in bit 31
   const int gx = x0 + lane;
+  int nroots = 0;
+  int *slots = rootlist + (size_t)tile * HYST_MAX_ROOTS;
   for (int r = 0; r < HT; r++) {
     const unsigned bits = __shfl_sync(0xffffffffu, emask, r);
-    if (!((bits >> lane) & 1u)) continue;                       // (no shuffles below: divergence is fine)
-    const int h = r * HT + run_start(bits, lane);
-    const int rt = uf_find(lab, h);
-    const int ry = rt / HT, rx = rt - ry * HT;
-    const size_t p = base + (size_t)(y0 + r) * nx + gx;
-    L[p] = (int)(base + (size_t)(y0 + ry) * nx + (x0 + rx));
-    if (rt == r * HT + lane) rinfo[p] = (unsigned char)(1 | (cstrong[rt] << 1));
+    if (bits == 0) continue;                                    // (warp-uniform)
+    const bool set = (bits >> lane) & 1u;
+    int rt = 0;
+    bool isroot = false;
+    size_t p = 0;
+    if (set) {
+      rt = uf_find(lab, r * HT + run_start(bits, lane));
+      const int ry = rt / HT, rx = rt - ry * HT;
+      p = base + (size_t)(y0 + r) * nx + gx;
+      L[p] = (int)(base + (size_t)(y0 + ry) * nx + (x0 + rx));
+      isroot = rt == r * HT + lane;
+    }
+    const unsigned rb = __ballot_sync(0xffffffffu, isroot);
+    if (isroot) {
+      slots[nroots + __popc(rb & ((1u << lane) - 1u))] = (int)p | (cstrong[rt] ? (int)0x80000000 : 0);
+      strong[p] = 0;                                            // every global root is some tile's root: no memset needed
+    }
+    nroots += __popc(rb);
   }
+  if (lane == 0) rootcnt[tile] = nroots;
 }
 
 // Level 2: seams.  A pixel on the right / bottom / left edge of its tile unions with its forward
@@ -997,40 +1013,31 @@ __global__ void hyst_seam_kernel(const unsigned char *__restrict__ cls, int *__r
     if ((bottom || right) && x + 1 < nx && cls[p + nx + 1]) uf_union(L, (int)p, (int)(p + nx + 1));
   }
 }
-// tile roots whose tile component holds a class-2 pixel mark the global root; 16 pixels per thread
-__global__ void hyst_mark(const unsigned char *__restrict__ rinfo, int *__restrict__ L, unsigned char *__restrict__ strong, size_t n) {
-  size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
-  if (i0 >= n) return;
-  if (i0 + 16 <= n) {
-    uint4 v = *reinterpret_cast<const uint4 *>(rinfo + i0);
-    unsigned w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-      if (!w[q]) continue;
-#pragma unroll
-      for (int b = 0; b < 4; b++)
-        if (((w[q] >> (8 * b)) & 0xff) == 3) strong[uf_find(L, (int)(i0 + 4 * q + b))] = 1;
-    }
-  } else {
-    for (size_t i = i0; i < n; i++) if (rinfo[i] == 3) strong[uf_find(L, (int)i)] = 1;
+// Tile roots whose tile component holds a class-2 pixel mark their global root.  One warp per tile walks
+// the tile's root list.
+__global__ void __launch_bounds__(256)
+hyst_mark_list(const int *__restrict__ rootlist, const int *__restrict__ rootcnt, int *__restrict__ L, unsigned char *__restrict__ strong, int n_tiles) {
+  const int tile = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (tile >= n_tiles) return;
+  const int cnt = rootcnt[tile];
+  const int *slots = rootlist + (size_t)tile * HYST_MAX_ROOTS;
+  for (int i = lane; i < cnt; i += 32) {
+    const int e = slots[i];
+    if (e < 0) strong[uf_find(L, e & 0x7fffffff)] = 1;
   }
 }
-// every tile root learns whether its global component is strong (bit2 of rinfo)
-__global__ void hyst_resolve(unsigned char *__restrict__ rinfo, int *__restrict__ L, const unsigned char *__restrict__ strong, size_t n) {
-  size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
-  if (i0 >= n) return;
-  if (i0 + 16 <= n) {
-    uint4 v = *reinterpret_cast<const uint4 *>(rinfo + i0);
-    unsigned w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-      if (!w[q]) continue;
-#pragma unroll
-      for (int b = 0; b < 4; b++)
-        if ((w[q] >> (8 * b)) & 1u) { size_t i = i0 + 4 * q + b; if (strong[uf_find(L, (int)i)]) rinfo[i] |= 4; }
-    }
-  } else {
-    for (size_t i = i0; i < n; i++) if ((rinfo[i] & 1) && strong[uf_find(L, (int)i)]) rinfo[i] |= 4;
+// Every tile root learns whether its global component is strong: rinfo[root] = 4 or 0 (only root positions
+// of rinfo are ever written or read).
+__global__ void __launch_bounds__(256)
+hyst_resolve_list(const int *__restrict__ rootlist, const int *__restrict__ rootcnt, int *__restrict__ L, const unsigned char *__restrict__ strong,
+                  unsigned char *__restrict__ rinfo, int n_tiles) {
+  const int tile = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (tile >= n_tiles) return;
+  const int cnt = rootcnt[tile];
+  const int *slots = rootlist + (size_t)tile * HYST_MAX_ROOTS;
+  for (int i = lane; i < cnt; i += 32) {
+    const int idx = slots[i] & 0x7fffffff;
+    rinfo[idx] = strong[uf_find(L, idx)] ? 4 : 0;
   }
 }
 // L[p] of an edge pixel is a tile-root node of its component (its own tile root, or an ancestor
@@ -1102,7 +1109,7 @@ static bool symmetric_taps(const std::vector<int> &c, const std::vector<double> 
 
 size_t canny_scratch_bytes(int n_frames, int nx, int ny) {
   size_t n = (size_t)n_frames * nx * ny;
-  return align256(n * 4) /*blur*/ + align256(n) /*cls*/ + align256(n * 4) /*labels*/ + align256(n) /*strong*/ + align256(n) /*rinfo*/ + 2 * align256((size_t)(ceil_div(nx, 32) + 1) * (ceil_div(ny, 32) + 1) * n_frames * 128) /*bit planes*/ + 4096 +
+  return align256(n * 4) /*blur*/ + align256(n) /*cls*/ + align256(n * 4) /*labels*/ + align256(n) /*strong*/ + align256(n) /*rinfo*/ + align256((size_t)ceil_div(nx, 32) * ceil_div(ny, 32) * n_frames * (HYST_MAX_ROOTS + 1) * 4) /*tile root lists + counts*/ + 8192 +
          align256(n * 8) /*generic path rows*/ + (1 << 16);
 }
 
@@ -1189,22 +1196,23 @@ int canny_device(b2f_ctx *ctx, const unsigned char *d_frames, int n_frames, int 
   }
   B2F_LAUNCH_CHECK(ctx);
   B2F_CUDA(cudaMemsetAsync(d_nonzero, 0, sizeof(int) * n_frames, st));
-  // ---- hysteresis: two-level union-find on the class bytes (tile-local in shared memory, seams with atomicMin)
-  B2F_CUDA(cudaMemsetAsync(strong, 0, n, st));
+  // ---- hysteresis: two-level union-find on the class bytes (tile-local in shared memory, seams with atomicMin);
+  // only root positions of `strong` / `rinfo` are used, and the local pass initialises them: no memsets
   dim3 tiles(ceil_div(nx, HT), ceil_div(ny, HT), n_frames);
-  B2F_CUDA(cudaMemsetAsync(rinfo, 0, n, st));
   {
     const int HTX = ceil_div(nx, HT), HTY = ceil_div(ny, HT), htn = HTX * HTY * n_frames;
-    hyst_local_kernel<<<ceil_div(htn, 8), 256, 0, st>>>(cls, L, rinfo, nx, ny, HTX, HTY, htn);
+    int *rootlist = ctx->arena.get<int>((size_t)htn * HYST_MAX_ROOTS);
+    int *rootcnt = ctx->arena.get<int>(htn);
+    B2F_ARENA_CHECK(ctx);
+    hyst_local_kernel<<<ceil_div(htn, 8), 256, 0, st>>>(cls, L, strong, rootlist, rootcnt, nx, ny, HTX, HTY, htn);
+    B2F_LAUNCH_CHECK(ctx);
+    hyst_seam_kernel<<<tiles, 3 * HT, 0, st>>>(cls, L, nx, ny);
+    B2F_LAUNCH_CHECK(ctx);
+    hyst_mark_list<<<ceil_div(htn, 8), 256, 0, st>>>(rootlist, rootcnt, L, strong, htn);
+    B2F_LAUNCH_CHECK(ctx);
+    hyst_resolve_list<<<ceil_div(htn, 8), 256, 0, st>>>(rootlist, rootcnt, L, strong, rinfo, htn);
+    B2F_LAUNCH_CHECK(ctx);
   }
-  B2F_LAUNCH_CHECK(ctx);
-  hyst_seam_kernel<<<tiles, 3 * HT, 0, st>>>(cls, L, nx, ny);
-  B2F_LAUNCH_CHECK(ctx);
-  unsigned nb16 = (unsigned)((n + 16 * 256 - 1) / (16 * 256));
-  hyst_mark<<<nb16, 256, 0, st>>>(rinfo, L, strong, n);
-  B2F_LAUNCH_CHECK(ctx);
-  hyst_resolve<<<nb16, 256, 0, st>>>(rinfo, L, strong, n);
-  B2F_LAUNCH_CHECK(ctx);
   const int vec = (plane % 16 == 0) && ((reinterpret_cast<uintptr_t>(d_edges) & 15) == 0);
   hyst_emit<<<dim3((unsigned)((plane + 16 * 256 - 1) / (16 * 256)), n_frames), 256, 0, st>>>(cls, L, rinfo, d_edges, d_nonzero, plane, vec);
   B2F_LAUNCH_CHECK(ctx);
