@@ -852,6 +852,11 @@ __device__ __forceinline__ int uf_find(volatile int *L, int a) {
   }
   return a;
 }
+__device__ __forceinline__ int uf_find_ro(const volatile int *L, int a) {   // no path compression: safe beside plain stores
+  int p = L[a];
+  while (p != a) { a = p; p = L[a]; }
+  return a;
+}
 __device__ __forceinline__ void uf_union(int *L, int a, int b) {
   while (true) {
     a = uf_find(L, a); b = uf_find(L, b);
@@ -902,7 +907,7 @@ hyst_local_kernel(const unsigned char *__restrict__ cls, int *__restrict__ L, un
   const int tx = tile % TX, ty = (tile / TX) % TY, f = tile / (TX * TY);
   const int x0 = tx * HT, y0 = ty * HT;
   const size_t base = (size_t)f * nx * ny;
-  // ---- row `lane` of the tile -> bit masks
+  // ---- row `lane` of the tile -> bit masks (class bytes are 0, 1 or 2: "edge" = bit0 | bit1, "strong" = bit1)
   unsigned emask = 0, smask = 0;
   {
     const int gy = y0 + lane;
@@ -912,9 +917,10 @@ hyst_local_kernel(const unsigned char *__restrict__ cls, int *__restrict__ L, un
         const uint4 a = *reinterpret_cast<const uint4 *>(row), b = *reinterpret_cast<const uint4 *>(row + 16);
         const unsigned w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-        for (int q = 0; q < 8; q++) {
-          emask |= nonzero_bytes_mask(__vcmpne4(w[q], 0u)) << (4 * q);
-          smask |= nonzero_bytes_mask(__vcmpeq4(w[q], 0x02020202u)) << (4 * q);
+        for (int q = 0; q < 8; q++) {       // one bit per byte at positions 0, 8, 16, 24 -> 4 adjacent bits (multiply, top byte)
+          const unsigned s1 = (w[q] >> 1) & 0x01010101u, e1 = (w[q] & 0x01010101u) | s1;
+          emask |= ((e1 * 0x01020408u) >> 24) << (4 * q);
+          smask |= ((s1 * 0x01020408u) >> 24) << (4 * q);
         }
       } else {
         for (int x = 0; x < 32; x++)
@@ -924,65 +930,62 @@ hyst_local_kernel(const unsigned char *__restrict__ cls, int *__restrict__ L, un
   }
   if (!__any_sync(0xffffffffu, emask != 0)) { if (lane == 0) rootcnt[tile] = 0; return; }   // empty tile
   const unsigned up = __shfl_up_sync(0xffffffffu, emask, 1);
-  // ---- heads
-  for (unsigned rem = emask; rem;) {
-    const int s = __ffs(rem) - 1;
-    rem &= ~run_mask_from(emask, s);
-    lab[lane * HT + s] = lane * HT + s;
-    cstrong[lane * HT + s] = 0;
-  }
+  // ---- every cell its own label (only run heads are ever looked at), flags cleared
+#pragma unroll
+  for (int r = 0; r < HT; r++) lab[r * HT + lane] = r * HT + lane;
+  reinterpret_cast<uint4 *>(cstrong)[lane] = make_uint4(0, 0, 0, 0);
+  reinterpret_cast<uint4 *>(cstrong)[lane + 32] = make_uint4(0, 0, 0, 0);
   __syncwarp();
-  // ---- link every run to the touching runs of the row above
+  // ---- link every run to the touching runs of the row above.  Runs are peeled lowest first:
+  //      low = lowest set bit, x = rem + low carries through the run, run = rem & ~x, rest = rem & x.
   if (lane > 0 && up) {
     for (unsigned rem = emask; rem;) {
-      const int s = __ffs(rem) - 1;
-      const unsigned rm = run_mask_from(emask, s);
-      rem &= ~rm;
+      const unsigned low = rem & (0u - rem), x = rem + low, rm = rem & ~x;
+      rem &= x;
       unsigned touch = up & (rm | (rm << 1) | (rm >> 1));
-      while (touch) {
-        const int b = __ffs(touch) - 1, us = run_start(up, b);
-        touch &= ~run_mask_from(up, us);
-        uf_union(lab, lane * HT + s, (lane - 1) * HT + us);
+      if (touch) {
+        const int me = lane * HT + (__ffs(low) - 1);
+        do {
+          const int b = __ffs(touch) - 1, us = run_start(up, b);
+          const unsigned uhi = up >> us << us, ulow = 1u << us;                 // the up-run that starts at us
+          touch &= ~(uhi & ~(uhi + ulow));
+          uf_union(lab, me, (lane - 1) * HT + us);
+        } while (touch);
       }
     }
   }
   __syncwarp();
-  // ---- flatten heads; afterwards every head holds its root
+  // ---- every head learns its root; a run with a class-2 pixel flags the root
   for (unsigned rem = emask; rem;) {
-    const int s = __ffs(rem) - 1;
-    rem &= ~run_mask_from(emask, s);
-    lab[lane * HT + s] = uf_find(lab, lane * HT + s);
-  }
-  __syncwarp();
-  for (unsigned rem = emask; rem;) {
-    const int s = __ffs(rem) - 1;
-    const unsigned rm = run_mask_from(emask, s);
-    rem &= ~rm;
-    if (smask & rm) cstrong[uf_find(lab, lane * HT + s)] = 1;
+    const unsigned low = rem & (0u - rem), x = rem + low, rm = rem & ~x;
+    rem &= x;
+    const int h = lane * HT + (__ffs(low) - 1);
+    const int rt = uf_find(lab, h);         // (compressing finds of other lanes may still rewrite lab[h] with an ancestor)
+    lab[h] = rt;
+    if (smask & rm) cstrong[rt] = 1;
   }
   __syncwarp();
   // ---- output (lane = column): root index per edge pixel; the tile's roots are appended to its slot list
-  // (<= 256 per tile: 8-connected components are at least two pixels apart) with the strong flag in bit 31
-  const int gx = x0 + lane;
+  // (<= 256 per tile: 8-connected components are at least two pixels apart) with the strong flag in bit 31.
+  // All indices fit in int (the batch is < 2^31 pixels).
   int nroots = 0;
   int *slots = rootlist + (size_t)tile * HYST_MAX_ROOTS;
+  const int gbase = (int)base + y0 * nx + x0;                   // global index of the tile's first pixel
   for (int r = 0; r < HT; r++) {
     const unsigned bits = __shfl_sync(0xffffffffu, emask, r);
     if (bits == 0) continue;                                    // (warp-uniform)
     const bool set = (bits >> lane) & 1u;
-    int rt = 0;
     bool isroot = false;
-    size_t p = 0;
+    int rt = 0, p = 0;
     if (set) {
-      rt = uf_find(lab, r * HT + run_start(bits, lane));
-      const int ry = rt / HT, rx = rt - ry * HT;
-      p = base + (size_t)(y0 + r) * nx + gx;
-      L[p] = (int)(base + (size_t)(y0 + ry) * nx + (x0 + rx));
+      rt = uf_find_ro(lab, r * HT + run_start(bits, lane));     // heads are (nearly) flat: one or two hops
+      p = gbase + r * nx + lane;
+      L[p] = gbase + (rt >> 5) * nx + (rt & 31);
       isroot = rt == r * HT + lane;
     }
     const unsigned rb = __ballot_sync(0xffffffffu, isroot);
     if (isroot) {
-      slots[nroots + __popc(rb & ((1u << lane) - 1u))] = (int)p | (cstrong[rt] ? (int)0x80000000 : 0);
+      slots[nroots + __popc(rb & ((1u << lane) - 1u))] = p | (cstrong[rt] ? (int)0x80000000 : 0);
       strong[p] = 0;                                            // every global root is some tile's root: no memset needed
     }
     nroots += __popc(rb);
@@ -1050,16 +1053,20 @@ __global__ void hyst_emit(const unsigned char *__restrict__ cls, const int *__re
   if (i0 < plane) {
     const size_t p0 = f * plane + i0;
     if (vec && i0 + 16 <= plane) {
-      uint4 v = *reinterpret_cast<const uint4 *>(cls + p0);
-      unsigned w[4] = {v.x, v.y, v.z, v.w}, o[4] = {0, 0, 0, 0};
+      const uint4 v = *reinterpret_cast<const uint4 *>(cls + p0);
+      const unsigned w[4] = {v.x, v.y, v.z, v.w};
+      unsigned o[4] = {0, 0, 0, 0};
+      if (v.x | v.y | v.z | v.w) {
+        // two dependent gathers per edge pixel: issue all label loads, then all flag loads
+        int l[16];
 #pragma unroll
-      for (int q = 0; q < 4; q++) {
-        if (!w[q]) continue;
+        for (int b = 0; b < 16; b++) l[b] = ((w[b >> 2] >> (8 * (b & 3))) & 0xff) ? L[p0 + b] : -1;
+        unsigned char r[16];
 #pragma unroll
-        for (int b = 0; b < 4; b++)
-          if ((w[q] >> (8 * b)) & 0xff) {
-            if (rinfo[L[p0 + 4 * q + b]] & 4) { o[q] |= 0xffu << (8 * b); mine++; }
-          }
+        for (int b = 0; b < 16; b++) r[b] = l[b] >= 0 ? rinfo[l[b]] : (unsigned char)0;
+#pragma unroll
+        for (int b = 0; b < 16; b++)
+          if (r[b] & 4) { o[b >> 2] |= 0xffu << (8 * (b & 3)); mine++; }
       }
       *reinterpret_cast<uint4 *>(edges + p0) = make_uint4(o[0], o[1], o[2], o[3]);
     } else {

@@ -128,28 +128,41 @@ harris_fused2_kernel(const void *__restrict__ frames, float *__restrict__ Rout, 
     constexpr int NP = 4 + 2 * RD + OFF;                       // positions loaded from the 4-aligned start (11) -> round up even
     constexpr int NL = (NP + 1) / 2 * 2;                       // 12
     constexpr int RPS = C::R1_H / 2;                           // 44 row pairs; consecutive threads = consecutive row pairs
-    for (int it = tid; it < RPS * GROUPS; it += C::NT) {
-      const int g = it / RPS, rp = it - g * RPS;
+    // software pipelined: the loads of item k+1 are issued before the stores of item k (the two tiles do not alias)
+    constexpr int NIT = (RPS * GROUPS + C::NT - 1) / C::NT;    // 4
+    float2 v[NL];
+    {
+      const int g = tid / RPS, rp = tid - g * RPS;             // (tid < RPS * GROUPS)
       const float2 *p = sINp + rp * C::IN_P + 4 * g;
-      float2 v[NL];
 #pragma unroll
-      for (int q = 0; q < NL / 2; q++) {
-        float4 t = *reinterpret_cast<const float4 *>(p + 2 * q);
-        v[2 * q] = f2(t.x, t.y); v[2 * q + 1] = f2(t.z, t.w);
+      for (int q = 0; q < NL / 2; q++) { const float4 t = *reinterpret_cast<const float4 *>(p + 2 * q); v[2 * q] = f2(t.x, t.y); v[2 * q + 1] = f2(t.z, t.w); }
+    }
+#pragma unroll
+    for (int k = 0; k < NIT; k++) {
+      const int it = tid + k * C::NT;
+      if (it < RPS * GROUPS) {
+        const int g = it / RPS, rp = it - g * RPS;
+        float2 o[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int c = j + OFF + RD;
+          float2 acc = __fmul2_rn(f2s(kc.wd[0]), v[c]);
+#pragma unroll
+          for (int t = 1; t <= RD; t++) acc = __ffma2_rn(f2s(kc.wd[t]), __fadd2_rn(v[c - t], v[c + t]), acc);
+          o[j] = acc;
+        }
+        const int itn = it + C::NT;
+        if (k + 1 < NIT && itn < RPS * GROUPS) {
+          const int gn = itn / RPS, rpn = itn - gn * RPS;
+          const float2 *p = sINp + rpn * C::IN_P + 4 * gn;
+#pragma unroll
+          for (int q = 0; q < NL / 2; q++) { const float4 t = *reinterpret_cast<const float4 *>(p + 2 * q); v[2 * q] = f2(t.x, t.y); v[2 * q + 1] = f2(t.z, t.w); }
+        }
+        float *d = sR1 + (2 * rp) * C::R1_P + 4 * g;
+        *reinterpret_cast<float4 *>(d) = make_float4(o[0].x, o[1].x, o[2].x, o[3].x);
+        *reinterpret_cast<float2 *>(d + C::R1_P) = make_float2(o[0].y, o[1].y);      // odd rows are only 8-byte aligned
+        *reinterpret_cast<float2 *>(d + C::R1_P + 2) = make_float2(o[2].y, o[3].y);
       }
-      float2 o[4];
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int c = j + OFF + RD;
-        float2 acc = __fmul2_rn(f2s(kc.wd[0]), v[c]);
-#pragma unroll
-        for (int t = 1; t <= RD; t++) acc = __ffma2_rn(f2s(kc.wd[t]), __fadd2_rn(v[c - t], v[c + t]), acc);
-        o[j] = acc;
-      }
-      float *d = sR1 + (2 * rp) * C::R1_P + 4 * g;
-      *reinterpret_cast<float4 *>(d) = make_float4(o[0].x, o[1].x, o[2].x, o[3].x);
-      *reinterpret_cast<float2 *>(d + C::R1_P) = make_float2(o[0].y, o[1].y);      // odd rows are only 8-byte aligned
-      *reinterpret_cast<float2 *>(d + C::R1_P + 2) = make_float2(o[2].y, o[3].y);
     }
   }
   __syncthreads();
