@@ -61,6 +61,9 @@ def load():
     lib.b2f_launch_count.argtypes = [vp]
     lib.b2f_launch_count.restype = C.c_longlong
     lib.b2f_set_chunk_bytes.argtypes = [vp, C.c_size_t]
+    lib.b2f_otsu_host.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, ip]
+    lib.b2f_otsu_batch_u8.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
+    lib.b2f_otsu_dev.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]
     lib.b2f_harris_default_params.argtypes = [C.POINTER(HarrisParams)]
     lib.b2f_harris_host.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(HarrisParams), C.POINTER(fp), C.POINTER(fp), C.POINTER(fp), ip]
     lib.b2f_harris_batch_u8.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(HarrisParams), C.c_int, vp, vp, vp, vp]
@@ -141,4 +144,5 @@ EXPORTS = [
     "b2f_launch_count", "b2f_set_chunk_bytes", "b2f_harris_default_params", "b2f_harris_host", "b2f_harris_batch_u8",
     "b2f_harris_response_dev", "b2f_harris_nms_dev", "b2f_canny_host", "b2f_canny_batch", "b2f_canny_dev",
     "b2f_fhog_size", "b2f_fhog_host", "b2f_fhog_batch", "b2f_fhog_dev", "b2f_surf_host", "b2f_surf_batch",
+    "b2f_otsu_host", "b2f_otsu_batch_u8", "b2f_otsu_dev",
 ]

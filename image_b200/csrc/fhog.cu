@@ -290,8 +290,80 @@ fhog_feature_kernel(const float *__restrict__ hist, const float *__restrict__ no
   for (int i = threadIdx.x; i < ncell * 31; i += FF_NT) dst[i] = so[i];
 }
 
+// ------------------------------------------------------------------------------------------ cell_size == 1
+// dlib's separate routine (impl_extract_fhog_features_cell_size_1, fhog.h:495-694): every interior pixel is
+// its own cell.  Pass 1 stores the SQUARED gradient length of the strongest channel (float) and the 18-way
+// orientation of every interior pixel (border: 0, zero_border_pixels fhog.h:545); pass 2 turns the 3x3 block of
+// norms around a pixel into the six non-zero features of its 31-vector (the others stay 0:
+// init_hog_zero_everything, fhog.h:473-491).
+__global__ void __launch_bounds__(256)
+fhog1_pixel_kernel(const unsigned char *__restrict__ frames, float *__restrict__ norm, unsigned char *__restrict__ angle,
+                   FhogGeom g, const unsigned char *__restrict__ lut) {
+  const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+  if (x >= g.cols || y >= g.rows) return;
+  const size_t px = (size_t)blockIdx.z * g.rows * g.cols + (size_t)y * g.cols + x;
+  if (x < 1 || y < 1 || x >= g.visible_nc || y >= g.visible_nr) { norm[px] = 0.f; angle[px] = 0; return; }
+  const unsigned char *p = frames + px * 3;
+  const int rs = g.cols * 3;
+  const bool simd = x < g.simd_end;
+  int bx = 0, by = 0, bl = -1;
+#pragma unroll
+  for (int ch = 0; ch < 3; ch++) {
+    const int dx = (int)__ldg(p + 3 + ch) - (int)__ldg(p - 3 + ch);
+    const int dy = (int)__ldg(p + rs + ch) - (int)__ldg(p - rs + ch);
+    const int l = dx * dx + dy * dy;
+    const bool take = (ch == 0) || (simd ? !(bl > l) : (l > bl));     // SIMD body keeps the later channel on ties, the scalar tail the earlier
+    if (take) { bx = dx; by = dy; bl = l; }
+  }
+  norm[px] = (float)bl;
+  angle[px] = __ldg(lut + ((by + 255) << 9) + (bx + 255));
+}
+
+constexpr int F1_NT = 64;
+__global__ void __launch_bounds__(F1_NT)
+fhog1_feature_kernel(const float *__restrict__ norm, const unsigned char *__restrict__ angle, float *__restrict__ out, FhogGeom g) {
+  __shared__ float sn[3][F1_NT + 2];
+  __shared__ float so[F1_NT * 31];
+  const int xb = blockIdx.x * F1_NT, y = blockIdx.y;
+  const int ncell = min(F1_NT, g.hog_nc - xb);
+  const float *N = norm + (size_t)blockIdx.z * g.rows * g.cols;
+  for (int i = threadIdx.x; i < 3 * (ncell + 2); i += F1_NT) {
+    const int r = i / (ncell + 2), c = i - r * (ncell + 2);
+    sn[r][c] = __ldg(N + (size_t)(y + r) * g.cols + xb + c);
+  }
+  for (int i = threadIdx.x; i < ncell * 31; i += F1_NT) so[i] = 0.f;
+  __syncthreads();
+  const int t = threadIdx.x;
+  if (t < ncell) {
+    const float n00 = sn[0][t], n01 = sn[0][t + 1], n02 = sn[0][t + 2], n10 = sn[1][t], n11 = sn[1][t + 1], n12 = sn[1][t + 2],
+                n20 = sn[2][t], n21 = sn[2][t + 1], n22 = sn[2][t + 2];
+    const float z1[4] = {n11, n01, n10, n00}, z2[4] = {n12, n02, n11, n01}, z3[4] = {n21, n11, n20, n10}, z4[4] = {n22, n12, n21, n11};
+    const float temp0 = __fsqrt_rn(n11);
+    float h0[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const float s = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(z1[k], z2[k]), z3[k]), z4[k]), 0.0001f);
+      const float nn = __fmul_rn(0.2f, __fsqrt_rn(s));
+      const float n = __fdiv_rn(0.1f, nn);
+      h0[k] = __fmul_rn(temp0 < nn ? temp0 : nn, n);                    // min(temp0, nn) * n
+    }
+    const float vv = __fadd_rn(__fadd_rn(h0[0], h0[2]), __fadd_rn(h0[1], h0[3]));   // sum(simd4f), SSE2 order
+    const float tscale = (float)(2 * 0.2357);
+    const int a = __ldg(angle + (size_t)blockIdx.z * g.rows * g.cols + (size_t)(y + 1) * g.cols + xb + t + 1);
+    float *o31 = so + t * 31;
+    o31[a] = vv;
+    o31[a % 9 + 18] = vv;
+#pragma unroll
+    for (int k = 0; k < 4; k++) o31[27 + k] = __fmul_rn(__fadd_rn(0.f, h0[k]), tscale);
+  }
+  __syncthreads();
+  float *dst = out + (((size_t)blockIdx.z * g.out_nr + (y + g.pad_r)) * g.out_nc + (xb + g.pad_c)) * 31;
+  for (int i = threadIdx.x; i < ncell * 31; i += F1_NT) dst[i] = so[i];
+}
+
 // ------------------------------------------------------------------------------------------ host
 size_t fhog_scratch_bytes(int n_frames, const FhogGeom &g) {
+  if (g.cell == 1) return align256((size_t)n_frames * g.rows * g.cols * 4) + align256((size_t)n_frames * g.rows * g.cols) + (1 << 16);
   size_t hist = (size_t)n_frames * (g.cells_nr + 2) * (g.cells_nc + 2) * 18 * 4;
   size_t norm = (size_t)n_frames * g.cells_nr * g.cells_nc * 4;
   size_t tabs = (size_t)(g.rows + g.cols) * (2 + 4 + 4) + (size_t)(g.cells_nr + g.cells_nc + 4) * 8 + 4096;
@@ -396,7 +468,34 @@ static int fhog_tables(b2f_ctx *ctx, const FhogGeom &g, cudaStream_t st, FhogTab
   return B2F_OK;
 }
 
+static int fhog_ensure_lut(b2f_ctx *ctx, cudaStream_t st) {
+  if (ctx->fhog_lut) return B2F_OK;       // one-time 256 KB orientation table
+  void *lut = nullptr;
+  B2F_CUDA(cudaMalloc(&lut, 512 * 512));
+  fhog_lut_kernel<<<dim3(2, 511), 256, 0, st>>>((unsigned char *)lut);
+  B2F_LAUNCH_CHECK(ctx);
+  ctx->fhog_lut = lut;
+  return B2F_OK;
+}
+
+static int fhog1_device(b2f_ctx *ctx, const unsigned char *d_frames, int n_frames, const FhogGeom &g, float *d_out, cudaStream_t st) {
+  const size_t px = (size_t)n_frames * g.rows * g.cols;
+  float *norm = ctx->arena.get<float>(px);
+  unsigned char *angle = ctx->arena.get<unsigned char>(px);
+  B2F_ARENA_CHECK(ctx);
+  int rc = fhog_ensure_lut(ctx, st);
+  if (rc != B2F_OK) return rc;
+  fhog1_pixel_kernel<<<dim3(ceil_div(g.cols, 64), ceil_div(g.rows, 4), n_frames), 256, 0, st>>>(d_frames, norm, angle, g, (const unsigned char *)ctx->fhog_lut);
+  B2F_LAUNCH_CHECK(ctx);
+  if (g.out_nr != g.hog_nr || g.out_nc != g.hog_nc)   // zero border of init_hog_zero_everything
+    B2F_CUDA(cudaMemsetAsync(d_out, 0, sizeof(float) * (size_t)n_frames * g.out_nr * g.out_nc * 31, st));
+  fhog1_feature_kernel<<<dim3(ceil_div(g.hog_nc, F1_NT), g.hog_nr, n_frames), F1_NT, 0, st>>>(norm, angle, d_out, g);
+  B2F_LAUNCH_CHECK(ctx);
+  return B2F_OK;
+}
+
 int fhog_device(b2f_ctx *ctx, const unsigned char *d_frames, int n_frames, const FhogGeom &g, float *d_out, cudaStream_t st) {
+  if (g.cell == 1) return fhog1_device(ctx, d_frames, n_frames, g, d_out, st);
   const int cell = g.cell, HR = g.cells_nr + 2, HC = g.cells_nc + 2;
   FhogTabDev td;
   int trc = fhog_tables(ctx, g, st, td);
@@ -413,12 +512,9 @@ int fhog_device(b2f_ctx *ctx, const unsigned char *d_frames, int n_frames, const
   B2F_ARENA_CHECK(ctx);
 
   const int NCB = g.cols / cell + 2, PW = cell * NCB;
-  if (!ctx->fhog_lut) {       // one-time 256 KB orientation table
-    void *lut = nullptr;
-    B2F_CUDA(cudaMalloc(&lut, 512 * 512));
-    fhog_lut_kernel<<<dim3(2, 511), 256, 0, st>>>((unsigned char *)lut);
-    B2F_LAUNCH_CHECK(ctx);
-    ctx->fhog_lut = lut;
+  {
+    int lrc = fhog_ensure_lut(ctx, st);
+    if (lrc != B2F_OK) return lrc;
   }
   fhog_pixel_kernel<<<dim3(ceil_div(std::max(g.visible_nc - 1, 1), FP_TW), ceil_div(std::max(g.visible_nr - 1, 1), FP_TH), n_frames), FH_NT, 0, st>>>(
       d_frames, vmag, obin, g, d_colidx, PW, (const unsigned char *)ctx->fhog_lut,
@@ -443,7 +539,6 @@ int fhog_device(b2f_ctx *ctx, const unsigned char *d_frames, int n_frames, const
 static int fhog_check(const char *who, int rows, int cols, int cell, int frp, int fcp) {
   if (rows <= 0 || cols <= 0) { set_error("%s: bad image size %dx%d", who, rows, cols); return B2F_EINVAL; }
   if (cell <= 0 || frp <= 0 || fcp <= 0) { set_error("%s: cell_size and the paddings must be > 0 (fhog.h:710-717)", who); return B2F_EINVAL; }
-  if (cell == 1) { set_error("%s: cell_size == 1 (dlib's separate routine fhog.h:495-694) is not implemented on the GPU path", who); return B2F_EUNSUP; }
   return B2F_OK;
 }
 
@@ -455,7 +550,7 @@ extern "C" {
 
 int b2f_fhog_size(int rows, int cols, int cell_size, int frp, int fcp, int *hog_nr, int *hog_nc) {
   if (!hog_nr || !hog_nc) { set_error("b2f_fhog_size: NULL output"); return B2F_EINVAL; }
-  int rc = fhog_check("b2f_fhog_size", rows, cols, cell_size == 1 ? 2 : cell_size, frp, fcp);
+  int rc = fhog_check("b2f_fhog_size", rows, cols, cell_size, frp, fcp);
   if (rc != B2F_OK) return rc;
   FhogGeom g;
   fhog_geometry(rows, cols, cell_size, frp, fcp, g);

@@ -131,6 +131,21 @@ int b2f_surf_host(b2f_ctx *ctx, const uint8_t *rgb, int rows, int cols, long max
 int b2f_surf_batch(b2f_ctx *ctx, const uint8_t *frames, int n_frames, int rows, int cols, long max_points,
                    double detection_threshold, int cap, b2f_surf_point *points, int *counts);
 
+/* -------------------------------------------------------------------------------- Otsu ----
+ * SURVEY.md 8f "next", rank 4.  Replaces the body of otsu() (image.Otsu/src/rcpp_otsu.cpp:166-186:
+ * computeHistogram :63-81, computeOtsusSegmentation :113-163, segmentImage :88-105).
+ * override_threshold 0 = compute the Otsu threshold (the reference's convention), 1..255 = use it.
+ * b2f_otsu_host: `img` = the NumericVector narrowed to float (rcpp_otsu.cpp:170-172), any linear order;
+ *   out = 255.0f / 0.0f per pixel, *threshold = the threshold used.  Pixel values whose (int) truncation is
+ *   outside 0..255 are undefined behaviour in the reference and give B2F_EINVAL here.
+ * b2f_otsu_batch_u8 / b2f_otsu_dev: new surface, u8 frames [n][height][width] in host / device memory,
+ *   u8 0/255 output, one threshold per frame. */
+int b2f_otsu_host(b2f_ctx *ctx, const float *img, int width, int height, int override_threshold, float *out, int *threshold);
+int b2f_otsu_batch_u8(b2f_ctx *ctx, const uint8_t *frames, int n_frames, int width, int height, int override_threshold,
+                      uint8_t *out, int *thresholds);
+int b2f_otsu_dev(b2f_ctx *ctx, const uint8_t *d_frames, int n_frames, int width, int height, int override_threshold,
+                 uint8_t *d_out, int *d_thresholds, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,7 +9,8 @@
  * Pinned by (a) oracle/_ref (the unmodified headers, bit-identical on every test frame) and
  * (b) dlib's own golden vectors dlib/test/fhog.cpp:156-213 replayed in tests/golden/fhog_dlib_*.npz.
  *
- * cell_size == 1 takes a separate routine in dlib (fhog.h:495-694) that is not restated here.
+ * cell_size == 1 takes a separate routine in dlib (impl_extract_fhog_features_cell_size_1,
+ * fhog.h:495-694), restated in orc_fhog_cell1 below.
  * Compiled with -ffp-contract=off: float expressions round exactly like the reference.
  */
 #include <math.h>
@@ -45,6 +46,81 @@ static void pixel_gradient(const uint8_t *rgb, int cols, int r, int c, int simd,
   *gx = bx; *gy = by; *len = bl;
 }
 
+/* cell_size == 1 (fhog.h:495-694): every interior pixel is its own cell.  norm = SQUARED gradient
+ * length of the strongest channel (the value get_gradient returns), angle = the 18-way snap; per hog
+ * cell only features angle, angle%9+18 and the four texture features are non-zero
+ * (init_hog_zero_everything, fhog.h:473-491). */
+static int orc_fhog_cell1(const uint8_t *rgb, int rows, int cols, int frp, int fcp, double *out, int onr, int onc) {
+  if (rows <= 2 || cols <= 2) return 0;                                    /* hog.clear(), fhog.h:535-539 */
+  const int hr = rows - 2, hc = cols - 2;
+  float *norm = (float *)calloc((size_t)rows * cols, sizeof(float));       /* zero_border_pixels(norm,1,1) */
+  unsigned char *angle = (unsigned char *)calloc((size_t)rows * cols, 1);
+  const int visible_nr = rows - 1, visible_nc = cols - 1;
+  for (int y = 1; y < visible_nr; y++) {
+    int x = 1;
+    for (; x < visible_nc - 7; x += 8)                                     /* simd8 body :560-609 */
+      for (int l = 0; l < 8; l++) {
+        int gx, gy, len;
+        pixel_gradient(rgb, cols, y, x + l, 1, &gx, &gy, &len);
+        float best_dot = 0, fgx = (float)gx, fgy = (float)gy;
+        int best_o = 0;
+        for (int o = 0; o < 9; o++) {
+          float dot = fgx * DIRX[o] + fgy * DIRY[o];
+          if (dot > best_dot) { best_dot = dot; best_o = o; }
+          dot *= -1;
+          if (dot > best_dot) { best_dot = dot; best_o = o + 9; }
+        }
+        norm[(size_t)y * cols + x + l] = (float)len;
+        angle[(size_t)y * cols + x + l] = (unsigned char)best_o;
+      }
+    for (; x < visible_nc; x++) {                                          /* scalar tail :611-637 */
+      int gx, gy, len;
+      pixel_gradient(rgb, cols, y, x, 0, &gx, &gy, &len);
+      float best_dot = 0, fgx = (float)gx, fgy = (float)gy;
+      int best_o = 0;
+      for (int o = 0; o < 9; o++) {
+        const float dot = DIRX[o] * fgx + DIRY[o] * fgy;
+        if (dot > best_dot) { best_dot = dot; best_o = o; }
+        else if (-dot > best_dot) { best_dot = -dot; best_o = o + 9; }
+      }
+      norm[(size_t)y * cols + x] = (float)len;
+      angle[(size_t)y * cols + x] = (unsigned char)best_o;
+    }
+  }
+#define N1(r, c) norm[(size_t)(r) * cols + (c)]
+  const float eps = 0.0001;
+  const int pro = (frp - 1) / 2, pco = (fcp - 1) / 2;
+  memset(out, 0, sizeof(double) * (size_t)onr * onc * 31);
+#define OUT1(yy, xx, f) out[(size_t)(yy) + (size_t)onr * ((size_t)(xx) + (size_t)onc * (f))]
+  for (int y = 0; y < hr; y++)
+    for (int x = 0; x < hc; x++) {                                         /* features :641-691 */
+      const float z1[4] = {N1(y + 1, x + 1), N1(y, x + 1), N1(y + 1, x), N1(y, x)};
+      const float z2[4] = {N1(y + 1, x + 2), N1(y, x + 2), N1(y + 1, x + 1), N1(y, x + 1)};
+      const float z3[4] = {N1(y + 2, x + 1), N1(y + 1, x + 1), N1(y + 2, x), N1(y + 1, x)};
+      const float z4[4] = {N1(y + 2, x + 2), N1(y + 1, x + 2), N1(y + 2, x + 1), N1(y + 1, x + 1)};
+      const float temp0 = sqrtf(N1(y + 1, x + 1));
+      float h0[4], t[4];
+      for (int k = 0; k < 4; k++) {
+        float s = z1[k] + z2[k]; s = s + z3[k]; s = s + z4[k]; s = s + eps;
+        const float nn = 0.2f * sqrtf(s);
+        const float n = 0.1f / nn;
+        h0[k] = (temp0 < nn ? temp0 : nn) * n;                             /* min(temp0,nn)*n */
+      }
+      const float vv = (h0[0] + h0[2]) + (h0[1] + h0[3]);                  /* sum(simd4f), SSE2 order */
+      const float tscale = 2 * 0.2357;
+      for (int k = 0; k < 4; k++) { t[k] = 0.0f + h0[k]; t[k] = t[k] * tscale; }
+      const int a = angle[(size_t)(y + 1) * cols + x + 1];
+      const int yy = y + pro, xx = x + pco;
+      OUT1(yy, xx, a) = vv;
+      OUT1(yy, xx, a % 9 + 18) = vv;
+      for (int k = 0; k < 4; k++) OUT1(yy, xx, 27 + k) = t[k];
+    }
+#undef N1
+#undef OUT1
+  free(norm); free(angle);
+  return 0;
+}
+
 /* img: interleaved RGB ints as R passes them (index 3*c + 3*cols*r + ch), narrowed to unsigned char
  * by rgb_pixel(...) (rcpp_fhog.cpp:21-22).  out (may be NULL for a size query): doubles in the
  * glue's order y + nr*(x + nc*feat) (rcpp_fhog.cpp:29-38). */
@@ -56,6 +132,7 @@ int orc_fhog(const int *img, int rows, int cols, int cell, int frp, int fcp, dou
   size_t npx = (size_t)rows * cols;
   uint8_t *rgb = (uint8_t *)malloc(npx * 3);
   for (size_t i = 0; i < npx * 3; i++) rgb[i] = (unsigned char)img[i];
+  if (cell == 1) { int rc1 = orc_fhog_cell1(rgb, rows, cols, frp, fcp, out, onr, onc); free(rgb); return rc1; }
   const int HW = cells_nc + 2;
   float *hist = (float *)calloc((size_t)(cells_nr + 2) * HW * 18, sizeof(float));
   float *norm = (float *)calloc((size_t)cells_nr * cells_nc, sizeof(float));

@@ -30,7 +30,7 @@ _cache = {}
 
 
 def lib(name):
-    """name in {'oracle','ref_harris','ref_canny','ref_dlib'}; None if that .so is absent."""
+    """name in {'oracle','ref_harris','ref_canny','ref_dlib','ref_otsu'}; None if that .so is absent."""
     if name not in _cache:
         p = os.path.join(HERE, "liboracle.so") if name == "oracle" else os.path.join(HERE, "_ref", "lib%s.so" % name)
         _cache[name] = _load(p)
@@ -169,6 +169,21 @@ def fhog(rgb, cell=8, frp=1, fcp=1, impl="oracle"):
     n = hnr.value * hnc.value * 31
     # glue order: y + nr*(x + nc*feat)  -> numpy [feat, x, y] -> [y, x, feat]
     return out[:n].reshape(31, hnc.value, hnr.value).transpose(2, 1, 0).copy()
+
+# ------------------------------------------------------------------------------------------ Otsu
+
+
+def otsu(x, width, height, threshold=0, impl="oracle"):
+    """otsu(x, width, height, threshold) of image.Otsu: x = width*height doubles.  Returns (out doubles, threshold)."""
+    v = np.ascontiguousarray(np.asarray(x, dtype=np.float64).ravel())
+    out = np.zeros_like(v)
+    t = C.c_int(0)
+    fn = lib("ref_otsu").ref_otsu if impl == "ref" else lib("oracle").orc_otsu
+    fn.restype = C.c_int
+    rc = fn(_p(v), int(width), int(height), int(threshold), _p(out), C.byref(t))
+    if rc != 0:
+        raise ValueError("pixel values outside 0..255")
+    return out, int(t.value)
 
 # ------------------------------------------------------------------------------------------ SURF
 

@@ -51,6 +51,10 @@ def boat():
         f[name] = po.fhog(img, impl="ref", **kw).astype(np.float32)
         f[name + "_args"] = np.array(repr(kw))
     np.savez_compressed(os.path.join(OUT, "fhog_boat.npz"), **f)
+    # cell_size == 1 (dlib's separate routine): a 96 x 128 crop keeps the fixture small (31 floats per pixel)
+    crop = np.ascontiguousarray(img[100:196, 200:328])
+    np.savez_compressed(os.path.join(OUT, "fhog_cell1.npz"), image=crop,
+                        fhog=po.fhog(crop, impl="ref", cell=1, frp=1, fcp=1).astype(np.float32))
     s = {"image": img}
     for name, kw in {"default": dict(max_points=1000, thr=30.0), "all": dict(max_points=10000, thr=5.0)}.items():
         r = po.surf(img, impl="ref", **kw)

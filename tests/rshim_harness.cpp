@@ -11,6 +11,7 @@ SEXP detect_corners(Rcpp::NumericVector x, int nx, int ny, float k, float sigma_
 Rcpp::List canny_edge_detector(Rcpp::IntegerVector image, int X, int Y, double s, double low_thr, double high_thr, bool accGrad);
 Rcpp::List dlib_fhog(std::vector<int> x, int rows, int cols, const int cell_size, const int frp, const int fcp);
 Rcpp::List dlib_surf_points(std::vector<int> x, int rows, int cols, long max_points, double detection_threshold);
+Rcpp::List otsu(Rcpp::NumericVector x, int width, int height, int threshold);
 
 extern "C" {
 int shim_harris(const double *img, int nx, int ny, float threshold, int gaussian, int precision, float *x, float *y, float *s, int cap) {
@@ -40,6 +41,15 @@ int shim_fhog(const int *img, int rows, int cols, double *out, int *nr, int *nc)
     const std::vector<double> &f = l.get("fhog").data;
     if (out) std::memcpy(out, f.data(), f.size() * sizeof(double));
     return 0;
+  } catch (std::exception &e) { return -1; }
+}
+int shim_otsu(const double *img, int width, int height, int threshold, double *out) {
+  try {
+    Rcpp::NumericVector v(img, (size_t)width * height);
+    Rcpp::List l = otsu(v, width, height, threshold);
+    const std::vector<double> &o = l.get("x").data;
+    for (size_t i = 0; i < o.size(); i++) out[i] = o[i];
+    return (int)l.get("threshold").data[0];
   } catch (std::exception &e) { return -1; }
 }
 int shim_surf(const int *img, int rows, int cols, long max_points, double thr, int cap, double *x, double *score, double *surf) {

@@ -32,6 +32,31 @@ def test_fhog_bit_exact_vs_oracle(oracle, shape, cell, frp, fcp):
         _check(hog[i], oracle.fhog(frames[i], cell, frp, fcp), "frame %d" % i)
 
 
+@pytest.mark.parametrize("shape,frp,fcp", [((40, 53), 1, 1), ((33, 64), 3, 5), ((3, 3), 1, 1), ((97, 203), 2, 2), ((64, 3), 1, 1),
+                                           ((5, 300), 1, 4), ((270, 480), 1, 1)])
+def test_fhog_cell_size_1_bit_exact_vs_oracle(oracle, shape, frp, fcp):
+    """dlib's separate cell_size == 1 routine (fhog.h:495-694): one cell per interior pixel."""
+    from image_b200 import synth
+    from image_b200.dlib import fhog_batch, fhog_size
+    rows, cols = shape
+    rng = np.random.default_rng(rows * 11 + cols)
+    frames = np.stack([synth.frame_rgb(910 + rows, rows, cols),
+                       (synth.frame_rgb(911 + cols, rows, cols) // 32 * 32).astype(np.uint8),     # many colour ties and flat areas
+                       rng.integers(0, 255, (rows, cols, 3)).astype(np.uint8)])
+    assert fhog_size(rows, cols, 1, frp, fcp) == (rows - 2 + frp - 1, cols - 2 + fcp - 1)
+    hog = fhog_batch(frames, 1, frp, fcp)
+    for i in range(3):
+        _check(hog[i], oracle.fhog(frames[i], 1, frp, fcp), "frame %d" % i)
+    assert int((hog[0] != 0).sum()) <= 6 * (rows - 2) * (cols - 2)          # at most six non-zero features per cell
+
+
+def test_fhog_cell_size_1_matches_reference_fixture(golden):
+    from image_b200.dlib import fhog_batch
+    g = golden("fhog_cell1")
+    hog = fhog_batch(g["image"][None], 1, 1, 1)[0]
+    _check(hog, g["fhog"], "cell_size 1 fixture (oracle/_ref output)")
+
+
 def test_image_fhog_mirror_layout(oracle):
     from image_b200 import synth
     from image_b200.dlib import image_fhog
@@ -47,6 +72,9 @@ def test_small_images_give_empty_output(oracle):
     for rows, cols in [(8, 8), (15, 40), (40, 19), (3, 3)]:
         assert fhog_size(rows, cols) == (0, 0)
         assert fhog_batch(np.zeros((1, rows, cols, 3), np.uint8)).size == 0
+    for rows, cols in [(2, 9), (9, 2), (1, 1)]:                                  # cell_size 1: nr <= 2 or nc <= 2 -> hog.clear()
+        assert fhog_size(rows, cols, 1) == (0, 0)
+        assert fhog_batch(np.zeros((1, rows, cols, 3), np.uint8), 1).size == 0
     from image_b200 import B2FError
     with pytest.raises(B2FError):
         fhog_size(64, 64, 0)

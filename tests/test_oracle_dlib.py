@@ -70,3 +70,30 @@ def test_surf_oracle_equals_reference(oracle):
         assert len(a["x"]) == len(b["x"])
         for k in a:
             assert np.array_equal(a[k], b[k]), k
+
+
+def test_fhog_cell_size_1_oracle_matches_reference_fixture(oracle, golden):
+    """cell_size == 1 takes dlib's separate routine (fhog.h:495-694); fixture = oracle/_ref output."""
+    g = golden("fhog_cell1")
+    out = oracle.fhog(g["image"], cell=1)
+    assert out.shape == g["fhog"].shape and np.array_equal(out.astype(np.float32), g["fhog"])
+    assert int((out != 0).sum()) <= 6 * out.shape[0] * out.shape[1]
+
+
+def test_otsu_oracle_matches_reference_build_and_fixture(oracle, golden):
+    """image.Otsu (8f rank 4): the restatement equals the unmodified source compiled in place, and the
+    frozen output of that build on the package's own coins.jpeg."""
+    g = golden("otsu_coins")
+    img = g["image"].astype(np.float64)
+    h, w = img.shape
+    o, t = oracle.otsu(img.ravel(order="F"), w, h, 0)
+    assert t == int(g["threshold"])
+    assert np.array_equal(o.reshape(img.shape, order="F") > 0, np.unpackbits(g["mask"])[: img.size].reshape(img.shape).astype(bool))
+    if oracle.have_ref("otsu"):
+        rng = np.random.default_rng(5)
+        for k in range(12):
+            hh, ww = int(rng.integers(1, 60)), int(rng.integers(1, 80))
+            x = rng.integers(0, 256, hh * ww).astype(np.float64) if k % 2 else rng.random(hh * ww) * 255.9
+            for thr in (0, 33):
+                a, b = oracle.otsu(x, ww, hh, thr), oracle.otsu(x, ww, hh, thr, impl="ref")
+                assert a[1] == b[1] and np.array_equal(a[0], b[0])

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def shim(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("shim") / "libshim.so")
     rs = os.path.join(ROOT, "image_b200", "rshim")
-    srcs = [os.path.join(rs, f) for f in ("rcpp_harris.cpp", "rcpp_canny.cpp", "rcpp_fhog.cpp", "rcpp_surf.cpp")]
+    srcs = [os.path.join(rs, f) for f in ("rcpp_harris.cpp", "rcpp_canny.cpp", "rcpp_fhog.cpp", "rcpp_surf.cpp", "rcpp_otsu.cpp")]
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "oracle", "stubs"),
                            "-I" + os.path.join(ROOT, "include"), "-I" + rs, os.path.join(ROOT, "tests", "rshim_harness.cpp")] + srcs +
                           ["-L" + os.path.join(ROOT, "image_b200"), "-lb200feat", "-Wl,-rpath," + os.path.join(ROOT, "image_b200"), "-o", out])
@@ -72,3 +72,12 @@ def test_surf_shim(shim, oracle):
     assert n == len(ref["x"]) and np.array_equal(x[:n], ref["x"]) and np.array_equal(sc[:n], ref["score"])
     if n:
         np.testing.assert_allclose(des[: n * 64].reshape(n, 64), ref["surf"], rtol=1e-4, atol=1e-9)
+
+
+def test_otsu_shim(shim, oracle):
+    from image_b200 import synth
+    img = synth.frame_shapes(25, 90, 140).astype(np.float64)
+    out = np.zeros(90 * 140, np.float64)
+    t = shim.shim_otsu(_p(img.ravel()), 140, 90, 0, _p(out))
+    o, ot = oracle.otsu(img.ravel(), 140, 90, 0)
+    assert t == ot and np.array_equal(out, o)
