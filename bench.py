@@ -102,31 +102,56 @@ def available_detectors():
 
 
 # ------------------------------------------------------------------------------------------ reference arm
+def _host_memory_available():
+    """Bytes this process may still allocate: MemAvailable, capped by the cgroup limit when there is one."""
+    avail = None
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                avail = int(line.split()[1]) * 1024
+    except OSError:
+        pass
+    try:
+        mx = open("/sys/fs/cgroup/memory.max").read().strip()
+        if mx != "max":
+            cur = int(open("/sys/fs/cgroup/memory.current").read())
+            avail = min(avail, int(mx) - cur) if avail is not None else int(mx) - cur
+    except (OSError, ValueError):
+        pass
+    return avail
+
+
 def run_reference(args, dets):
     """The reference's own CPU implementation (oracle/_ref when built, else the oracle port) on the
-    box's host cores.  Harris is OpenMP-parallel inside one frame (reference behaviour); Canny and
-    FHOG are single-threaded in the reference, so independent frames run one per core."""
+    box's host cores, with every core busy: a step is `nf` independent frames (default: up to 64, bounded
+    by host memory) whose Harris / Canny / FHOG calls all go through one thread pool.  Canny and FHOG are
+    single-threaded in the reference; Harris is OpenMP-parallel inside a frame and gets cores/nf threads."""
     from concurrent.futures import ThreadPoolExecutor
+    cores = os.cpu_count() or 1
+    mem = _host_memory_available()
+    nf_mem = max(1, int(mem // (3 << 30))) if mem else 16          # ~1 GB per 4K Canny call, 0.5 GB Harris: keep 3 GB per frame
+    nf = max(1, args.ref_frames if args.ref_frames > 0 else min(cores, 64, nf_mem))
+    omp = max(1, cores // nf)
+    os.environ["OMP_NUM_THREADS"] = str(omp)                       # read by libgomp when libref_harris.so is loaded below
     from oracle import pyoracle as po
     from image_b200 import synth
-    cores = os.cpu_count() or 1
     if po.lib("oracle") is None:
         po.build(ref=False)
         po._cache.clear()
     kind = "reference" if all(po.have_ref(w) for w in ("harris", "canny", "dlib")) else "port"
     impl = "ref" if kind == "reference" else "oracle"
-    nf = max(1, args.ref_frames if args.ref_frames > 0 else min(cores, 16))
-    rgb = [synth.frame_rgb(2000 + i, NY, NX) for i in range(nf)]
-    grey = [(f.astype(np.uint16).sum(axis=2) // 3).astype(np.uint8) for f in rgb]
+    base = [synth.frame_rgb(2000 + i, NY, NX) for i in range(min(nf, 2))]          # two distinct frames, repeated (as the GPU arm)
+    rgb = [base[i % len(base)] for i in range(nf)]
+    grey = [(f.astype(np.uint16).sum(axis=2) // 3).astype(np.uint8) for f in base]
+    grey = [grey[i % len(base)] for i in range(nf)]
 
     def step():
-        if "harris" in dets:
-            for g in grey:
-                po.harris_detect(g, precision=0, impl=impl, **{k: v for k, v in HARRIS_KW.items()})
         with ThreadPoolExecutor(max_workers=cores) as ex:
             jobs = []
-            if "canny" in dets:
+            if "canny" in dets:                                    # longest jobs first
                 jobs += [ex.submit(po.canny, g, impl=impl, **CANNY_KW) for g in grey]
+            if "harris" in dets:
+                jobs += [ex.submit(po.harris_detect, g, precision=0, impl=impl, **HARRIS_KW) for g in grey]
             if "fhog" in dets:
                 jobs += [ex.submit(po.fhog, f, impl=impl, **FHOG_KW) for f in rgb]
             for j in jobs:
@@ -146,8 +171,8 @@ def run_reference(args, dets):
         "data": "synthetic",
         "config": {"workload": "+".join(dets) + " @3840x2160", "frames_per_step": nf, "detectors": dets},
         "cpu_baseline": {"value": mpix, "unit": "Mpixels/s", "cores": cores, "kind": kind,
-                         "sample": "%d synthetic 4K frame(s) per step, %d steps; Harris OpenMP, Canny/FHOG one frame per core%s"
-                                   % (nf, args.steps, "; Canny FFT through the oracle DFT shim (FFTW3 absent)" if kind == "reference" else "")},
+                         "sample": "%d synthetic 4K frame(s) per step (2 distinct), %d steps; all calls of a step in one %d-thread pool, Harris with %d OpenMP thread(s) per frame%s"
+                                   % (nf, args.steps, cores, omp, "; Canny FFT through the oracle DFT shim (FFTW3 absent)" if kind == "reference" else "")},
         "e2e": {"value": mpix, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -461,6 +486,18 @@ def main():
             cpu = {"value": NX * NY / tot / 1e6, "unit": "Mpixels/s", "cores": os.cpu_count(), "kind": kind,
                    "sample": "1 synthetic 4K frame through %s (Harris OpenMP on all cores; Canny, FHOG single thread as in the reference)" % "+".join(dets),
                    "parts": parts}
+            # all cores busy: the reference arm's own step (independent frames in one thread pool), one step, in a
+            # child process so that its OpenMP team size and memory stay its own
+            try:
+                nfr = max(2, min((os.cpu_count() or 2) // 4, 32))
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                                    "--ref-frames", str(nfr), "--detectors", ",".join(dets)], capture_output=True, text=True, timeout=600)
+                pl = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+                cpu["single_frame_value"] = cpu["value"]
+                cpu["value"] = pl["value"]
+                cpu["sample"] = pl["cpu_baseline"]["sample"] + " | single frame, one call at a time: %.2f Mpixels/s" % cpu["single_frame_value"]
+            except Exception as ex2:
+                cpu["pool_error"] = str(ex2)
         except Exception as ex:
             cpu = {"value": None, "unit": "Mpixels/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %s" % ex}
 
