@@ -7,7 +7,8 @@
 //   fhog_pixel_kernel    one CTA = a 64 x 16 pixel tile (+1 ring, word-aligned staging of the RGB bytes).
 //                        Per pixel: max-length colour channel with the reference's position-dependent
 //                        tie-break (SIMD body vs scalar tail, fhog.h:48-58 / :133-141), LUT snap,
-//                        correctly rounded sqrt.  Writes a magnitude plane and an orientation plane in a
+//                        correctly rounded sqrt.  A thread takes 4 consecutive rows of one column (column-only
+//                        work is formed once).  Writes a magnitude plane and an orientation plane in a
 //                        cell-phase de-interleaved column order, so the next kernel's loads coalesce.
 //   fhog_cell_kernel     ONE thread per histogram cell replays that cell's votes in raster order (the
 //                        order of the reference's sequential `hist += v` statements, fhog.h:879-917,
@@ -72,8 +73,9 @@ __device__ __forceinline__ void snap18(float gx, float gy, int &best_o) {
 // ---- pass 1: per-pixel (orientation bin, gradient magnitude), written in a cell-phase
 // de-interleaved layout  idx(y,x) = y*PW + (x % cell)*NCB + x / cell  so that pass 2 (one thread per
 // cell, consecutive threads = consecutive cells) reads consecutive addresses.
+constexpr int FC_NT = 128;                                 // threads (= histogram cells) per CTA of the cell kernel
 constexpr int FP_TW = 64, FP_TH = 16;
-constexpr int FP_RB = ((FP_TW + 2) * 3 + 3 + 3) & ~3;      // staged bytes per row, word aligned (+ up to 3 lead bytes)
+constexpr int FP_RB = ((FP_TW + 2) * 3 + 3 + 15) & ~15;    // staged bytes per row (208): 16-byte chunks, + up to 3 lead bytes
 
 // 18-way orientation snap for every integer gradient (gx, gy) in [-255, 255]^2, built once per
 // context with the same un-fused float expressions (snap18): lut[(gy+255)*512 + gx+255].
@@ -94,7 +96,23 @@ fhog_pixel_kernel(const unsigned char *__restrict__ frames, float *__restrict__ 
   const int b0 = (x0 - 1) * 3;                      // first byte of the staged row segment
   const int lead = aligned ? (b0 & 3) : 0;          // bytes in front of it when loading whole words
   const int rowlimit = g.cols * 3;
-  if (aligned) {
+  if (aligned == 2) {
+    // rows are multiples of 16 bytes and b0 = 192 * blockIdx.x: 13 aligned 16-byte chunks per row, one per thread
+    if (threadIdx.x < (FP_TH + 2) * (FP_RB / 16)) {
+      const int r = threadIdx.x / (FP_RB / 16), q = threadIdx.x - r * (FP_RB / 16);
+      const int gy = min(y0 - 1 + r, g.rows - 1), gb = b0 + 16 * q;
+      const unsigned char *row = src + (size_t)gy * rowlimit;
+      uint4 v;
+      if (gb + 16 <= rowlimit) v = __ldg(reinterpret_cast<const uint4 *>(row + gb));
+      else {      // chunk crosses the end of the row: words past it are never read by a voter
+        unsigned w[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) w[k] = gb + 4 * k + 4 <= rowlimit ? __ldg(reinterpret_cast<const unsigned *>(row + gb + 4 * k)) : 0u;
+        v = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      reinterpret_cast<uint4 *>(srgb)[r * (FP_RB / 16) + q] = v;
+    }
+  } else if (aligned) {
     const int w0 = (b0 - lead) >> 2;
     for (int i = threadIdx.x; i < (FP_TH + 2) * (FP_RB / 4); i += FH_NT) {
       int r = i / (FP_RB / 4), w = i - r * (FP_RB / 4);
@@ -110,34 +128,90 @@ fhog_pixel_kernel(const unsigned char *__restrict__ frames, float *__restrict__ 
     }
   }
   __syncthreads();
+  // thread = (column c, group of 4 consecutive rows): everything that depends on the column alone -- the
+  // SIMD-body / scalar-tail rule, the de-interleaved output column, the staged byte offset -- is formed once
+  const int c = threadIdx.x & (FP_TW - 1), rg = threadIdx.x >> 6;
+  const int x = x0 + c;
+  if (x >= g.visible_nc) return;
+  const bool simd = x < g.simd_end;
   const size_t plane = (size_t)g.rows * PW;
-  float *vout = vmag + (size_t)blockIdx.z * plane;
-  unsigned char *oout = obin + (size_t)blockIdx.z * plane;
-  for (int i = threadIdx.x; i < FP_TW * FP_TH; i += FH_NT) {
-    const int r = i / FP_TW, c = i - r * FP_TW;
-    const int x = x0 + c, y = y0 + r;
-    if (x >= g.visible_nc || y >= g.visible_nr) continue;
-    const unsigned char *p = srgb + (r + 1) * FP_RB + lead + (c + 1) * 3;
-    const bool simd = x < g.simd_end;
+  const size_t col = (size_t)blockIdx.z * plane + __ldg(colidx + x);
+  const unsigned char *p0 = srgb + lead + (c + 1) * 3 + (4 * rg + 1) * FP_RB;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int y = y0 + 4 * rg + j;
+    if (y >= g.visible_nr) break;
+    const unsigned char *p = p0 + j * FP_RB;
     int bx = 0, by = 0, bl = -1;
 #pragma unroll
     for (int ch = 0; ch < 3; ch++) {
-      int dx = (int)p[3 + ch] - (int)p[-3 + ch];
-      int dy = (int)p[FP_RB + ch] - (int)p[-FP_RB + ch];
-      int l = dx * dx + dy * dy;
-      bool take = (ch == 0) || (simd ? !(bl > l) : (l > bl));
+      const int dx = (int)p[3 + ch] - (int)p[-3 + ch];
+      const int dy = (int)p[FP_RB + ch] - (int)p[-FP_RB + ch];
+      const int l = dx * dx + dy * dy;
+      const bool take = (ch == 0) || (simd ? !(bl > l) : (l > bl));
       if (take) { bx = dx; by = dy; bl = l; }
     }
     const int o = __ldg(lut + ((by + 255) << 9) + (bx + 255));
-    const size_t idx = (size_t)y * PW + __ldg(colidx + x);
-    vout[idx] = __fsqrt_rn((float)bl);
-    oout[idx] = (unsigned char)o;
+    const size_t idx = col + (size_t)y * PW;
+    vmag[idx] = __fsqrt_rn((float)bl);
+    obin[idx] = (unsigned char)o;
+  }
+}
+
+// cell_size == 8 (the default): same arithmetic, thread mapping chosen for the stores.  A tile is 256 x 16
+// pixels; warp w owns the columns of one cell phase (x0 + w, x0 + w + 8, ...), lane l the l-th cell of the tile,
+// so a warp's 32 outputs of a row are 32 CONSECUTIVE entries of the de-interleaved planes: one full 32-byte
+// sector of orientation bytes and four of magnitudes per store instruction (the generic mapping scatters every
+// store over 8 sectors).  A thread walks its column down the 16 rows.
+constexpr int P8_TW = 256, P8_TH = 16;
+constexpr int P8_RB = ((P8_TW + 2) * 3 + 15) & ~15;        // 784 staged bytes per row
+__global__ void __launch_bounds__(256)
+fhog_pixel8_kernel(const unsigned char *__restrict__ frames, float *__restrict__ vmag, unsigned char *__restrict__ obin,
+                   FhogGeom g, const int *__restrict__ colidx, int PW, const unsigned char *__restrict__ lut) {
+  __shared__ __align__(16) unsigned char srgb[(P8_TH + 2) * P8_RB];
+  const int x0 = 1 + blockIdx.x * P8_TW, y0 = 1 + blockIdx.y * P8_TH;
+  const unsigned char *src = frames + (size_t)blockIdx.z * g.rows * g.cols * 3;
+  const int b0 = (x0 - 1) * 3, rowlimit = g.cols * 3;        // b0 = 768 * blockIdx.x: 16-byte aligned, like every row start
+  for (int i = threadIdx.x; i < (P8_TH + 2) * (P8_RB / 16); i += 256) {
+    const int r = i / (P8_RB / 16), q = i - r * (P8_RB / 16);
+    const int gy = min(y0 - 1 + r, g.rows - 1), gb = b0 + 16 * q;
+    const unsigned char *row = src + (size_t)gy * rowlimit;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (gb + 16 <= rowlimit) v = __ldg(reinterpret_cast<const uint4 *>(row + gb));
+    else if (gb < rowlimit) {     // chunk crosses the end of the row: bytes past it are never read by a voter
+      unsigned w[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) w[k] = gb + 4 * k + 4 <= rowlimit ? __ldg(reinterpret_cast<const unsigned *>(row + gb + 4 * k)) : 0u;
+      v = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    reinterpret_cast<uint4 *>(srgb)[i] = v;
+  }
+  __syncthreads();
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const int c = 8 * l + w, x = x0 + c;
+  if (x >= g.visible_nc) return;
+  const bool simd = x < g.simd_end;
+  const size_t plane = (size_t)g.rows * PW;
+  size_t idx = (size_t)blockIdx.z * plane + (size_t)y0 * PW + __ldg(colidx + x);
+  const unsigned char *p = srgb + (c + 1) * 3 + P8_RB;
+  const int nrow = min(P8_TH, g.visible_nr - y0);
+  for (int j = 0; j < nrow; j++, p += P8_RB, idx += PW) {
+    int bx = 0, by = 0, bl = -1;
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) {
+      const int dx = (int)p[3 + ch] - (int)p[-3 + ch];
+      const int dy = (int)p[P8_RB + ch] - (int)p[-P8_RB + ch];
+      const int len = dx * dx + dy * dy;
+      const bool take = (ch == 0) || (simd ? !(bl > len) : (len > bl));
+      if (take) { bx = dx; by = dy; bl = len; }
+    }
+    vmag[idx] = __fsqrt_rn((float)bl);
+    obin[idx] = __ldg(lut + ((by + 255) << 9) + (bx + 255));
   }
 }
 
 // ---- pass 2: one thread per histogram cell replays that cell's votes in raster order into a
 // private shared-memory histogram (bank = thread, conflict-free); bit-identical to the reference.
-constexpr int FC_NT = 128;
 __global__ void __launch_bounds__(FC_NT)
 fhog_cell_kernel(const float *__restrict__ vmag, const unsigned char *__restrict__ obin, float *__restrict__ hist,
                  FhogGeom g, FhogTables tb, const int *__restrict__ colidx, int PW, int KW /* cached x weights per thread */) {
@@ -516,8 +590,13 @@ int fhog_device(b2f_ctx *ctx, const unsigned char *d_frames, int n_frames, const
     int lrc = fhog_ensure_lut(ctx, st);
     if (lrc != B2F_OK) return lrc;
   }
+  if (cell == 8 && g.cols % 16 == 0 && (reinterpret_cast<uintptr_t>(d_frames) & 15) == 0)
+    fhog_pixel8_kernel<<<dim3(ceil_div(std::max(g.visible_nc - 1, 1), P8_TW), ceil_div(std::max(g.visible_nr - 1, 1), P8_TH), n_frames), 256, 0, st>>>(
+        d_frames, vmag, obin, g, d_colidx, PW, (const unsigned char *)ctx->fhog_lut);
+  else
   fhog_pixel_kernel<<<dim3(ceil_div(std::max(g.visible_nc - 1, 1), FP_TW), ceil_div(std::max(g.visible_nr - 1, 1), FP_TH), n_frames), FH_NT, 0, st>>>(
       d_frames, vmag, obin, g, d_colidx, PW, (const unsigned char *)ctx->fhog_lut,
+      (g.cols % 16 == 0 && (reinterpret_cast<uintptr_t>(d_frames) & 15) == 0) ? 2 :
       (g.cols % 4 == 0 && (reinterpret_cast<uintptr_t>(d_frames) & 3) == 0) ? 1 : 0);
   B2F_LAUNCH_CHECK(ctx);
   {
