@@ -108,7 +108,7 @@ def surf_batch(frames, max_points=10000, detection_threshold=30.0, cap=None):
     f = np.ascontiguousarray(frames, dtype=np.uint8)
     n, rows, cols, _ = f.shape
     cap = int(cap or max_points)
-    rec = np.zeros((n, cap, 70), np.float64)
+    rec = np.empty((n, cap, 70), np.float64)       # only the first counts[i] rows of a frame are written and read
     cnt = np.zeros(n, np.int32)
     _lib.check(lib.b2f_surf_batch(_lib.context(), _lib.ptr(f), n, rows, cols, C.c_long(int(max_points)),
                                   float(detection_threshold), cap, _lib.ptr(rec), _lib.ptr(cnt)))
