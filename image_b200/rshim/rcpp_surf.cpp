@@ -1,31 +1,28 @@
-// Drop-in replacement for image.dlib/src/rcpp_surf.cpp (reference :10-54).
+// Replacement body for the export of image.dlib/src/rcpp_surf.cpp (reference :10-54): same exported name,
+// arguments, defaults and returned list; key points and descriptors come from b2f_surf_host.
 #include <Rcpp.h>
 #include <vector>
 #include "b2f_r_context.h"
 
 // [[Rcpp::export]]
-Rcpp::List dlib_surf_points(std::vector<int> x, int rows, int cols,
-                            long max_points = 10000, double detection_threshold = 30.0) {
-  if (x.size() != (size_t)rows * cols * 3) Rcpp::stop("dlib_surf_points: x must hold 3*rows*cols values");
-  std::vector<unsigned char> rgb(x.size());
-  for (size_t i = 0; i < x.size(); i++) rgb[i] = (unsigned char)x[i];
-  b2f_surf_point *sp = nullptr;
-  int n = 0;
-  b2f_r_check(b2f_surf_host(b2f_r_ctx(), rgb.data(), rows, cols, max_points, detection_threshold, &sp, &n));
-  Rcpp::NumericVector ip_center_x(n), ip_center_y(n), ip_angle(n), ip_scale(n), ip_score(n), ip_laplacian(n);
-  Rcpp::NumericMatrix ip_surf(n, 64);
-  for (int i = 0; i < n; i++) {
-    ip_center_x[i] = sp[i].x; ip_center_y[i] = sp[i].y; ip_angle[i] = sp[i].angle;
-    ip_scale[i] = sp[i].scale; ip_score[i] = sp[i].score; ip_laplacian[i] = sp[i].laplacian;
-    for (int j = 0; j < 64; j++) ip_surf(i, j) = sp[i].des[j];
+Rcpp::List dlib_surf_points(std::vector<int> x, int rows, int cols, long max_points = 10000, double detection_threshold = 30.0) {
+  using Rcpp::Named;
+  const std::vector<unsigned char> pixels = b2f_r_rgb_bytes(x, rows, cols, "dlib_surf_points");
+  b2f_surf_point *kp = nullptr;
+  int count = 0;
+  b2f_r_check(b2f_surf_host(b2f_r_ctx(), pixels.data(), rows, cols, max_points, detection_threshold, &kp, &count));
+  // one numeric vector per scalar field, and the descriptors as a count x 64 matrix (column-major, like R)
+  double b2f_surf_point::*const field[6] = {&b2f_surf_point::x, &b2f_surf_point::y, &b2f_surf_point::angle,
+                                            &b2f_surf_point::scale, &b2f_surf_point::score, &b2f_surf_point::laplacian};
+  Rcpp::NumericVector col[6] = {Rcpp::NumericVector(count), Rcpp::NumericVector(count), Rcpp::NumericVector(count),
+                                Rcpp::NumericVector(count), Rcpp::NumericVector(count), Rcpp::NumericVector(count)};
+  Rcpp::NumericMatrix descriptors(count, 64);
+  for (int q = 0; q < count; q++) {
+    for (int f = 0; f < 6; f++) col[f][q] = kp[q].*field[f];
+    for (int d = 0; d < 64; d++) descriptors(q, d) = kp[q].des[d];
   }
-  b2f_free(sp);
-  return Rcpp::List::create(Rcpp::Named("points") = n,
-                            Rcpp::Named("x") = ip_center_x,
-                            Rcpp::Named("y") = ip_center_y,
-                            Rcpp::Named("angle") = ip_angle,
-                            Rcpp::Named("pyramid_scale") = ip_scale,
-                            Rcpp::Named("score") = ip_score,
-                            Rcpp::Named("laplacian") = ip_laplacian,
-                            Rcpp::Named("surf") = ip_surf);
+  b2f_free(kp);
+  return Rcpp::List::create(Named("points") = count, Named("x") = col[0], Named("y") = col[1], Named("angle") = col[2],
+                            Named("pyramid_scale") = col[3], Named("score") = col[4], Named("laplacian") = col[5],
+                            Named("surf") = descriptors);
 }
