@@ -102,6 +102,16 @@ def available_detectors():
 
 
 # ------------------------------------------------------------------------------------------ reference arm
+def _cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.lower().startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def _host_memory_available():
     """Bytes this process may still allocate: MemAvailable, capped by the cgroup limit when there is one."""
     avail = None
@@ -172,7 +182,7 @@ def run_reference(args, dets):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64/f32 (CPU reference)",
         "data": "synthetic",
         "config": {"workload": "+".join(dets) + " @3840x2160", "frames_per_step": nf, "detectors": dets},
-        "cpu_baseline": {"value": mpix, "unit": "Mpixels/s", "cores": cores, "kind": kind,
+        "cpu_baseline": {"value": mpix, "unit": "Mpixels/s", "cores": cores, "cpu_model": _cpu_model(), "omp_num_threads": omp, "kind": kind,
                          "sample": "%d synthetic 4K frame(s) per step (2 distinct), %d steps; all calls of a step in one %d-thread pool, Harris with %d OpenMP thread(s) per frame%s"
                                    % (nf, args.steps, cores, omp, "; Canny FFT through the oracle DFT shim (FFTW3 absent)" if kind == "reference" else "")},
         "e2e": {"value": mpix, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -493,7 +503,7 @@ def main():
             if "fhog" in dets:
                 t0 = time.perf_counter(); po.fhog(f1, impl=impl, **FHOG_KW); parts["fhog_s"] = time.perf_counter() - t0
                 tot += parts["fhog_s"]
-            cpu = {"value": NX * NY / tot / 1e6, "unit": "Mpixels/s", "cores": os.cpu_count(), "kind": kind,
+            cpu = {"value": NX * NY / tot / 1e6, "unit": "Mpixels/s", "cores": os.cpu_count(), "cpu_model": _cpu_model(), "kind": kind,
                    "sample": "1 synthetic 4K frame through %s (Harris OpenMP on all cores; Canny, FHOG single thread as in the reference)" % "+".join(dets),
                    "parts": parts}
             # all cores busy: the reference arm's own step (independent frames in one thread pool), one step, in a
