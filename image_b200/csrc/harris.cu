@@ -378,6 +378,7 @@ nms_bitmask_sep2_kernel(const float *__restrict__ R, unsigned *__restrict__ mask
   const int x0 = blockIdx.x * NMS2_TW, y0 = blockIdx.y * NMS2_TH;
   const float *Rf = R + (size_t)nx * ny * blockIdx.z;
   const int lane = threadIdx.x & 31;
+  float tmax = -INFINITY;
   if ((nx & 3) == 0 && x0 >= NMS2_LP && x0 + NMS2_TW + NMS2_LP <= nx && y0 >= RAD && y0 + NMS2_TH + RAD <= ny) {
     constexpr int NV4 = TH2 * (P / 4), PER = (NV4 + NMS_NT - 1) / NMS_NT;
     const float *org = Rf + (size_t)(y0 - RAD) * nx + (x0 - NMS2_LP);
@@ -385,21 +386,32 @@ nms_bitmask_sep2_kernel(const float *__restrict__ R, unsigned *__restrict__ mask
 #pragma unroll
     for (int k = 0; k < PER; k++) {
       const int u = threadIdx.x + k * NMS_NT, r = u / (P / 4), c4 = u - r * (P / 4);
-      if (u < NV4) v[k] = __ldg(reinterpret_cast<const float4 *>(org + (size_t)r * nx + 4 * c4));
+      v[k] = u < NV4 ? __ldg(reinterpret_cast<const float4 *>(org + (size_t)r * nx + 4 * c4)) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
     }
 #pragma unroll
     for (int k = 0; k < PER; k++) {
       const int u = threadIdx.x + k * NMS_NT;
       if (u < NV4) reinterpret_cast<float4 *>(tile)[u] = v[k];
+      tmax = fmaxf(tmax, fmaxf(fmaxf(v[k].x, v[k].y), fmaxf(v[k].z, v[k].w)));
     }
   } else {
     for (int u = threadIdx.x; u < TH2 * P; u += NMS_NT) {
       const int r = u / P, c = u - r * P;
       const int gy = y0 - RAD + r, gx = x0 - NMS2_LP + c;
-      tile[u] = (gy >= 0 && gy < ny && gx >= 0 && gx < nx) ? __ldg(Rf + (size_t)gy * nx + gx) : -INFINITY;
+      const float t = (gy >= 0 && gy < ny && gx >= 0 && gx < nx) ? __ldg(Rf + (size_t)gy * nx + gx) : -INFINITY;
+      tile[u] = t;
+      tmax = fmaxf(tmax, t);
     }
   }
-  __syncthreads();
+  // A candidate needs R >= Th (harris.cpp:176): a tile none of whose values (halo included) reaches the threshold
+  // has an all-zero mask.  On natural frames that is most tiles; the barrier doubles as the vote.  (NaN never votes,
+  // and a NaN candidate fails `val >= window max` below as well.)
+  if (!__syncthreads_or(!(tmax < Th))) {
+    const int row = threadIdx.x >> 2, wq = threadIdx.x & 3;      // 32 rows x 4 mask words
+    const int gy = y0 + row, word = (x0 >> 5) + wq;
+    if (threadIdx.x < NMS2_TH * 4 && gy < ny && word < words_per_row) mask[((size_t)blockIdx.z * ny + gy) * words_per_row + word] = 0u;
+    return;
+  }
   // row pass: an item = 4 consecutive outputs of one tile row (output col j <-> tile cols j+8-RAD .. j+8+RAD)
   for (int it = threadIdx.x; it < TH2 * (NMS2_TW / 4); it += NMS_NT) {
     const int r = it >> 5, g = it & 31;
