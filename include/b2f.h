@@ -105,7 +105,9 @@ int b2f_canny_dev(b2f_ctx *ctx, const uint8_t *d_frames, int n_frames, int nx, i
  * dlib_fhog: rgb = rows*cols*3 interleaved u8 (x[3*c + 3*cols*r + ch], rcpp_fhog.cpp:19-23).
  * Output `hog` is [hog_nr][hog_nc][31] floats (row, col, feature) — the element order of
  * dlib's array2d<matrix<float,31,1>>; the Rcpp shim transposes to R's y + nr*(x + nc*feat).
- * b2f_fhog_size gives the output shape for given inputs (fhog.h:790-813, init_hog :448-471). */
+ * b2f_fhog_size gives the output shape for given inputs (fhog.h:790-813, init_hog :448-471).
+ * Every cell_size >= 1 is served: cell_size == 1 takes dlib's separate routine (fhog.h:495-694), like the
+ * reference's extract_fhog_features does (fhog.h:1099-1113). */
 int b2f_fhog_size(int rows, int cols, int cell_size, int filter_rows_padding, int filter_cols_padding,
                   int *hog_nr, int *hog_nc);
 int b2f_fhog_host(b2f_ctx *ctx, const uint8_t *rgb, int rows, int cols, int cell_size,
