@@ -106,3 +106,16 @@ def test_tile_components_equal_8_connected_labelling(seed):
     iso = np.zeros((32, 32), bool); iso[::2, ::2] = True    # the extreme case: 256 isolated pixels
     roots, _ = label_tile(iso, iso)
     assert len(set(roots[iso].tolist())) == 256
+
+
+def test_class_bytes_to_mask_bits():
+    """One multiply turns the per-byte flags (bits 0, 8, 16, 24) of a word of class bytes into 4 adjacent bits."""
+    import itertools
+    for b in itertools.product((0, 1, 2), repeat=4):
+        w = b[0] | b[1] << 8 | b[2] << 16 | b[3] << 24
+        s1 = (w >> 1) & 0x01010101
+        e1 = (w & 0x01010101) | s1
+        edge = ((e1 * 0x01020408) & M) >> 24
+        strong = ((s1 * 0x01020408) & M) >> 24
+        assert edge == sum((1 << k) for k in range(4) if b[k] != 0)
+        assert strong == sum((1 << k) for k in range(4) if b[k] == 2)
