@@ -68,6 +68,9 @@ def load():
     lib.b2f_harris_host.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(HarrisParams), C.POINTER(fp), C.POINTER(fp), C.POINTER(fp), ip]
     lib.b2f_harris_batch_u8.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(HarrisParams), C.c_int, vp, vp, vp, vp]
     lib.b2f_harris_response_dev.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(HarrisParams), vp, vp]
+    lib.b2f_harris_corners_dev.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(HarrisParams), C.c_int, vp, vp, vp, vp, vp]
+    lib.b2f_harris_cert_stats.argtypes = [vp, C.POINTER(C.c_ulonglong)]
+    lib.b2f_harris_response_eps_dev.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(HarrisParams), vp, vp, vp]
     lib.b2f_harris_nms_dev.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, vp, vp, vp, vp]
     for name, args in [
         ("b2f_canny_host", [vp, vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, vp, ip]),
@@ -142,7 +145,8 @@ def ptr(a):
 EXPORTS = [
     "b2f_init", "b2f_shutdown", "b2f_last_error", "b2f_version", "b2f_device_count", "b2f_free", "b2f_stream",
     "b2f_launch_count", "b2f_set_chunk_bytes", "b2f_harris_default_params", "b2f_harris_host", "b2f_harris_batch_u8",
-    "b2f_harris_response_dev", "b2f_harris_nms_dev", "b2f_canny_host", "b2f_canny_batch", "b2f_canny_dev",
+    "b2f_harris_response_dev", "b2f_harris_nms_dev", "b2f_harris_corners_dev", "b2f_harris_cert_stats",
+    "b2f_harris_response_eps_dev", "b2f_canny_host", "b2f_canny_batch", "b2f_canny_dev",
     "b2f_fhog_size", "b2f_fhog_host", "b2f_fhog_batch", "b2f_fhog_dev", "b2f_surf_host", "b2f_surf_batch",
     "b2f_otsu_host", "b2f_otsu_batch_u8", "b2f_otsu_dev",
 ]

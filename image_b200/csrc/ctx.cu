@@ -121,6 +121,7 @@ void b2f_shutdown(b2f_ctx *c) {
   cudaStreamSynchronize(c->stream);
   if (c->arena.base) cudaFree(c->arena.base);
   if (c->pinned) cudaFreeHost(c->pinned);
+  if (c->harris_stats) cudaFree(c->harris_stats);
   if (c->fhog_lut) cudaFree(c->fhog_lut);
   if (c->fhog_tab) cudaFree(c->fhog_tab);
   if (c->s_in) { cudaStreamSynchronize(c->s_in); cudaStreamDestroy(c->s_in); }

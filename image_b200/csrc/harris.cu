@@ -1,11 +1,14 @@
 // harris.cu — host orchestration + remaining kernels of the Harris corner path
 // (image.CornerDetectionHarris).
 //
-//   response map    harris_fused_kernel (harris_kernels.cuh) or the bit-exact staged kernels here
+//   response map    harris_fused3_kernel (harris_kernels3.cuh) or the bit-exact staged kernels here
 //   NMS             nms_bitmask_kernel: window predicate of harris.cpp:141-255 -> 1 bit / pixel
 //   compaction      row_count / row_scan / emit kernels -> corners in raster order (harris.cpp:250-252)
-//   selection, sub-pixel, scale check (H7, <1 % of the time): host code in harris_host.cpp
-#include "harris_kernels2.cuh"
+//   certification   nms_tolerant_kernel (candidates of the fp32 map with its error bound) ->
+//                   harris_exact_patch_kernel (reference arithmetic on a patch) -> compact_kept_kernel:
+//                   the fast path's key-point lists and strengths are the reference's, bit for bit
+//   selection, sub-pixel, scale check (H7, <1 % of the time): harris_api.cu
+#include "harris_kernels3.cuh"
 #include "harris_host.h"
 #include <cmath>
 #include <algorithm>
@@ -149,6 +152,7 @@ nms_bitmask_kernel(const float *__restrict__ R, unsigned *__restrict__ mask, int
     bool ok = gx >= radius && gx < nx - radius && gy >= radius && gy < ny - radius && !(v < Th);
     if (ok) {   // cheap 3x3 pre-test, then the full window
       ok = v > c[-P - 1] && v > c[-P] && v > c[-P + 1] && v > c[1] && v >= c[-1] && v >= c[P - 1] && v >= c[P] && v >= c[P + 1];
+      if (gx == radius && c[-1] >= v) ok = false;   // the row scan starts by walking off the downhill (harris.cpp:173)
     }
     if (ok) {
       for (int dy = -radius; dy <= radius && ok; dy++) {
@@ -242,6 +246,7 @@ nms_bitmask_sep_kernel(const float *__restrict__ R, unsigned *__restrict__ mask,
       const float *c = tile + (row + RAD) * P + col + RAD;
       const float val = *c;
       bool ok = gx >= RAD && gx < nx - RAD && gy >= RAD && gy < ny - RAD && !(val < Th) && val >= m;
+      if (ok && gx == RAD && c[-1] >= val) ok = false;   // harris.cpp:173
       if (ok) {       // val equals its window maximum: apply the reference's tie rules exactly
         for (int dy = -RAD; dy <= RAD && ok; dy++) {
           const float *q = c + dy * P;
@@ -449,6 +454,7 @@ nms_bitmask_sep2_kernel(const float *__restrict__ R, unsigned *__restrict__ mask
       const float *c = c0 + j * P;
       const float val = *c;
       bool ok = colok && gy >= RAD && gy < ny - RAD && !(val < Th) && val >= m[j];
+      if (ok && gx == RAD && c[-1] >= val) ok = false;   // harris.cpp:173
       if (ok) {       // val equals its window maximum: apply the reference's tie rules exactly
         for (int dy = -RAD; dy <= RAD && ok; dy++) {
           const float *q = c + dy * P;
@@ -467,67 +473,340 @@ nms_bitmask_sep2_kernel(const float *__restrict__ R, unsigned *__restrict__ mask
 }
 
 // ------------------------------------------------------------------------------------------
+// certified key points on the fast path
+//   The fused kernel's R is fp32-accumulated; with it comes, per 8x8 block, a bound eps >= |R - R_ref|
+//   (harris_eps).  nms_tolerant_kernel keeps every pixel that COULD satisfy the reference's predicate
+//   (harris.cpp:161-243) for some R_ref within the bounds, and marks those for which it certainly does.
+//   harris_exact_patch_kernel then repeats the reference's arithmetic (double accumulation in its order,
+//   gaussian.cpp:353-358; float products; float measure) on a patch around each candidate: a 1x1 / 3x3 patch
+//   for certain ones (their strength, and the 3x3 of the sub-pixel fit), the whole (2r+1)^2 window for the
+//   undecided ones, whose predicate is then evaluated on exact values.  compact_kept_kernel keeps the raster order.
+// ------------------------------------------------------------------------------------------
+constexpr int TN_TW = 128, TN_TH = 32, TN_LP = 8, TN_P = TN_TW + 2 * TN_LP, TN_NT = 256;
+constexpr int TN_EBW = TN_P / 8 + 1, TN_EBH = (TN_TH + 2 * 5) / 8 + 2;    // eps blocks a tile (+halo) can touch
+
+template <int RAD>
+__global__ void __launch_bounds__(TN_NT)
+nms_tolerant_kernel(const float *__restrict__ R, const unsigned *__restrict__ eps_blk, unsigned *__restrict__ cand,
+                    unsigned *__restrict__ cert, int nx, int ny, int words_per_row, float Th) {
+  static_assert(RAD >= 1 && RAD <= 5, "radius range of the padded tile");
+  constexpr int TH2 = TN_TH + 2 * RAD, P = TN_P;
+  __shared__ __align__(16) float tile[TH2 * P];                 // L = R - eps rounded down (lower bound of R_ref); -inf outside
+  __shared__ __align__(16) float rmax[TH2 * TN_TW];
+  __shared__ float epsb[TN_EBH * TN_EBW];
+  const int x0 = blockIdx.x * TN_TW, y0 = blockIdx.y * TN_TH;
+  const int ebx = (nx + 7) >> 3, eby = (ny + 7) >> 3;
+  const float *Rf = R + (size_t)nx * ny * blockIdx.z;
+  const float *Ef = reinterpret_cast<const float *>(eps_blk) + (size_t)ebx * eby * blockIdx.z;
+  const int bx0 = max(x0 - TN_LP, 0) >> 3, by0 = max(y0 - RAD, 0) >> 3;
+  for (int u = threadIdx.x; u < TN_EBH * TN_EBW; u += TN_NT) {
+    const int br = u / TN_EBW, bc = u - br * TN_EBW;
+    epsb[u] = (by0 + br < eby && bx0 + bc < ebx) ? Ef[(size_t)(by0 + br) * ebx + bx0 + bc] : 0.f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  float umax = -INFINITY;                                      // largest upper bound in the tile
+  for (int u = threadIdx.x; u < TH2 * P; u += TN_NT) {
+    const int r = u / P, c = u - r * P;
+    const int gy = y0 - RAD + r, gx = x0 - TN_LP + c;
+    float L = -INFINITY;
+    if (gy >= 0 && gy < ny && gx >= 0 && gx < nx) {
+      const float v = __ldg(Rf + (size_t)gy * nx + gx);
+      const float e = epsb[((gy >> 3) - by0) * TN_EBW + ((gx >> 3) - bx0)];
+      L = __fsub_rd(v, e);
+      umax = fmaxf(umax, __fadd_ru(v, e));
+    }
+    tile[u] = L;
+  }
+  // A corner needs R_ref >= Th: a tile none of whose upper bounds reaches the threshold has empty masks.
+  if (!__syncthreads_or(!(umax < Th))) {
+    const int row = threadIdx.x >> 2, wq = threadIdx.x & 3;      // 32 rows x 4 mask words
+    const int gy = y0 + row, word = (x0 >> 5) + wq;
+    if (threadIdx.x < TN_TH * 4 && gy < ny && word < words_per_row) {
+      const size_t o = ((size_t)blockIdx.z * ny + gy) * words_per_row + word;
+      cand[o] = 0u; cert[o] = 0u;
+    }
+    return;
+  }
+  // row pass of the separable window maximum of L
+  for (int it = threadIdx.x; it < TH2 * (TN_TW / 4); it += TN_NT) {
+    const int r = it >> 5, g = it & 31;
+    const float4 *p = reinterpret_cast<const float4 *>(tile + r * P + 4 * g);
+    float v[20];
+#pragma unroll
+    for (int q = 0; q < 5; q++) { const float4 t = p[q]; v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w; }
+    constexpr int O = TN_LP - RAD;
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      float m = v[O + j];
+#pragma unroll
+      for (int q = 1; q <= 2 * RAD; q++) m = fmaxf(m, v[O + j + q]);
+      o[j] = m;
+    }
+    reinterpret_cast<float4 *>(rmax + r * TN_TW)[g] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+  __syncthreads();
+  // column pass + classification: thread = (column, half of the tile rows); a warp = 32 consecutive columns = one mask word
+  {
+    const int col = threadIdx.x & (TN_TW - 1), rg = threadIdx.x >> 7;
+    constexpr int NR = TN_TH / 2;
+    const int gx = x0 + col;
+    const bool colok = gx >= RAD && gx < nx - RAD;
+    const int word = (x0 >> 5) + (col >> 5);
+    float win[2 * RAD + 1];
+#pragma unroll
+    for (int q = 0; q < 2 * RAD; q++) win[q + 1] = rmax[(rg * NR + q) * TN_TW + col];
+#pragma unroll 1
+    for (int j = 0; j < NR; j++) {
+#pragma unroll
+      for (int q = 0; q < 2 * RAD; q++) win[q] = win[q + 1];
+      win[2 * RAD] = rmax[(rg * NR + j + 2 * RAD) * TN_TW + col];
+      float m = win[0];
+#pragma unroll
+      for (int q = 1; q <= 2 * RAD; q++) m = fmaxf(m, win[q]);
+      const int gy = y0 + rg * NR + j;
+      bool is_cand = false, is_cert = false;
+      if (colok && gy >= RAD && gy < ny - RAD) {
+        const float e = epsb[((gy >> 3) - by0) * TN_EBW + ((gx >> 3) - bx0)];
+        const float Lp = tile[(rg * NR + j + RAD) * P + col + TN_LP];
+        const float Up = fmaf(2.5f, e, Lp);                    // >= R + eps (eps >= 4 ulp(R): harris_eps carries R's own rounding)
+        if (Up >= Th && Up >= m) {
+          // rare: decide precisely on the window, in double (sums of two floats are exact there)
+          const double rp = (double)Rf[(size_t)gy * nx + gx];
+          const double up = rp + (double)e, lp = rp - (double)e;
+          is_cand = up >= (double)Th;
+          is_cert = lp >= (double)Th;
+          for (int dy = -RAD; dy <= RAD && is_cand; dy++)
+            for (int dx = -RAD; dx <= RAD; dx++) {
+              if (dx == 0 && dy == 0) continue;
+              const int qy = gy + dy, qx = gx + dx;
+              const double rq = (double)Rf[(size_t)qy * nx + qx];
+              const double eq = (double)Ef[(size_t)(qy >> 3) * ebx + (qx >> 3)];
+              if (rq - eq > up) { is_cand = false; break; }     // q certainly larger: p cannot be a corner
+              if (!(rq + eq < lp)) is_cert = false;            // q could be as large as p: undecided
+            }
+          is_cert = is_cert && is_cand;
+        }
+      }
+      const unsigned bc = __ballot_sync(0xffffffffu, is_cand), bt = __ballot_sync(0xffffffffu, is_cert);
+      if (lane == 0 && gy < ny && word < words_per_row) {
+        const size_t o = ((size_t)blockIdx.z * ny + gy) * words_per_row + word;
+        cand[o] = bc; cert[o] = bt;
+      }
+    }
+  }
+}
+
+// one warp per row: expand the candidate mask into (y*nx+x, certain?) records at the scanned offsets
+__global__ void emit_candidates_kernel(const unsigned *__restrict__ cand, const unsigned *__restrict__ cert,
+                                       const int *__restrict__ row_off, int *__restrict__ xy, unsigned char *__restrict__ flag,
+                                       int nx, int ny, int words_per_row, int cap) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31, f = blockIdx.y;
+  if (row >= ny) return;
+  const unsigned *m = cand + ((size_t)f * ny + row) * words_per_row;
+  const unsigned *mc = cert + ((size_t)f * ny + row) * words_per_row;
+  int base = row_off[(size_t)f * ny + row];
+  for (int w0 = 0; w0 < words_per_row; w0 += 32) {
+    int w = w0 + lane;
+    unsigned bits = w < words_per_row ? m[w] : 0u;
+    unsigned cbits = w < words_per_row ? mc[w] : 0u;
+    int c = __popc(bits), incl = c;
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    int pos = base + incl - c;
+    while (bits) {
+      int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      if (pos < cap) {
+        xy[(size_t)f * cap + pos] = row * nx + w * 32 + b;
+        flag[(size_t)f * cap + pos] = (cbits >> b) & 1u;
+      }
+      pos++;
+    }
+    base += __shfl_sync(0xffffffffu, incl, 31);
+  }
+}
+
+// ---- exact patch -------------------------------------------------------------------------------
+// Dimensions for the largest case (window radius 5, sigma_i taps 8, sigma_d taps 4).
+constexpr int XP_NT = 128;
+constexpr int XP_MAXM = 5, XP_MAXRI = 7, XP_MAXRD = 3;
+constexpr int XP_PW = 2 * XP_MAXM + 1 + 2 * XP_MAXRI;          // 25 virtual product positions per axis
+constexpr int XP_ISW = XP_PW + 2, XP_INW = XP_ISW + 2 * XP_MAXRD;   // 27, 33
+
+struct PatchStats { unsigned long long candidates, undecided, violations, kept; };
+
+template <bool U8>
+__global__ void __launch_bounds__(XP_NT)
+harris_exact_patch_kernel(const void *__restrict__ frames, const float *__restrict__ Rfused, const unsigned *__restrict__ eps_blk,
+                          const int *__restrict__ cand_xy, const unsigned char *__restrict__ cand_flag,
+                          const int *__restrict__ cand_cnt, int cap, float *__restrict__ strength, unsigned char *__restrict__ keep,
+                          float *__restrict__ M9, PatchStats *__restrict__ stats, int nx, int ny,
+                          const __grid_constant__ ExactTaps td, const __grid_constant__ ExactTaps ti,
+                          float k, int measure, int grad, float Th, int radius) {
+  __shared__ float sI[XP_INW * XP_INW], sT[XP_INW * XP_ISW], sIs[XP_ISW * XP_ISW];
+  __shared__ float sP[3][XP_PW * XP_PW], sA[3][XP_PW * (2 * XP_MAXM + 1)], sO[(2 * XP_MAXM + 1) * (2 * XP_MAXM + 1)];
+  const int f = blockIdx.y, tid = threadIdx.x;
+  const int n = min(cand_cnt[f], cap);
+  const int RD = td.size - 1, RI = ti.size - 1;
+  const size_t plane = (size_t)nx * ny;
+  for (int ci = blockIdx.x; ci < n; ci += gridDim.x) {
+    const int p = cand_xy[(size_t)f * cap + ci];
+    const bool certain = cand_flag[(size_t)f * cap + ci] != 0;
+    const int x = p % nx, y = p / nx;
+    const int m = certain ? (M9 ? 1 : 0) : radius;
+    const int W = 2 * m + 1, PW = W + 2 * RI;
+    // real coordinate ranges (every reflected / replicated coordinate falls inside them)
+    const int ix0 = max(0, x - m - RI - 1), ix1 = min(nx - 1, x + m + RI + 1), isw = ix1 - ix0 + 1;
+    const int iy0 = max(0, y - m - RI - 1), iy1 = min(ny - 1, y + m + RI + 1), ish = iy1 - iy0 + 1;
+    const int cx0 = max(0, ix0 - RD), cx1 = min(nx - 1, ix1 + RD), inw = cx1 - cx0 + 1;
+    const int cy0 = max(0, iy0 - RD), cy1 = min(ny - 1, iy1 + RD), inh = cy1 - cy0 + 1;
+    __syncthreads();                                           // previous candidate's buffers are free
+    for (int i = tid; i < inh * inw; i += XP_NT) {
+      const int r = i / inw, c = i - r * inw;
+      const size_t g = (size_t)f * plane + (size_t)(cy0 + r) * nx + cx0 + c;
+      sI[i] = U8 ? (float)static_cast<const unsigned char *>(frames)[g] : static_cast<const float *>(frames)[g];
+    }
+    __syncthreads();
+    // row pass of discrete_gaussian at sigma_d (gaussian.cpp:332-361): rows cy0..cy1, columns ix0..ix1
+    for (int i = tid; i < inh * isw; i += XP_NT) {
+      const int r = i / isw, c = i - r * isw, gx = ix0 + c;
+      const float *row = sI + r * inw - cx0;
+      double sum = __dmul_rn(td.B[0], (double)row[gx]);
+      for (int j = 1; j <= RD; j++)
+        sum = __dadd_rn(sum, __dmul_rn(td.B[j], __dadd_rn((double)row[pad_index(gx - j, nx)], (double)row[pad_index(gx + j, nx)])));
+      sT[i] = __double2float_rn(sum);
+    }
+    __syncthreads();
+    // column pass (gaussian.cpp:363-392): rows iy0..iy1
+    for (int i = tid; i < ish * isw; i += XP_NT) {
+      const int r = i / isw, c = i - r * isw, gy = iy0 + r;
+      const float *col = sT + c - cy0 * isw;
+      double sum = __dmul_rn(td.B[0], (double)col[gy * isw]);
+      for (int j = 1; j <= RD; j++)
+        sum = __dadd_rn(sum, __dmul_rn(td.B[j], __dadd_rn((double)col[pad_index(gy - j, ny) * isw], (double)col[pad_index(gy + j, ny) * isw])));
+      sIs[i] = __double2float_rn(sum);
+    }
+    __syncthreads();
+    // gradient (gradient.cpp:17-128) and products (harris.cpp:57-62) at the virtual positions of the sigma_i blur:
+    // reflect padding of the product planes, then the replicate rule of the gradient
+    for (int i = tid; i < PW * PW; i += XP_NT) {
+      const int r = i / PW, c = i - r * PW;
+      const int px = min(max(pad_index(x - m - RI + c, nx), 1), nx - 2), py = min(max(pad_index(y - m - RI + r, ny), 1), ny - 2);
+      const float *I = sIs + (py - iy0) * isw + (px - ix0);
+      float gx, gy;
+      if (grad == 1) {
+        float hx = __fsub_rn(I[1], I[-1]);
+        float dx = __fsub_rn(__fsub_rn(__fadd_rn(I[-isw + 1], I[isw + 1]), I[-isw - 1]), I[isw - 1]);
+        gx = __double2float_rn(__dadd_rn(__dmul_rn(0.25, (double)hx), __dmul_rn(0.125, (double)dx)));
+        float hy = __fsub_rn(I[isw], I[-isw]);
+        float dy = __fsub_rn(__fsub_rn(__fadd_rn(I[isw + 1], I[isw - 1]), I[-isw + 1]), I[-isw - 1]);
+        gy = __double2float_rn(__dadd_rn(__dmul_rn(0.25, (double)hy), __dmul_rn(0.125, (double)dy)));
+      } else {
+        gx = __fmul_rn(0.5f, __fsub_rn(I[1], I[-1]));
+        gy = __fmul_rn(0.5f, __fsub_rn(I[isw], I[-isw]));
+      }
+      sP[0][i] = __fmul_rn(gx, gx); sP[1][i] = __fmul_rn(gx, gy); sP[2][i] = __fmul_rn(gy, gy);
+    }
+    __syncthreads();
+    // sigma_i row pass on the virtual arrays: all PW rows, the W patch columns
+    for (int i = tid; i < 3 * PW * W; i += XP_NT) {
+      const int pl = i / (PW * W), rr = i - pl * (PW * W), r = rr / W, c = rr - r * W;
+      const float *row = sP[pl] + r * PW + c + RI;
+      double sum = __dmul_rn(ti.B[0], (double)row[0]);
+      for (int j = 1; j <= RI; j++) sum = __dadd_rn(sum, __dmul_rn(ti.B[j], __dadd_rn((double)row[-j], (double)row[j])));
+      sA[pl][r * W + c] = __double2float_rn(sum);
+    }
+    __syncthreads();
+    // sigma_i column pass + corner measure (harris.cpp:100-129)
+    for (int i = tid; i < W * W; i += XP_NT) {
+      const int r = i / W, c = i - r * W;
+      float v[3];
+      for (int pl = 0; pl < 3; pl++) {
+        const float *col = sA[pl] + (r + RI) * W + c;
+        double sum = __dmul_rn(ti.B[0], (double)col[0]);
+        for (int j = 1; j <= RI; j++) sum = __dadd_rn(sum, __dmul_rn(ti.B[j], __dadd_rn((double)col[-j * W], (double)col[j * W])));
+        v[pl] = __double2float_rn(sum);
+      }
+      sO[i] = corner_measure(v[0], v[1], v[2], k, measure);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const float val = sO[m * W + m];
+      bool ok = true;
+      if (!certain) {                                          // the reference's predicate on exact values (harris.cpp:161-243)
+        ok = !(val < Th);
+        for (int dy = -m; dy <= m && ok; dy++)
+          for (int dx = -m; dx <= m && ok; dx++) {
+            const float q = sO[(m + dy) * W + m + dx];
+            if (dy < 0) ok = val > q;
+            else if (dy > 0) ok = val >= q;
+            else if (dx < 0) ok = val >= q;
+            else if (dx > 0) ok = val > q;
+          }
+        if (ok && x == radius && sO[m * W + m - 1] >= val) ok = false;   // harris.cpp:173
+      }
+      const size_t o = (size_t)f * cap + ci;
+      strength[o] = val;
+      keep[o] = ok ? 1 : 0;
+      if (M9 && m >= 1)
+        for (int dy = -1; dy <= 1; dy++)
+          for (int dx = -1; dx <= 1; dx++) M9[o * 9 + (dy + 1) * 3 + dx + 1] = sO[(m + dy) * W + m + dx];
+      // the bound the decision relied on must hold: counted, and asserted == 0 by the tests
+      const float e = reinterpret_cast<const float *>(eps_blk)[((size_t)f * ((ny + 7) >> 3) + (y >> 3)) * ((nx + 7) >> 3) + (x >> 3)];
+      const float rf = Rfused[(size_t)f * plane + p];
+      if (!(fabs((double)rf - (double)val) <= (double)e)) atomicAdd(&stats->violations, 1ull);
+      if (!certain) atomicAdd(&stats->undecided, 1ull);
+      if (ok) atomicAdd(&stats->kept, 1ull);
+      if (ci == 0) atomicAdd(&stats->candidates, (unsigned long long)n);
+    }
+  }
+}
+
+// one CTA per frame: stable compaction of the kept candidates (raster order of harris.cpp:250-252)
+__global__ void __launch_bounds__(1024)
+compact_kept_kernel(const int *__restrict__ cand_xy, const unsigned char *__restrict__ keep, const float *__restrict__ cand_s,
+                    const float *__restrict__ cand_M9, const int *__restrict__ cand_cnt, int cand_cap,
+                    int *__restrict__ xy, float *__restrict__ strength, float *__restrict__ M9, int *__restrict__ counts, int cap) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry;
+  const int f = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = min(cand_cnt[f], cand_cap);
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    const size_t ci = (size_t)f * cand_cap + i;
+    const int kflag = (i < n && keep[ci]) ? 1 : 0;
+    int incl = kflag;
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int t = warp_tot[lane], ti = t;
+      for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, ti, o); if (lane >= o) ti += u; }
+      warp_tot[lane] = ti - t;
+    }
+    __syncthreads();
+    const int pos = carry + warp_tot[warp] + incl - kflag;
+    if (kflag && pos < cap) {
+      const size_t o = (size_t)f * cap + pos;
+      xy[o] = cand_xy[ci];
+      strength[o] = cand_s[ci];
+      if (M9) for (int q = 0; q < 9; q++) M9[o * 9 + q] = cand_M9[ci * 9 + q];
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = pos + kflag;
+    __syncthreads();
+  }
+  // more candidates than record slots: the list is incomplete, say so (callers fall back or report B2F_ECAP)
+  if (threadIdx.x == 0) counts[f] = cand_cnt[f] > cand_cap ? -1 : carry;
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-static int taps_double(float sigma, double *B) {     // gaussian.cpp:306-329
-  int size = (int)(3 * sigma) + 1;
-  if (size > HARRIS_MAX_TAPS) return -1;
-  float den_f = 2 * sigma * sigma;
-  double den = den_f, s = sigma;
-  for (int i = 0; i < size; i++) B[i] = 1 / (s * sqrt(2.0 * 3.1415926)) * exp(-i * i / den);
-  double norm = 0;
-  for (int i = 0; i < size; i++) norm += B[i];
-  norm *= 2;
-  norm -= B[0];
-  for (int i = 0; i < size; i++) B[i] /= norm;
-  return size;
-}
-
-template <int RD, int RI, bool U8, int GRAD>
-static int launch_fused_t(b2f_ctx *ctx, const void *d_frames, int n_frames, int nx, int ny, float *d_R,
-                          const HarrisConsts &kc, cudaStream_t st) {
-  using C = FusedCfg<RD, RI>;
-  using C2 = Fused2Cfg<RD, RI>;
-  auto kern = harris_fused_kernel<RD, RI, U8, GRAD>;
-  auto kern2 = harris_fused2_kernel<RD, RI, U8, GRAD>;
-  static bool configured = false;   // per instantiation
-  if (!configured) {
-    B2F_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-    B2F_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2::SMEM));
-    configured = true;
-  }
-  static const bool force_v1 = getenv("B2F_HARRIS_V1") != nullptr;
-  dim3 grid(ceil_div(nx, C::TW), ceil_div(ny, C::TH), n_frames);
-  // the packed kernel needs 4-pixel aligned rows; it takes the interior tiles, v1 the border ring
-  const bool v2 = !force_v1 && (nx % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_frames) & 15) == 0) &&
-                  ((reinterpret_cast<uintptr_t>(d_R) & 7) == 0) && nx >= 64 + 24 && ny >= 64 + 24;
-  if (v2) {
-    kern2<<<grid, C2::NT, C2::SMEM, st>>>(d_frames, d_R, nx, ny, kc);
-    B2F_LAUNCH_CHECK(ctx);
-  }
-  kern<<<grid, C::NT, C::SMEM, st>>>(d_frames, d_R, nx, ny, kc, v2 ? 1 : 0);
-  B2F_LAUNCH_CHECK(ctx);
-  return B2F_OK;
-}
-
-template <int RD, int RI>
-static int launch_fused(b2f_ctx *ctx, const void *d_frames, bool u8, int grad, int n_frames, int nx, int ny,
-                        float *d_R, const HarrisConsts &kc, cudaStream_t st) {
-  if (u8) return grad ? launch_fused_t<RD, RI, true, 1>(ctx, d_frames, n_frames, nx, ny, d_R, kc, st)
-                      : launch_fused_t<RD, RI, true, 0>(ctx, d_frames, n_frames, nx, ny, d_R, kc, st);
-  return grad ? launch_fused_t<RD, RI, false, 1>(ctx, d_frames, n_frames, nx, ny, d_R, kc, st)
-              : launch_fused_t<RD, RI, false, 0>(ctx, d_frames, n_frames, nx, ny, d_R, kc, st);
-}
-
-bool harris_fused_supported(int nx, int ny, float sigma_d, float sigma_i, int gaussian) {
-  if (gaussian != 0) return false;
-  if (sigma_d <= 0 || sigma_i <= 0) return false;
-  int rd = (int)(3 * sigma_d), ri = (int)(3 * sigma_i);
-  if (!(rd == 3 && (ri == 7 || ri == 3))) return false;
-  // frames must be large enough that every reflection stays inside its own tile window
-  return nx >= 32 && ny >= 32 && (long long)nx * ny < (1ll << 31);
-}
-
 // exact staged path: d_I (float planes) is blurred IN PLACE like harris.cpp:511, R written to d_R.
 // Scratch: 4 float planes per frame (+ SII line buffers) from the arena.
 static int response_exact(b2f_ctx *ctx, float *d_I, int n_frames, int nx, int ny, const b2f_harris_params *p,
@@ -550,7 +829,7 @@ static int response_exact(b2f_ctx *ctx, float *d_I, int n_frames, int nx, int ny
     if (type == 0) {
       if (sigma <= 0) return B2F_OK;                               // copy of itself
       ExactTaps tp;
-      tp.size = taps_double(sigma, tp.B);
+      tp.size = harris_taps_double(sigma, tp.B);
       if (tp.size < 0) { set_error("harris: sigma %.3f needs more than %d taps", sigma, HARRIS_MAX_TAPS); return B2F_EUNSUP; }
       if (tp.size > nx) return B2F_OK;                             // gaussian.cpp:312 early-out
       if (tp.size > ny) { set_error("harris: image height %d below the Gaussian half-width %d (undefined in the reference)", ny, tp.size); return B2F_EUNSUP; }
@@ -598,20 +877,8 @@ static int response_exact(b2f_ctx *ctx, float *d_I, int n_frames, int nx, int ny
 // frames are first copied into arena scratch.
 int harris_response_device(b2f_ctx *ctx, const void *d_frames, bool u8, int n_frames, int nx, int ny,
                            const b2f_harris_params *p, int exact, float *d_R, cudaStream_t st) {
-  if (!exact && harris_fused_supported(nx, ny, p->sigma_d, p->sigma_i, p->gaussian)) {
-    HarrisConsts kc;
-    memset(&kc, 0, sizeof(kc));
-    double Bd[HARRIS_MAX_TAPS], Bi[HARRIS_MAX_TAPS];
-    int sd = taps_double(p->sigma_d, Bd), si = taps_double(p->sigma_i, Bi);
-    const float gscale = (p->gradient == 1) ? 1.f : 0.25f;
-    for (int i = 0; i < sd; i++) kc.wd[i] = (float)Bd[i];
-    for (int i = 0; i < si; i++) { kc.wic[i] = (float)Bi[i]; kc.wir[i] = gscale * (float)Bi[i]; }
-    kc.k = p->k;
-    kc.measure = p->measure;
-    int ri = si - 1;
-    if (ri == 7) return launch_fused<3, 7>(ctx, d_frames, u8, p->gradient == 1, n_frames, nx, ny, d_R, kc, st);
-    return launch_fused<3, 3>(ctx, d_frames, u8, p->gradient == 1, n_frames, nx, ny, d_R, kc, st);
-  }
+  if (!exact && harris_fused_supported(nx, ny, p->sigma_d, p->sigma_i, p->gaussian))
+    return harris_fused_launch(ctx, d_frames, u8, n_frames, nx, ny, p, d_R, nullptr, st);
   size_t tot = (size_t)nx * ny * n_frames;
   float *I = ctx->arena.get<float>(tot);
   B2F_ARENA_CHECK(ctx);
@@ -649,6 +916,92 @@ int harris_nms_device(b2f_ctx *ctx, const float *d_R, int n_frames, int nx, int 
   B2F_LAUNCH_CHECK(ctx);
   emit_corners_kernel<<<dim3(ceil_div(ny, 8), n_frames), 256, 0, st>>>(mask, row_off, d_R, d_xy, d_strength, nx, ny, wpr, cap);
   B2F_LAUNCH_CHECK(ctx);
+  return B2F_OK;
+}
+
+// ---- certified corners on the fast path ---------------------------------------------------------
+bool harris_certified_supported(int nx, int ny, const b2f_harris_params *p) {
+  if (!harris_fused_supported(nx, ny, p->sigma_d, p->sigma_i, p->gaussian)) return false;
+  if (p->measure != 0) return false;                            // the error bound is derived for the Harris measure
+  const int radius = 2 * p->sigma_i + 0.5;                      // harris.cpp:523
+  if (!(radius == 2 || radius == 3 || radius == 5)) return false;
+  return !(ny <= 2 * radius + 1 || nx <= 2 * radius + 1);
+}
+
+size_t harris_certified_scratch_bytes(int n_frames, int nx, int ny, int cap, bool want_m9) {
+  const size_t wpr = ceil_div(nx, 32), ebx = (nx + 7) >> 3, eby = (ny + 7) >> 3;
+  size_t b = align256((size_t)n_frames * nx * ny * 4);                          // R
+  b += align256((size_t)n_frames * ebx * eby * 4);                               // eps blocks
+  b += 2 * align256((size_t)n_frames * ny * wpr * 4) + align256((size_t)n_frames * ny * 4);   // masks, row offsets
+  b += align256((size_t)n_frames * cap * 4) * 2 + align256((size_t)n_frames * cap) * 2 + align256((size_t)n_frames * 4);
+  if (want_m9) b += align256((size_t)n_frames * cap * 36);
+  return b + 4096;
+}
+
+// frames (u8 or float, resident on the device) -> raster-ordered corner lists identical to the reference's:
+// d_xy[f*cap + i] = y*nx + x, d_strength = the reference's R there (bit for bit), d_M9 (optional) its 3x3
+// neighbourhood, d_counts[f] = number of corners (may exceed cap: the caller reports B2F_ECAP).
+// d_R_out (optional) receives the fp32 response planes.  Scratch from the arena (harris_certified_scratch_bytes).
+int harris_corners_certified(b2f_ctx *ctx, const void *d_frames, bool u8, int n_frames, int nx, int ny,
+                             const b2f_harris_params *p, int cap, int *d_xy, float *d_strength, float *d_M9,
+                             int *d_counts, float *d_R_out, cudaStream_t st) {
+  const int radius = 2 * p->sigma_i + 0.5;
+  const size_t plane = (size_t)nx * ny;
+  const int wpr = ceil_div(nx, 32), ebx = (nx + 7) >> 3, eby = (ny + 7) >> 3;
+  float *d_R = d_R_out ? d_R_out : ctx->arena.get<float>(plane * n_frames);
+  unsigned *eps = ctx->arena.get<unsigned>((size_t)n_frames * ebx * eby);
+  unsigned *cand = ctx->arena.get<unsigned>((size_t)n_frames * ny * wpr);
+  unsigned *cert = ctx->arena.get<unsigned>((size_t)n_frames * ny * wpr);
+  int *row_off = ctx->arena.get<int>((size_t)n_frames * ny);
+  int *c_xy = ctx->arena.get<int>((size_t)n_frames * cap);
+  float *c_s = ctx->arena.get<float>((size_t)n_frames * cap);
+  unsigned char *c_flag = ctx->arena.get<unsigned char>((size_t)n_frames * cap);
+  unsigned char *c_keep = ctx->arena.get<unsigned char>((size_t)n_frames * cap);
+  int *c_cnt = ctx->arena.get<int>(n_frames);
+  float *c_M9 = d_M9 ? ctx->arena.get<float>((size_t)n_frames * cap * 9) : nullptr;
+  B2F_ARENA_CHECK(ctx);
+  if (!ctx->harris_stats) {
+    B2F_CUDA(cudaMalloc(&ctx->harris_stats, sizeof(PatchStats)));
+    B2F_CUDA(cudaMemsetAsync(ctx->harris_stats, 0, sizeof(PatchStats), st));
+  }
+  B2F_CUDA(cudaMemsetAsync(eps, 0, sizeof(unsigned) * (size_t)n_frames * ebx * eby, st));
+  int rc = harris_fused_launch(ctx, d_frames, u8, n_frames, nx, ny, p, d_R, eps, st);
+  if (rc != B2F_OK) return rc;
+  dim3 grid(ceil_div(nx, TN_TW), ceil_div(ny, TN_TH), n_frames);
+  if (radius == 5) nms_tolerant_kernel<5><<<grid, TN_NT, 0, st>>>(d_R, eps, cand, cert, nx, ny, wpr, p->threshold);
+  else if (radius == 3) nms_tolerant_kernel<3><<<grid, TN_NT, 0, st>>>(d_R, eps, cand, cert, nx, ny, wpr, p->threshold);
+  else nms_tolerant_kernel<2><<<grid, TN_NT, 0, st>>>(d_R, eps, cand, cert, nx, ny, wpr, p->threshold);
+  B2F_LAUNCH_CHECK(ctx);
+  row_count_kernel<<<dim3(ceil_div(ny, 8), n_frames), 256, 0, st>>>(cand, row_off, ny, wpr);
+  B2F_LAUNCH_CHECK(ctx);
+  row_scan_kernel<<<n_frames, 1024, 0, st>>>(row_off, c_cnt, ny);
+  B2F_LAUNCH_CHECK(ctx);
+  emit_candidates_kernel<<<dim3(ceil_div(ny, 8), n_frames), 256, 0, st>>>(cand, cert, row_off, c_xy, c_flag, nx, ny, wpr, cap);
+  B2F_LAUNCH_CHECK(ctx);
+  ExactTaps td, ti;
+  td.size = harris_taps_double(p->sigma_d, td.B);
+  ti.size = harris_taps_double(p->sigma_i, ti.B);
+  if (td.size - 1 > XP_MAXRD || ti.size - 1 > XP_MAXRI || radius > XP_MAXM) { set_error("harris: patch dimensions exceeded"); return B2F_EUNSUP; }
+  PatchStats *stats = static_cast<PatchStats *>(ctx->harris_stats);
+  const dim3 pgrid(std::max(1, std::min(cap, 2 * ctx->sm_count)), n_frames);
+  if (u8) harris_exact_patch_kernel<true><<<pgrid, XP_NT, 0, st>>>(d_frames, d_R, eps, c_xy, c_flag, c_cnt, cap, c_s, c_keep, c_M9, stats, nx, ny,
+                                                                   td, ti, p->k, p->measure, p->gradient == 1 ? 1 : 0, p->threshold, radius);
+  else harris_exact_patch_kernel<false><<<pgrid, XP_NT, 0, st>>>(d_frames, d_R, eps, c_xy, c_flag, c_cnt, cap, c_s, c_keep, c_M9, stats, nx, ny,
+                                                                  td, ti, p->k, p->measure, p->gradient == 1 ? 1 : 0, p->threshold, radius);
+  B2F_LAUNCH_CHECK(ctx);
+  compact_kept_kernel<<<n_frames, 1024, 0, st>>>(c_xy, c_keep, c_s, c_M9, c_cnt, cap, d_xy, d_strength, d_M9, d_counts, cap);
+  B2F_LAUNCH_CHECK(ctx);
+  return B2F_OK;
+}
+
+// candidates / undecided / bound violations / kept since the context was created (synchronises `st`)
+int harris_cert_stats(b2f_ctx *ctx, unsigned long long out[4], cudaStream_t st) {
+  out[0] = out[1] = out[2] = out[3] = 0;
+  if (!ctx->harris_stats) return B2F_OK;
+  PatchStats h;
+  B2F_CUDA(cudaMemcpyAsync(&h, ctx->harris_stats, sizeof(h), cudaMemcpyDeviceToHost, st));
+  B2F_CUDA(cudaStreamSynchronize(st));
+  out[0] = h.candidates; out[1] = h.undecided; out[2] = h.violations; out[3] = h.kept;
   return B2F_OK;
 }
 

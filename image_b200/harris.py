@@ -120,6 +120,40 @@ def harris_response_dev(d_frames, is_u8, n_frames, nx, ny, d_R, stream=None, ctx
                                            C.byref(p), _lib.ptr(d_R), _lib.ptr(stream) if stream is not None else None))
 
 
+def _params(kw):
+    d = dict(k=0.06, sigma_d=1.0, sigma_i=2.5, threshold=130.0, gaussian=0, gradient=0, strategy=0, Nselect=1,
+             measure=0, Nscales=1, precision=0, cells=10, verbose=0, exact=0)
+    d.update(kw)
+    return _lib.HarrisParams(*[d[k] for k in ("k", "sigma_d", "sigma_i", "threshold", "gaussian", "gradient", "strategy",
+                                              "Nselect", "measure", "Nscales", "precision", "cells", "verbose", "exact")])
+
+
+def harris_corners_dev(d_frames, is_u8, n_frames, nx, ny, cap, d_xy, d_strength, d_counts, d_R=None, stream=None, ctx=None, **kw):
+    """Device-resident frames -> reference-identical raster-ordered corner lists (b2f_harris_corners_dev)."""
+    lib = _lib.load()
+    p = _params(kw)
+    _lib.check(lib.b2f_harris_corners_dev(ctx or _lib.context(), _lib.ptr(d_frames), int(bool(is_u8)), n_frames, nx, ny, C.byref(p),
+                                          int(cap), _lib.ptr(d_xy), _lib.ptr(d_strength), _lib.ptr(d_counts),
+                                          _lib.ptr(d_R) if d_R is not None else None,
+                                          _lib.ptr(stream) if stream is not None else None))
+
+
+def harris_response_eps_dev(d_frames, is_u8, n_frames, nx, ny, d_R, d_eps, stream=None, ctx=None, **kw):
+    lib = _lib.load()
+    p = _params(kw)
+    _lib.check(lib.b2f_harris_response_eps_dev(ctx or _lib.context(), _lib.ptr(d_frames), int(bool(is_u8)), n_frames, nx, ny,
+                                               C.byref(p), _lib.ptr(d_R), _lib.ptr(d_eps),
+                                               _lib.ptr(stream) if stream is not None else None))
+
+
+def cert_stats(ctx=None):
+    """dict(candidates, undecided, violations, kept) of the certified path on this context since it was created."""
+    lib = _lib.load()
+    out = (C.c_ulonglong * 4)()
+    _lib.check(lib.b2f_harris_cert_stats(ctx or _lib.context(), out))
+    return dict(candidates=int(out[0]), undecided=int(out[1]), violations=int(out[2]), kept=int(out[3]))
+
+
 def harris_nms_dev(d_R, n_frames, nx, ny, threshold, radius, cap, d_xy, d_strength, d_counts, stream=None, ctx=None):
     lib = _lib.load()
     _lib.check(lib.b2f_harris_nms_dev(ctx or _lib.context(), _lib.ptr(d_R), n_frames, nx, ny, float(threshold), int(radius),

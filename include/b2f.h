@@ -62,9 +62,13 @@ int b2f_set_chunk_bytes(b2f_ctx *ctx, size_t bytes);
 typedef struct {
   float k, sigma_d, sigma_i, threshold;
   int gaussian, gradient, strategy, Nselect, measure, Nscales, precision, cells, verbose;
-  /* not a reference argument: 0 = fused fp32 kernel (R within 1e-4 of the reference, corner lists
-   * identical except at float near-ties); 1 = staged kernels that repeat the reference's
-   * double-accumulate arithmetic operation by operation (R bit-identical, ~6x slower). */
+  /* not a reference argument.
+   * 0 (default) = certified fast path: the fused fp32 kernel proposes key points together with a bound on its
+   *     distance from the reference's R; every proposed key point is re-evaluated with the reference's own
+   *     arithmetic on a small patch, so the lists (positions, order) and strengths are the reference's bit for
+   *     bit.  Parameter sets the fused kernel does not cover run the staged kernels instead (same results).
+   * 1 = staged kernels that repeat the reference's double-accumulate arithmetic over whole planes.
+   * 2 = fused fp32 kernel + plain NMS, uncertified: R within 1e-4, lists identical except at float near-ties. */
   int exact;
 } b2f_harris_params;
 void b2f_harris_default_params(b2f_harris_params *p);   /* defaults of rcpp_harris.cpp:19-32 */
@@ -84,6 +88,20 @@ int b2f_harris_batch_u8(b2f_ctx *ctx, const uint8_t *frames, int n_frames, int n
  * d_R: n_frames*nx*ny floats.  Asynchronous on `stream` (cudaStream_t; NULL = ctx stream). */
 int b2f_harris_response_dev(b2f_ctx *ctx, const void *d_frames, int is_u8, int n_frames, int nx, int ny,
                             const b2f_harris_params *p, float *d_R, void *stream);
+/* Frames resident in HBM -> reference-identical corner lists, all on the device and asynchronous on `stream`:
+ * d_xy[f*cap + i] = y*nx + x (raster order, harris.cpp:250-252), d_strength the reference's R there,
+ * d_counts[f] the number of corners (may exceed cap: only cap are stored; -1 = the internal candidate records
+ * overflowed, rerun with a larger cap).  d_R (optional, n_frames*nx*ny floats) receives the fp32 response planes.
+ * strategy / precision / Nscales of `p` are not applied here (b2f_harris_host does them per frame). */
+int b2f_harris_corners_dev(b2f_ctx *ctx, const void *d_frames, int is_u8, int n_frames, int nx, int ny,
+                           const b2f_harris_params *p, int cap, int *d_xy, float *d_strength, int *d_counts,
+                           float *d_R, void *stream);
+/* certification counters of this context since b2f_init: out4 = {candidates proposed by the tolerant NMS,
+ * of which undecided (full window recomputed exactly), violations of the error bound (must be 0), kept}. */
+int b2f_harris_cert_stats(b2f_ctx *ctx, unsigned long long *out4);
+/* diagnostics: fused response plus its per-8x8-block error bound (d_eps: n_frames*ceil(ny/8)*ceil(nx/8) floats) */
+int b2f_harris_response_eps_dev(b2f_ctx *ctx, const void *d_frames, int is_u8, int n_frames, int nx, int ny,
+                                const b2f_harris_params *p, float *d_R, float *d_eps, void *stream);
 /* NMS + raster-ordered compaction on device: d_xy receives y*nx+x (int32), d_strength the R
  * value, d_counts[f] the number of corners of frame f (may exceed cap; only cap are stored). */
 int b2f_harris_nms_dev(b2f_ctx *ctx, const float *d_R, int n_frames, int nx, int ny, float threshold,
