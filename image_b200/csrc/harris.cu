@@ -506,17 +506,39 @@ nms_tolerant_kernel(const float *__restrict__ R, const unsigned *__restrict__ ep
   __syncthreads();
   const int lane = threadIdx.x & 31;
   float umax = -INFINITY;                                      // largest upper bound in the tile
-  for (int u = threadIdx.x; u < TH2 * P; u += TN_NT) {
-    const int r = u / P, c = u - r * P;
-    const int gy = y0 - RAD + r, gx = x0 - TN_LP + c;
-    float L = -INFINITY;
-    if (gy >= 0 && gy < ny && gx >= 0 && gx < nx) {
-      const float v = __ldg(Rf + (size_t)gy * nx + gx);
-      const float e = epsb[((gy >> 3) - by0) * TN_EBW + ((gx >> 3) - bx0)];
-      L = __fsub_rd(v, e);
-      umax = fmaxf(umax, __fadd_ru(v, e));
+  if ((nx & 3) == 0 && x0 >= TN_LP && x0 + TN_TW + TN_LP <= nx && y0 >= RAD && y0 + TN_TH + RAD <= ny) {
+    // interior tile: 16-byte loads, all of a thread's loads before its stores; the 4 pixels of a vector share an eps block
+    constexpr int NV4 = TH2 * (P / 4), PER = (NV4 + TN_NT - 1) / TN_NT;
+    const float *org = Rf + (size_t)(y0 - RAD) * nx + (x0 - TN_LP);
+    float4 v[PER];
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+      const int u = min((int)threadIdx.x + k * TN_NT, NV4 - 1), r = u / (P / 4), c4 = u - r * (P / 4);
+      v[k] = __ldg(reinterpret_cast<const float4 *>(org + (size_t)r * nx + 4 * c4));
     }
-    tile[u] = L;
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+      const int u = threadIdx.x + k * TN_NT;
+      if (u < NV4) {
+        const int r = u / (P / 4), c4 = u - r * (P / 4);
+        const float e = epsb[(((y0 - RAD + r) >> 3) - by0) * TN_EBW + (((x0 - TN_LP + 4 * c4) >> 3) - bx0)];
+        reinterpret_cast<float4 *>(tile)[u] = make_float4(__fsub_rd(v[k].x, e), __fsub_rd(v[k].y, e), __fsub_rd(v[k].z, e), __fsub_rd(v[k].w, e));
+        umax = fmaxf(umax, __fadd_ru(fmaxf(fmaxf(v[k].x, v[k].y), fmaxf(v[k].z, v[k].w)), e));
+      }
+    }
+  } else {
+    for (int u = threadIdx.x; u < TH2 * P; u += TN_NT) {
+      const int r = u / P, c = u - r * P;
+      const int gy = y0 - RAD + r, gx = x0 - TN_LP + c;
+      float L = -INFINITY;
+      if (gy >= 0 && gy < ny && gx >= 0 && gx < nx) {
+        const float v = __ldg(Rf + (size_t)gy * nx + gx);
+        const float e = epsb[((gy >> 3) - by0) * TN_EBW + ((gx >> 3) - bx0)];
+        L = __fsub_rd(v, e);
+        umax = fmaxf(umax, __fadd_ru(v, e));
+      }
+      tile[u] = L;
+    }
   }
   // A corner needs R_ref >= Th: a tile none of whose upper bounds reaches the threshold has empty masks.
   if (!__syncthreads_or(!(umax < Th))) {

@@ -49,7 +49,7 @@ static int launch_cfg(b2f_ctx *ctx, const void *d_frames, int n_frames, int nx, 
   if (TMA) {
     if (!make_u8_tile_map(&map, d_frames, n_frames, nx, ny, C::IN_H)) { set_error("harris: cuTensorMapEncodeTiled failed"); return B2F_ECUDA; }
     const long long tiles = (long long)tiles_x * tiles_y * n_frames;
-    const int per_sm = (C::NT <= 256) ? 2 : 1;
+    const int per_sm = C::CTAS;
     const int grid = (int)std::min<long long>(tiles, (long long)ctx->sm_count * per_sm);
     kern<<<grid, C::NT, smem, st>>>(d_frames, d_R, d_eps, nx, ny, n_frames, generic_all, kc, map);
   } else {
@@ -119,19 +119,19 @@ int harris_fused_launch(b2f_ctx *ctx, const void *d_frames, bool u8, int n_frame
   const bool aligned = (nx % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_frames) & 15) == 0) && ((reinterpret_cast<uintptr_t>(d_R) & 7) == 0);
   const int generic_all = aligned ? 0 : 1;
   if (ri == 3) {
-    using C = Fused3Cfg<3, 3, 64, 256, 4>;
+    using C = Fused3Cfg<3, 3, 64, 256, 4, 2>;
     return launch_shape<C, false>(ctx, d_frames, u8, grad, n_frames, nx, ny, d_R, d_eps, generic_all, false, kc, st);
   }
   // tall tiles pay when the frame has many tile rows; TMA needs 16-byte row strides (u8)
   const int cfg_env = env_int("B2F_HARRIS_TILE", 0), tma_env = env_int("B2F_HARRIS_TMA", -1);
-  const bool tall = cfg_env ? (cfg_env == 108) : (ny >= 432);
+  const bool tall = cfg_env ? (cfg_env == 48) : false;
   const bool tma_ok = u8 && aligned && (nx % 16 == 0) && (((size_t)nx * ny) % 16 == 0) && encode_tiled_fn() != nullptr;
   const bool tma = tma_ok && (tma_env < 0 ? true : tma_env != 0);
   if (tall) {
-    using C = Fused3Cfg<3, 7, 108, 512, 8>;
-    return launch_shape<C, true>(ctx, d_frames, u8, grad, n_frames, nx, ny, d_R, d_eps, generic_all, tma, kc, st);
+    using C = Fused3Cfg<3, 7, 48, 256, 4, 3>;
+    return launch_shape<C, false>(ctx, d_frames, u8, grad, n_frames, nx, ny, d_R, d_eps, generic_all, false, kc, st);
   }
-  using C = Fused3Cfg<3, 7, 64, 256, 4>;
+  using C = Fused3Cfg<3, 7, 64, 256, 4, 2>;
   return launch_shape<C, true>(ctx, d_frames, u8, grad, n_frames, nx, ny, d_R, d_eps, generic_all, tma, kc, st);
 }
 

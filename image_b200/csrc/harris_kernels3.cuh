@@ -80,9 +80,9 @@ __device__ __forceinline__ float harris_eps(float T, float M, float k) {
   return fmaf(e, 1.25f, 1e-30f);
 }
 
-template <int RD_, int RI_, int TH_, int NT_, int DW_> struct Fused3Cfg {
+template <int RD_, int RI_, int TH_, int NT_, int DW_, int CTAS_> struct Fused3Cfg {
   static constexpr int RD = RD_, RI = RI_;
-  static constexpr int TW = 64, TH = TH_, NT = NT_, DW = DW_;
+  static constexpr int TW = 64, TH = TH_, NT = NT_, DW = DW_, CTAS = CTAS_;
   static constexpr int HALO = 12;                               // >= RD + 1 + RI + 1, multiple of 4
   static constexpr int IN_W = TW + 2 * HALO, IN_H = TH + 2 * HALO;
   static constexpr int G = RI + 1;                              // halo of Is needed by the products
@@ -100,18 +100,27 @@ template <int RD_, int RI_, int TH_, int NT_, int DW_> struct Fused3Cfg {
   static constexpr int AR_P = TW + 2;                           // float
   static_assert(IN_P % 4 == 2 && IS_P % 4 == 2 && R1_P % 4 == 2 && AR_P % 4 == 2, "bank-conflict-free pitches");
   static_assert(IN_H % 2 == 0 && IS_H % 2 == 0 && AR_H % 2 == 0, "row pairs");
-  static constexpr int REGION_X = (IN_H * IN_P > IS_H * IS_P) ? IN_H * IN_P : IS_H * IS_P;   // floats
-  static constexpr int REGION_Y = (R1_H * R1_P > 3 * AR_H * AR_P) ? R1_H * R1_P : 3 * AR_H * AR_P;
+  // Shared-memory layout (floats).  Live ranges: IN (A-B), R1 (B-C), IS (C-D), AR (D-E).  IS sits at 0 and AR right
+  // behind it (both live in stage D); IN also starts at 0 and may run into AR's space; R1 takes the tail of AR's
+  // space, behind IN (both live in stage B) and behind IS (both live in stage C).
+  static constexpr int IN_N = IN_H / 2 * IN_P * 2, IS_N = IS_H / 2 * IS_P * 2, R1_N = R1_H * R1_P, AR_N = 3 * AR_H * AR_P;
+  static constexpr int OFF_AR = (IS_N + 3) & ~3;
+  static constexpr int OFF_R1 = ((((OFF_AR + AR_N - R1_N) > IN_N ? (OFF_AR + AR_N - R1_N) : IN_N) + 3) & ~3);
+  static constexpr int TILE_N = ((OFF_AR + AR_N > OFF_R1 + R1_N ? OFF_AR + AR_N : OFF_R1 + R1_N) + 3) & ~3;
+  static_assert(OFF_R1 >= IN_N && OFF_R1 >= IS_N && OFF_AR >= IS_N, "live tiles must not overlap");
   static constexpr int MAP_N = (TW + 2 * RI) + (TH + 2 * RI);   // product-coordinate remap tables (generic tiles)
-  static constexpr int U8_P = 96, U8_BYTES = IN_H * U8_P;       // TMA staging buffer: box 96 x IN_H bytes
-  static constexpr size_t SMEM_CORE = sizeof(float) * (REGION_X + REGION_Y) + sizeof(short) * ((MAP_N + 7) & ~7) + sizeof(float) * (NT / 32);
+  // TMA staging buffer: box 96 x IN_H bytes starting at column x0-16 (the global start of every box row must be
+  // 16-byte aligned), so input column c = x0-12+c' sits at box column c'+4
+  static constexpr int U8_P = 96, U8_BYTES = IN_H * U8_P, U8_X0 = 16, U8_SKIP = U8_X0 - HALO;
+  static_assert(U8_SKIP >= 0 && U8_SKIP + IN_W <= U8_P, "the box covers the input tile");
+  static constexpr size_t SMEM_CORE = sizeof(float) * TILE_N + sizeof(short) * ((MAP_N + 7) & ~7) + sizeof(float) * (NT / 32);
   static constexpr size_t SMEM = SMEM_CORE;
   static constexpr size_t SMEM_TMA = ((SMEM_CORE + 127) & ~size_t(127)) + U8_BYTES + 128;
   static_assert(RD + 1 + RI + 1 <= HALO, "halo too small");
   static_assert(HALO - G - RD >= 0, "row-blur taps must stay inside the input tile");
   static_assert(DW == 4 || DW == 8, "stage-D item width");
   // stage C: RB Is rows per item (even), stage E: RB output rows per item
-  static constexpr int C_RB = (TH_ > 64) ? 12 : 10;
+  static constexpr int C_RB = (IS_H % 10 == 0) ? 10 : ((IS_H % 8 == 0) ? 8 : 12);
   static constexpr int E_NRG = NT / (TW / 2);                   // row groups of stage E
   static constexpr int E_RB = (TH + E_NRG - 1) / E_NRG;
   static_assert(E_RB <= 8, "a stage-E item must not span more than two 8-row eps blocks");
@@ -151,7 +160,7 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
 // TMA = 1: persistent grid; u8 frames only; interior tiles get their bytes through the tensor map (prefetched one
 //          tile ahead), generic tiles load with scalar reflected loads.
 template <class C, bool U8, int GRAD, bool TMA>
-__global__ void __launch_bounds__(C::NT, (C::NT <= 256) ? 2 : 1)
+__global__ void __launch_bounds__(C::NT, C::CTAS)
 harris_fused3_kernel(const void *__restrict__ frames, float *__restrict__ Rout, unsigned *__restrict__ eps_blk,
                      int nx, int ny, int n_frames, int generic_all, const __grid_constant__ HarrisConsts kc,
                      const __grid_constant__ CUtensorMap tmap) {
@@ -159,9 +168,9 @@ harris_fused3_kernel(const void *__restrict__ frames, float *__restrict__ Rout, 
   extern __shared__ __align__(128) float smem[];
   float2 *sINp = reinterpret_cast<float2 *>(smem);             // [IN_H/2][IN_P]
   float2 *sISp = reinterpret_cast<float2 *>(smem);             // [IS_H/2][IS_P]   (aliases sINp)
-  float *sR1 = smem + C::REGION_X;                             // [R1_H][R1_P], odd rows shifted by 2
-  float *sAR = smem + C::REGION_X;                             // [3][AR_H][AR_P]  (aliases sR1), odd rows shifted by 2
-  short *mapx = reinterpret_cast<short *>(smem + C::REGION_X + C::REGION_Y);
+  float *sR1 = smem + C::OFF_R1;                               // [R1_H][R1_P], odd rows shifted by 2 (tail of AR's space)
+  float *sAR = smem + C::OFF_AR;                               // [3][AR_H][AR_P], odd rows shifted by 2
+  short *mapx = reinterpret_cast<short *>(smem + C::TILE_N);
   short *mapy = mapx + (C::TW + 2 * RI);
   float *sM = reinterpret_cast<float *>(mapx + ((C::MAP_N + 7) & ~7));         // per-warp max |pixel| of the tile
   const int tid = threadIdx.x;
@@ -198,7 +207,7 @@ harris_fused3_kernel(const void *__restrict__ frames, float *__restrict__ Rout, 
       decode(tile, tx0, ty0, tf);
       if (!generic_all && harris3_tile_is_interior<C>(tx0, ty0, nx, ny)) {
         mbar_expect_tx(bar, C::U8_BYTES);
-        tma_load_3d(sU8, &tmap, bar, tx0 - C::HALO, ty0 - C::HALO, tf);
+        tma_load_3d(sU8, &tmap, bar, tx0 - C::U8_X0, ty0 - C::HALO, tf);
       }
     }
   }
@@ -223,8 +232,8 @@ harris_fused3_kernel(const void *__restrict__ frames, float *__restrict__ Rout, 
         unsigned mx = 0;
         for (int it = tid; it < ITEMS; it += C::NT) {
           const int rp = it / CPR, cpi = it - rp * CPR;
-          const unsigned a = *reinterpret_cast<const unsigned short *>(sU8 + (2 * rp) * C::U8_P + 2 * cpi);
-          const unsigned b = *reinterpret_cast<const unsigned short *>(sU8 + (2 * rp + 1) * C::U8_P + 2 * cpi);
+          const unsigned a = *reinterpret_cast<const unsigned short *>(sU8 + (2 * rp) * C::U8_P + C::U8_SKIP + 2 * cpi);
+          const unsigned b = *reinterpret_cast<const unsigned short *>(sU8 + (2 * rp + 1) * C::U8_P + C::U8_SKIP + 2 * cpi);
           mx = max(mx, max(max(a & 0xff, a >> 8), max(b & 0xff, b >> 8)));
           *reinterpret_cast<float4 *>(sINp + rp * C::IN_P + 2 * cpi) =
               make_float4((float)(a & 0xff), (float)(b & 0xff), (float)(a >> 8), (float)(b >> 8));
@@ -285,15 +294,26 @@ harris_fused3_kernel(const void *__restrict__ frames, float *__restrict__ Rout, 
       }
     } else {
       // generic tile: scalar loads, reflected at the frame border (the blur's padding rule applied to the INPUT,
-      // which makes every later plane of the tile the reference's plane at the reflected coordinate)
-      for (int i = tid; i < C::IN_H * C::IN_W; i += C::NT) {
+      // which makes every later plane of the tile the reference's plane at the reflected coordinate); all loads of a
+      // thread are issued before its stores, so that the memory latency is paid once
+      constexpr int N = C::IN_H * C::IN_W, PER = (N + C::NT - 1) / C::NT;
+      float v[PER];
+#pragma unroll
+      for (int k = 0; k < PER; k++) {
+        const int i = min(tid + k * C::NT, N - 1);
         const int r = i / C::IN_W, c = i - r * C::IN_W;
         const int gy = reflect_index(y0 - C::HALO + r, ny), gx = reflect_index(x0 - C::HALO + c, nx);
-        float v;
-        if (U8) v = (float)__ldg(static_cast<const unsigned char *>(frames) + fofs + (size_t)gy * nx + gx);
-        else v = __ldg(static_cast<const float *>(frames) + fofs + (size_t)gy * nx + gx);
-        reinterpret_cast<float *>(sINp + (r >> 1) * C::IN_P + c)[r & 1] = v;
-        mloc = fmaxf(mloc, fabsf(v));
+        if (U8) v[k] = (float)__ldg(static_cast<const unsigned char *>(frames) + fofs + (size_t)gy * nx + gx);
+        else v[k] = __ldg(static_cast<const float *>(frames) + fofs + (size_t)gy * nx + gx);
+      }
+#pragma unroll
+      for (int k = 0; k < PER; k++) {
+        const int i = tid + k * C::NT;
+        if (i < N) {
+          const int r = i / C::IN_W, c = i - r * C::IN_W;
+          reinterpret_cast<float *>(sINp + (r >> 1) * C::IN_P + c)[r & 1] = v[k];
+          mloc = fmaxf(mloc, fabsf(v[k]));
+        }
       }
       // product-coordinate remap tables: Is-tile index of the pixel whose gradient the reference uses there
       for (int q = tid; q < C::TW + 2 * RI; q += C::NT) {
@@ -317,7 +337,7 @@ harris_fused3_kernel(const void *__restrict__ frames, float *__restrict__ Rout, 
         decode(nt, tx0, ty0, tf);
         if (!generic_all && harris3_tile_is_interior<C>(tx0, ty0, nx, ny)) {
           mbar_expect_tx(bar, C::U8_BYTES);
-          tma_load_3d(sU8, &tmap, bar, tx0 - C::HALO, ty0 - C::HALO, tf);
+          tma_load_3d(sU8, &tmap, bar, tx0 - C::U8_X0, ty0 - C::HALO, tf);
         }
       }
     }
@@ -414,80 +434,7 @@ harris_fused3_kernel(const void *__restrict__ frames, float *__restrict__ Rout, 
       constexpr int PL = C::AR_H * C::AR_P;                    // plane stride (multiple of 4 floats)
       static_assert(PL % 4 == 0, "plane stride keeps 16-byte alignment");
       static_assert(RPS + 1 <= C::IS_H / 2, "row pairs and their two pair lines");
-      for (int it = tid; it < RPS_PAD * GROUPS; it += C::NT) {
-        const int g = it / RPS_PAD, r = it - g * RPS_PAD;
-        if (r >= RPS) continue;
-        float2 a0[DW], b0[DW], c0[DW];
-#pragma unroll
-        for (int j = 0; j < DW; j++) { a0[j] = b0[j] = c0[j] = f2s(0.f); }
-        if (!generic) {
-          const float2 *l0 = sISp + r * C::IS_P + DW * g;      // pair line r   = Is rows 2r,   2r+1
-          const float2 *l1 = l0 + C::IS_P;                     // pair line r+1 = Is rows 2r+2, 2r+3
-          float2 p0[3], p1[3];                                 // sliding window of Is columns q, q+1, q+2
-          {
-            const float4 t0 = *reinterpret_cast<const float4 *>(l0), t1 = *reinterpret_cast<const float4 *>(l1);
-            p0[0] = f2(t0.x, t0.y); p0[1] = f2(t0.z, t0.w); p1[0] = f2(t1.x, t1.y); p1[1] = f2(t1.z, t1.w);
-          }
-#pragma unroll
-          for (int q = 0; q < NPOS; q++) {
-            float2 n0 = f2s(0.f), n1 = f2s(0.f);
-            if ((q & 1) == 0) {                                // columns q+2, q+3 arrive as one 16-byte load per line
-              const float4 t0 = *reinterpret_cast<const float4 *>(l0 + q + 2), t1 = *reinterpret_cast<const float4 *>(l1 + q + 2);
-              p0[2] = f2(t0.x, t0.y); p1[2] = f2(t1.x, t1.y);
-              n0 = f2(t0.z, t0.w); n1 = f2(t1.z, t1.w);
-            }
-            // ---- products at column q+1
-            float2 gx, gy;
-            if (GRAD == 0) {
-              gy = sub2(p1[1], p0[1]);
-              gx = f2(p0[2].y - p0[0].y, p1[2].x - p1[0].x);
-            } else {
-              gx = f2(fmaf(0.25f, p0[2].y - p0[0].y, 0.125f * (p0[2].x + p1[2].x - p0[0].x - p1[0].x)),
-                      fmaf(0.25f, p1[2].x - p1[0].x, 0.125f * (p0[2].y + p1[2].y - p0[0].y - p1[0].y)));
-              gy = f2(fmaf(0.25f, p1[1].x - p0[1].x, 0.125f * (p1[2].x + p1[0].x - p0[2].x - p0[0].x)),
-                      fmaf(0.25f, p1[1].y - p0[1].y, 0.125f * (p1[2].y + p1[0].y - p0[2].y - p0[0].y)));
-            }
-            const float2 pa = __fmul2_rn(gx, gx), pb = __fmul2_rn(gx, gy), pc = __fmul2_rn(gy, gy);
-#pragma unroll
-            for (int j = 0; j < DW; j++) {
-              const int t = q - j - RI;
-              if (t >= -RI && t <= RI) {
-                const float2 w = f2s(kc.wir[t < 0 ? -t : t]);
-                a0[j] = __ffma2_rn(w, pa, a0[j]); b0[j] = __ffma2_rn(w, pb, b0[j]); c0[j] = __ffma2_rn(w, pc, c0[j]);
-              }
-            }
-            // slide: (q, q+1, q+2) -> (q+1, q+2, q+3)
-            p0[0] = p0[1]; p0[1] = p0[2]; p1[0] = p1[1]; p1[1] = p1[2];
-            if ((q & 1) == 0) { p0[2] = n0; p1[2] = n1; }
-          }
-        } else {
-          // generic tile: the product at virtual position (row a, column q) is the product at the remapped pixel
-          auto IS = [&](int row, int col) -> float { return reinterpret_cast<const float *>(sISp + (row >> 1) * C::IS_P + col)[row & 1]; };
-          const int ry0 = mapy[2 * r], ry1 = mapy[2 * r + 1];
-#pragma unroll 2
-          for (int q = 0; q < NPOS; q++) {
-            const int rx = mapx[DW * g + q];
-            float2 gx, gy;
-            if (GRAD == 0) {
-              gx = f2(IS(ry0, rx + 1) - IS(ry0, rx - 1), IS(ry1, rx + 1) - IS(ry1, rx - 1));
-              gy = f2(IS(ry0 + 1, rx) - IS(ry0 - 1, rx), IS(ry1 + 1, rx) - IS(ry1 - 1, rx));
-            } else {
-              gx = f2(fmaf(0.25f, IS(ry0, rx + 1) - IS(ry0, rx - 1), 0.125f * (IS(ry0 - 1, rx + 1) + IS(ry0 + 1, rx + 1) - IS(ry0 - 1, rx - 1) - IS(ry0 + 1, rx - 1))),
-                      fmaf(0.25f, IS(ry1, rx + 1) - IS(ry1, rx - 1), 0.125f * (IS(ry1 - 1, rx + 1) + IS(ry1 + 1, rx + 1) - IS(ry1 - 1, rx - 1) - IS(ry1 + 1, rx - 1))));
-              gy = f2(fmaf(0.25f, IS(ry0 + 1, rx) - IS(ry0 - 1, rx), 0.125f * (IS(ry0 + 1, rx + 1) + IS(ry0 + 1, rx - 1) - IS(ry0 - 1, rx + 1) - IS(ry0 - 1, rx - 1))),
-                      fmaf(0.25f, IS(ry1 + 1, rx) - IS(ry1 - 1, rx), 0.125f * (IS(ry1 + 1, rx + 1) + IS(ry1 + 1, rx - 1) - IS(ry1 - 1, rx + 1) - IS(ry1 - 1, rx - 1))));
-            }
-            const float2 pa = __fmul2_rn(gx, gx), pb = __fmul2_rn(gx, gy), pc = __fmul2_rn(gy, gy);
-#pragma unroll
-            for (int j = 0; j < DW; j++) {
-              const int t = q - j - RI;
-              if (t >= -RI && t <= RI) {
-                const float2 w = f2s(kc.wir[t < 0 ? -t : t]);
-                a0[j] = __ffma2_rn(w, pa, a0[j]); b0[j] = __ffma2_rn(w, pb, b0[j]); c0[j] = __ffma2_rn(w, pc, c0[j]);
-              }
-            }
-          }
-        }
+      auto store_item = [&](int g, int r, const float2 (&a0)[DW], const float2 (&b0)[DW], const float2 (&c0)[DW]) {
         float *o = sAR + (2 * r) * C::AR_P + DW * g;
 #define ST_ROWPAIR(dst, v)                                                                          \
         *reinterpret_cast<float4 *>(dst) = make_float4(v[0].x, v[1].x, v[2].x, v[3].x);             \
@@ -498,6 +445,120 @@ harris_fused3_kernel(const void *__restrict__ frames, float *__restrict__ Rout, 
         }
         ST_ROWPAIR(o, a0) ST_ROWPAIR(o + PL, b0) ST_ROWPAIR(o + 2 * PL, c0)
 #undef ST_ROWPAIR
+      };
+      // regular item: every product position lies inside the frame's gradient domain -> sliding windows over Is
+      auto fast_item = [&](int g, int r) {
+        float2 a0[DW], b0[DW], c0[DW];
+#pragma unroll
+        for (int j = 0; j < DW; j++) { a0[j] = b0[j] = c0[j] = f2s(0.f); }
+        const float2 *l0 = sISp + r * C::IS_P + DW * g;      // pair line r   = Is rows 2r,   2r+1
+        const float2 *l1 = l0 + C::IS_P;                     // pair line r+1 = Is rows 2r+2, 2r+3
+        float2 p0[3], p1[3];                                 // sliding window of Is columns q, q+1, q+2
+        {
+          const float4 t0 = *reinterpret_cast<const float4 *>(l0), t1 = *reinterpret_cast<const float4 *>(l1);
+          p0[0] = f2(t0.x, t0.y); p0[1] = f2(t0.z, t0.w); p1[0] = f2(t1.x, t1.y); p1[1] = f2(t1.z, t1.w);
+        }
+#pragma unroll
+        for (int q = 0; q < NPOS; q++) {
+          float2 n0 = f2s(0.f), n1 = f2s(0.f);
+          if ((q & 1) == 0) {                                // columns q+2, q+3 arrive as one 16-byte load per line
+            const float4 t0 = *reinterpret_cast<const float4 *>(l0 + q + 2), t1 = *reinterpret_cast<const float4 *>(l1 + q + 2);
+            p0[2] = f2(t0.x, t0.y); p1[2] = f2(t1.x, t1.y);
+            n0 = f2(t0.z, t0.w); n1 = f2(t1.z, t1.w);
+          }
+          // ---- products at column q+1
+          float2 gx, gy;
+          if (GRAD == 0) {
+            gy = sub2(p1[1], p0[1]);
+            gx = f2(p0[2].y - p0[0].y, p1[2].x - p1[0].x);
+          } else {
+            gx = f2(fmaf(0.25f, p0[2].y - p0[0].y, 0.125f * (p0[2].x + p1[2].x - p0[0].x - p1[0].x)),
+                    fmaf(0.25f, p1[2].x - p1[0].x, 0.125f * (p0[2].y + p1[2].y - p0[0].y - p1[0].y)));
+            gy = f2(fmaf(0.25f, p1[1].x - p0[1].x, 0.125f * (p1[2].x + p1[0].x - p0[2].x - p0[0].x)),
+                    fmaf(0.25f, p1[1].y - p0[1].y, 0.125f * (p1[2].y + p1[0].y - p0[2].y - p0[0].y)));
+          }
+          const float2 pa = __fmul2_rn(gx, gx), pb = __fmul2_rn(gx, gy), pc = __fmul2_rn(gy, gy);
+#pragma unroll
+          for (int j = 0; j < DW; j++) {
+            const int t = q - j - RI;
+            if (t >= -RI && t <= RI) {
+              const float2 w = f2s(kc.wir[t < 0 ? -t : t]);
+              a0[j] = __ffma2_rn(w, pa, a0[j]); b0[j] = __ffma2_rn(w, pb, b0[j]); c0[j] = __ffma2_rn(w, pc, c0[j]);
+            }
+          }
+          // slide: (q, q+1, q+2) -> (q+1, q+2, q+3)
+          p0[0] = p0[1]; p0[1] = p0[2]; p1[0] = p1[1]; p1[1] = p1[2];
+          if ((q & 1) == 0) { p0[2] = n0; p1[2] = n1; }
+        }
+        store_item(g, r, a0, b0, c0);
+      };
+      // irregular item of a border tile: the product at virtual position (row a, column q) is the product at the
+      // remapped pixel (reflect padding of the product planes, then the gradient's replicate rule)
+      auto remapped_item = [&](int g, int r) {
+        float2 a0[DW], b0[DW], c0[DW];
+#pragma unroll
+        for (int j = 0; j < DW; j++) { a0[j] = b0[j] = c0[j] = f2s(0.f); }
+        auto IS = [&](int row, int col) -> float { return reinterpret_cast<const float *>(sISp + (row >> 1) * C::IS_P + col)[row & 1]; };
+        const int ry0 = mapy[2 * r], ry1 = mapy[2 * r + 1];
+#pragma unroll 2
+        for (int q = 0; q < NPOS; q++) {
+          const int rx = mapx[DW * g + q];
+          float2 gx, gy;
+          if (GRAD == 0) {
+            gx = f2(IS(ry0, rx + 1) - IS(ry0, rx - 1), IS(ry1, rx + 1) - IS(ry1, rx - 1));
+            gy = f2(IS(ry0 + 1, rx) - IS(ry0 - 1, rx), IS(ry1 + 1, rx) - IS(ry1 - 1, rx));
+          } else {
+            gx = f2(fmaf(0.25f, IS(ry0, rx + 1) - IS(ry0, rx - 1), 0.125f * (IS(ry0 - 1, rx + 1) + IS(ry0 + 1, rx + 1) - IS(ry0 - 1, rx - 1) - IS(ry0 + 1, rx - 1))),
+                    fmaf(0.25f, IS(ry1, rx + 1) - IS(ry1, rx - 1), 0.125f * (IS(ry1 - 1, rx + 1) + IS(ry1 + 1, rx + 1) - IS(ry1 - 1, rx - 1) - IS(ry1 + 1, rx - 1))));
+            gy = f2(fmaf(0.25f, IS(ry0 + 1, rx) - IS(ry0 - 1, rx), 0.125f * (IS(ry0 + 1, rx + 1) + IS(ry0 + 1, rx - 1) - IS(ry0 - 1, rx + 1) - IS(ry0 - 1, rx - 1))),
+                    fmaf(0.25f, IS(ry1 + 1, rx) - IS(ry1 - 1, rx), 0.125f * (IS(ry1 + 1, rx + 1) + IS(ry1 + 1, rx - 1) - IS(ry1 - 1, rx + 1) - IS(ry1 - 1, rx - 1))));
+          }
+          const float2 pa = __fmul2_rn(gx, gx), pb = __fmul2_rn(gx, gy), pc = __fmul2_rn(gy, gy);
+#pragma unroll
+          for (int j = 0; j < DW; j++) {
+            const int t = q - j - RI;
+            if (t >= -RI && t <= RI) {
+              const float2 w = f2s(kc.wir[t < 0 ? -t : t]);
+              a0[j] = __ffma2_rn(w, pa, a0[j]); b0[j] = __ffma2_rn(w, pb, b0[j]); c0[j] = __ffma2_rn(w, pc, c0[j]);
+            }
+          }
+        }
+        store_item(g, r, a0, b0, c0);
+      };
+      // Regular ranges of a border tile: group g is regular in x iff all its NPOS product columns x0-RI+DW*g+q lie in
+      // [1, nx-2]; row pair r iff its two product rows y0-RI+2r, +1 lie in [1, ny-2].  Interior tiles: everything.
+      int gb0 = 0, gb1 = GROUPS, rb0 = 0, rb1 = RPS;
+      if (generic) {
+        gb0 = max(0, (RI + 1 - x0 + DW - 1) / DW);
+        const int gx_hi = nx - 2 - (NPOS - 1) - x0 + RI;          // largest regular DW*g
+        gb1 = gx_hi < 0 ? 0 : min(GROUPS, gx_hi / DW + 1);
+        rb0 = max(0, (RI + 1 - y0 + 1) / 2);
+        const int ry_hi = ny - 3 - y0 + RI;                        // largest regular 2r
+        rb1 = ry_hi < 0 ? 0 : min(RPS, ry_hi / 2 + 1);
+        if (gb1 < gb0) gb1 = gb0;
+        if (rb1 < rb0) rb1 = rb0;
+      }
+      for (int it = tid; it < RPS_PAD * GROUPS; it += C::NT) {
+        const int g = it / RPS_PAD, r = it - g * RPS_PAD;
+        if (r >= rb1 || r < rb0 || g < gb0 || g >= gb1) continue;
+        fast_item(g, r);
+      }
+      if (generic) {   // the irregular items, densely packed over the threads: whole groups first, then the irregular row pairs of regular groups
+        const int ng = gb1 - gb0, nbg = GROUPS - ng, nbr = RPS - (rb1 - rb0);
+        const int n_irr = nbg * RPS + ng * nbr;
+        for (int j = tid; j < n_irr; j += C::NT) {
+          int g, r;
+          if (j < nbg * RPS) {
+            const int gi = j / RPS;
+            r = j - gi * RPS;
+            g = gi < gb0 ? gi : gb1 + (gi - gb0);
+          } else {
+            const int j2 = j - nbg * RPS, ri = j2 / ng;
+            g = gb0 + (j2 - ri * ng);
+            r = ri < rb0 ? ri : rb1 + (ri - rb0);
+          }
+          remapped_item(g, r);
+        }
       }
     }
     __syncthreads();

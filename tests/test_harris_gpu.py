@@ -120,10 +120,10 @@ def _trace_plane(oracle, Is, grad, sigma_i=2.5):
     return oracle.harris_gaussian((gx * gx + gy * gy).astype(np.float32), sigma_i).astype(np.float64)
 
 
-@pytest.mark.parametrize("tile,tma", [(64, 0), (64, 1), (108, 0), (108, 1)])
+@pytest.mark.parametrize("tile,tma", [(64, 0), (48, 0), (64, 1)])
 @pytest.mark.parametrize("shape", [(216, 320), (333, 517), (540, 960), (1080, 1920)])
 def test_fused_plane_within_certified_bound_for_every_kernel_shape(oracle, shape, tile, tma, monkeypatch):
-    """Every tile configuration of the fused kernel (64- and 108-row tiles, register-staged and TMA-staged input,
+    """Every tile configuration of the fused kernel (64- and 48-row tiles, register-staged and TMA-staged input,
     aligned and unaligned widths, border tiles): identical planes, each pixel within the certified per-block bound
     of the oracle's R, and the bound itself below 1e-3 of the local response scale in the bulk."""
     import torch

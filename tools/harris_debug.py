@@ -30,8 +30,8 @@ def plane(frames, **env):
 for (ny, nx) in [(216, 320), (333, 517), (1080, 1920)]:
     f = np.stack([synth.frame_shapes(900 + i, ny, nx) for i in range(2)])
     Ro = np.stack([po.harris_response(f[i], grad=0, measure=0)[0] for i in range(2)])
-    for tile in (64, 108):
-        for tma in (0, 1):
+    for tile, tma in ((64, 0), (48, 0), (64, 1)):
+        if True:
             try:
                 R, eps = plane(f, B2F_HARRIS_TILE=tile, B2F_HARRIS_TMA=tma)
             except Exception as ex:
