@@ -82,6 +82,13 @@ def load():
         ("b2f_fhog_dev", [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
         ("b2f_surf_host", [vp, vp, C.c_int, C.c_int, C.c_long, C.c_double, C.POINTER(C.POINTER(SurfPoint)), ip]),
         ("b2f_surf_batch", [vp, vp, C.c_int, C.c_int, C.c_int, C.c_long, C.c_double, C.c_int, vp, vp]),
+        ("b2f_lsd_front_size", [C.c_int, C.c_int, C.c_double, ip, ip]),
+        ("b2f_lsd_front_host", [vp, vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, vp, vp, vp, ip, vp]),
+        ("b2f_lsd_front_dev", [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, vp, vp, vp, vp, vp]),
+        ("b2f_contour_edge_points_host", [vp, vp, C.c_int, C.c_int, C.c_double, vp, C.POINTER(ip), C.POINTER(C.POINTER(C.c_double)),
+                                          C.POINTER(C.POINTER(C.c_double)), C.POINTER(C.POINTER(C.c_double)), C.POINTER(C.POINTER(C.c_double)), ip]),
+        ("b2f_contour_edge_points_batch_u8", [vp, vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, vp, vp, vp, vp, vp, vp]),
+        ("b2f_contour_edge_points_dev", [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]),
     ]:
         if hasattr(lib, name):
             getattr(lib, name).argtypes = args
@@ -149,4 +156,6 @@ EXPORTS = [
     "b2f_harris_response_eps_dev", "b2f_canny_host", "b2f_canny_batch", "b2f_canny_dev",
     "b2f_fhog_size", "b2f_fhog_host", "b2f_fhog_batch", "b2f_fhog_dev", "b2f_surf_host", "b2f_surf_batch",
     "b2f_otsu_host", "b2f_otsu_batch_u8", "b2f_otsu_dev",
+    "b2f_lsd_front_size", "b2f_lsd_front_host", "b2f_lsd_front_dev",
+    "b2f_contour_edge_points_host", "b2f_contour_edge_points_batch_u8", "b2f_contour_edge_points_dev",
 ]

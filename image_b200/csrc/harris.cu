@@ -941,6 +941,14 @@ int harris_nms_device(b2f_ctx *ctx, const float *d_R, int n_frames, int nx, int 
   return B2F_OK;
 }
 
+int mask_row_offsets(b2f_ctx *ctx, const unsigned *mask, int *row_off, int *d_counts, int n_frames, int ny, int wpr, cudaStream_t st) {
+  row_count_kernel<<<dim3(ceil_div(ny, 8), n_frames), 256, 0, st>>>(mask, row_off, ny, wpr);
+  B2F_LAUNCH_CHECK(ctx);
+  row_scan_kernel<<<n_frames, 1024, 0, st>>>(row_off, d_counts, ny);
+  B2F_LAUNCH_CHECK(ctx);
+  return B2F_OK;
+}
+
 // ---- certified corners on the fast path ---------------------------------------------------------
 bool harris_certified_supported(int nx, int ny, const b2f_harris_params *p) {
   if (!harris_fused_supported(nx, ny, p->sigma_d, p->sigma_i, p->gaussian)) return false;

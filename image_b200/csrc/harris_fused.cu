@@ -127,6 +127,10 @@ int harris_fused_launch(b2f_ctx *ctx, const void *d_frames, bool u8, int n_frame
   const bool tall = cfg_env ? (cfg_env == 48) : false;
   const bool tma_ok = u8 && aligned && (nx % 16 == 0) && (((size_t)nx * ny) % 16 == 0) && encode_tiled_fn() != nullptr;
   const bool tma = tma_ok && (tma_env < 0 ? true : tma_env != 0);
+  if (cfg_env == 488) {   // 48-row tiles, stage-D items of 8 outputs (exactly one pass), 2 CTAs / SM
+    using C = Fused3Cfg<3, 7, 48, 256, 8, 2>;
+    return launch_shape<C, false>(ctx, d_frames, u8, grad, n_frames, nx, ny, d_R, d_eps, generic_all, false, kc, st);
+  }
   if (tall) {
     using C = Fused3Cfg<3, 7, 48, 256, 4, 3>;
     return launch_shape<C, false>(ctx, d_frames, u8, grad, n_frames, nx, ny, d_R, d_eps, generic_all, false, kc, st);

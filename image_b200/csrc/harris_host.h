@@ -19,6 +19,8 @@ int harris_corners_certified(b2f_ctx *ctx, const void *d_frames, bool u8, int n_
 int harris_cert_stats(b2f_ctx *ctx, unsigned long long out[4], cudaStream_t st);
 int harris_nms_device(b2f_ctx *ctx, const float *d_R, int n_frames, int nx, int ny, float Th, int radius, int cap,
                       int *d_xy, float *d_strength, int *d_counts, cudaStream_t st);
+// bit mask [n_frames][ny][wpr] -> exclusive per-row offsets of the set bits (row_off) and per-frame totals (d_counts)
+int mask_row_offsets(b2f_ctx *ctx, const unsigned *mask, int *row_off, int *d_counts, int n_frames, int ny, int wpr, cudaStream_t st);
 int harris_gather3x3(b2f_ctx *ctx, const float *d_R, const int *d_xy, float *d_M, int n, int nx, cudaStream_t st);
 int harris_decimate2(b2f_ctx *ctx, const float *d_src, float *d_dst, int nx, int ny, cudaStream_t st);
 int harris_u8_to_float(b2f_ctx *ctx, const unsigned char *s, float *d, size_t n, cudaStream_t st);

@@ -394,8 +394,13 @@ harris_fused3_kernel(const void *__restrict__ frames, float *__restrict__ Rout, 
       constexpr int RGS = (C::IS_H + RB - 1) / RB;
       constexpr int OFFR = C::HALO - C::G - RD;                // Is row 0 (global y0-G) uses R1 rows OFFR .. OFFR+2RD
       static_assert(OFFR >= 0 && RB % 2 == 0, "R1 must cover the taps of Is row 0; item rows start even");
+      // items: first the column pairs 0..31 of every row group (a warp = one row group: conflict-free 8-byte loads),
+      // then the remaining CP-32 column pairs (a warp spans several row groups there: a small conflicted tail)
+      constexpr int MAIN = 32 * RGS, TAILW = CP - 32;
       for (int it = tid; it < CP * RGS; it += C::NT) {
-        const int rg = it / CP, cp = it - rg * CP;
+        int rg, cp;
+        if (it < MAIN) { rg = it >> 5; cp = it & 31; }
+        else { const int u = it - MAIN; rg = u / TAILW; cp = 32 + (u - rg * TAILW); }
         const int row0 = rg * RB + OFFR;                       // parity of row0 + q is compile-time per q (RB even)
         float2 acc[RB];
 #pragma unroll
@@ -573,7 +578,8 @@ harris_fused3_kernel(const void *__restrict__ frames, float *__restrict__ Rout, 
       for (int w = 0; w < C::NT / 32; w++) Mtile = fmaxf(Mtile, sM[w]);
       for (int it = tid; it < CP * C::E_NRG; it += C::NT) {
         const int rg = it / CP, cp = it - rg * CP;
-        const int r0 = min(rg * RB, C::TH - RB);               // the last groups may overlap (TH not a multiple of RB)
+        // the last groups may overlap when TH is not a multiple of RB; otherwise r0 is even at compile time (row parity known)
+        const int r0 = (C::TH % RB == 0) ? rg * RB : min(rg * RB, C::TH - RB);
         float2 aa[RB], ab[RB], ac[RB];
 #pragma unroll
         for (int j = 0; j < RB; j++) { aa[j] = f2s(0.f); ab[j] = f2s(0.f); ac[j] = f2s(0.f); }

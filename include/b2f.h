@@ -151,6 +151,43 @@ int b2f_surf_host(b2f_ctx *ctx, const uint8_t *rgb, int rows, int cols, long max
 int b2f_surf_batch(b2f_ctx *ctx, const uint8_t *frames, int n_frames, int rows, int cols, long max_points,
                    double detection_threshold, int cap, b2f_surf_point *points, int *counts);
 
+/* ------------------------------------------------------------------- ContourDetector ----
+ * SURVEY.md 8f "next", rank 1: the data-parallel front end of smooth_contours() (image.ContourDetector/src/
+ * smooth_contours.c: gaussian_filter :184-262, compute_gradient :339-356, compute_edge_points :427-505).
+ * The reference materialises seven double planes for its sequential chainer; here the planes stay on the device
+ * and the COMPACT list of edge points comes back, in raster order: idx = x + y*X, (ex, ey) the sub-pixel position
+ * (Ex, Ey of the reference), (gx, gy) the gradient there (all that chain() :289-336 reads).  Every value is
+ * bit-identical to the reference's doubles.  sigma <= 0 selects the reference's own sigma (:1466-1479).
+ * `gauss` (optional) receives the blurred image for `diff = image - gauss` (:1498).  image[x + y*X] as in the reference.
+ * b2f_contour_edge_points_host mallocs its five outputs (b2f_free); the batch / dev forms (new surface, u8 or double
+ * frames) write at most `cap` records per frame at [f*cap + i] and the true count to counts[f] (B2F_ECAP if any exceeds). */
+int b2f_contour_edge_points_host(b2f_ctx *ctx, const double *image, int X, int Y, double sigma, double *gauss, int **idx,
+                                 double **ex, double **ey, double **gx, double **gy, int *n);
+int b2f_contour_edge_points_batch_u8(b2f_ctx *ctx, const uint8_t *frames, int n_frames, int X, int Y, double sigma, int cap,
+                                     int *idx, double *ex, double *ey, double *gx, double *gy, int *counts);
+int b2f_contour_edge_points_dev(b2f_ctx *ctx, const void *d_frames, int is_u8, int n_frames, int X, int Y, double sigma, int cap,
+                                int *d_idx, double *d_ex, double *d_ey, double *d_gx, double *d_gy, int *d_counts, double *d_gauss,
+                                void *stream);
+
+/* --------------------------------------------------------------- LineSegmentDetector ----
+ * SURVEY.md 8f "next", rank 2: the data-parallel front end of LineSegmentDetection() (image.LineSegmentDetector/src/
+ * lsd.c: gaussian_sampler :603-720 and ll_angle :744-880, called at :2455-2462).  For an X x Y image (image[x + y*X])
+ * the outputs live on the scaled grid N x M = ceil(X*scale) x ceil(Y*scale) (b2f_lsd_front_size):
+ *   angles  [y*N + x]  level-line angle, or NOTDEF = -1024.0 where modgrad <= quant / sin(pi*ang_th/180)
+ *   modgrad [y*N + x]  gradient modulus (0 in the last row / column, which the reference leaves unset)
+ *   list               the (N-1)(M-1) gradient pixels as x + y*N, in the order of the reference's bucket list
+ *                      (n_bins buckets of modgrad*n_bins/max_grad, highest first; inside a bucket x outer, y inner)
+ *   scaled  (optional) the sub-sampled image.
+ * modgrad, the NOTDEF pattern and the list order are bit-identical to the reference; defined angles differ from libm's
+ * atan2 by at most a few ulp.  The Rcpp defaults are scale 0.8, sigma_scale 0.6, quant 2, ang_th 22.5, n_bins 1024
+ * (line_segment_detector.cpp:8-21).  The `_dev` form takes n_frames u8 or double frames resident in HBM. */
+int b2f_lsd_front_size(int X, int Y, double scale, int *N, int *M);
+int b2f_lsd_front_host(b2f_ctx *ctx, const double *image, int X, int Y, double scale, double sigma_scale, double quant,
+                       double ang_th, int n_bins, double *angles, double *modgrad, int *list, int *list_len, double *scaled);
+int b2f_lsd_front_dev(b2f_ctx *ctx, const void *d_frames, int is_u8, int n_frames, int X, int Y, double scale,
+                      double sigma_scale, double quant, double ang_th, int n_bins, double *d_angles, double *d_modgrad,
+                      int *d_list, double *d_scaled, void *stream);
+
 /* -------------------------------------------------------------------------------- Otsu ----
  * SURVEY.md 8f "next", rank 4.  Replaces the body of otsu() (image.Otsu/src/rcpp_otsu.cpp:166-186:
  * computeHistogram :63-81, computeOtsusSegmentation :113-163, segmentImage :88-105).

@@ -30,7 +30,7 @@ _cache = {}
 
 
 def lib(name):
-    """name in {'oracle','ref_harris','ref_canny','ref_dlib','ref_otsu'}; None if that .so is absent."""
+    """name in {'oracle','ref_harris','ref_canny','ref_dlib','ref_otsu','ref_contour','ref_lsd'}; None if that .so is absent."""
     if name not in _cache:
         p = os.path.join(HERE, "liboracle.so") if name == "oracle" else os.path.join(HERE, "_ref", "lib%s.so" % name)
         _cache[name] = _load(p)
@@ -204,6 +204,133 @@ def surf(rgb, max_points=1000, thr=30.0, impl="oracle"):
     return out
 
 # ------------------------------------------------------------------------------------------ fixtures
+
+
+# ------------------------------------------------------------------------------------------ ContourDetector front end
+def contour_sigma():
+    """smooth_contours.c:1466-1479: sigma_step * sqrt(dog_rate^2 - 1)."""
+    return float(0.8 * np.sqrt(np.float64(1.6) * np.float64(1.6) - 1.0))
+
+
+def contour_gaussian(img, sigma=None, impl="oracle"):
+    """gaussian_filter (smooth_contours.c:184-262) of a [Y, X] image -> float64 [Y, X]."""
+    I = np.ascontiguousarray(img, dtype=np.float64)
+    Y, X = I.shape
+    out = np.zeros((Y, X), np.float64)
+    s = contour_sigma() if sigma is None else float(sigma)
+    if impl == "ref":
+        lib("ref_contour").ref_contour_gaussian(_p(I), X, Y, f64(s), _p(out))
+    else:
+        lib("oracle").orc_contour_gaussian(_p(I), X, Y, f64(s), _p(out))
+    return out
+
+
+def contour_edge_points(gauss, impl="oracle"):
+    """compute_gradient + compute_edge_points on the blurred image -> dict(idx, Ex, Ey, Gx, Gy) in raster order."""
+    g = np.ascontiguousarray(gauss, dtype=np.float64)
+    Y, X = g.shape
+    if impl == "ref":
+        planes = [np.zeros((Y, X), np.float64) for _ in range(5)]
+        Gx, Gy, modG, Ex, Ey = planes
+        lib("ref_contour").ref_contour_edge_points(_p(g), X, Y, _p(Gx), _p(Gy), _p(modG), _p(Ex), _p(Ey))
+        idx = np.flatnonzero((Ex.ravel() >= 0) & (Ey.ravel() >= 0)).astype(np.int32)
+        return dict(idx=idx, Ex=Ex.ravel()[idx], Ey=Ey.ravel()[idx], Gx=Gx.ravel()[idx], Gy=Gy.ravel()[idx])
+    cap = X * Y
+    idx = np.zeros(cap, np.int32)
+    Ex = np.zeros(cap); Ey = np.zeros(cap); Gx = np.zeros(cap); Gy = np.zeros(cap)
+    fn = lib("oracle").orc_contour_edge_points
+    fn.restype = C.c_int
+    n = fn(_p(g), X, Y, _p(idx), _p(Ex), _p(Ey), _p(Gx), _p(Gy), cap)
+    return dict(idx=idx[:n].copy(), Ex=Ex[:n].copy(), Ey=Ey[:n].copy(), Gx=Gx[:n].copy(), Gy=Gy[:n].copy())
+
+
+def contour_chain_ref(Ex, Ey, Gx, Gy):
+    """The reference's sequential chainer on given [Y, X] planes -> (x, y, curve_limits)."""
+    planes = [np.ascontiguousarray(p, dtype=np.float64).copy() for p in (Ex, Ey, Gx, Gy)]
+    Y, X = planes[0].shape
+    cap = X * Y
+    x = np.zeros(cap); y = np.zeros(cap)
+    lim = np.zeros(cap + 1, np.int32)
+    M = C.c_int(0)
+    fn = lib("ref_contour").ref_contour_chain_from_planes
+    fn.restype = C.c_int
+    n = fn(_p(planes[0]), _p(planes[1]), _p(planes[2]), _p(planes[3]), X, Y, _p(x), _p(y), cap, _p(lim), cap, C.byref(M))
+    return x[:n].copy(), y[:n].copy(), lim[:M.value + 1].copy()
+
+
+def contour_planes_ref(gauss):
+    """compute_gradient + compute_edge_points of the reference -> full planes (Ex, Ey, Gx, Gy)."""
+    g = np.ascontiguousarray(gauss, dtype=np.float64)
+    Y, X = g.shape
+    Gx, Gy, modG, Ex, Ey = [np.zeros((Y, X), np.float64) for _ in range(5)]
+    lib("ref_contour").ref_contour_edge_points(_p(g), X, Y, _p(Gx), _p(Gy), _p(modG), _p(Ex), _p(Ey))
+    return Ex, Ey, Gx, Gy
+
+
+def contour_detect_ref(img, Q=2.0):
+    """The whole reference detector (smooth_contours) -> (x, y, curve_limits)."""
+    I = np.ascontiguousarray(img, dtype=np.float64)
+    Y, X = I.shape
+    cap = X * Y
+    x = np.zeros(cap); y = np.zeros(cap)
+    lim = np.zeros(cap + 1, np.int32)
+    M = C.c_int(0)
+    fn = lib("ref_contour").ref_contour_detect
+    fn.restype = C.c_int
+    n = fn(_p(I), X, Y, f64(Q), _p(x), _p(y), cap, _p(lim), cap, C.byref(M))
+    return x[:n].copy(), y[:n].copy(), lim[:M.value + 1].copy()
+
+
+# ------------------------------------------------------------------------------------------ LSD front end
+def lsd_rho(quant=2.0, ang_th=22.5):
+    """lsd.c:2449-2451: gradient magnitude threshold quant / sin(pi ang_th / 180)."""
+    return float(quant / np.sin(np.pi * ang_th / 180.0))
+
+
+def lsd_sampler(img, scale=0.8, sigma_scale=0.6, impl="oracle"):
+    """gaussian_sampler (lsd.c:603-720): [Y, X] -> float64 [ceil(Y*scale), ceil(X*scale)]."""
+    I = np.ascontiguousarray(img, dtype=np.float64)
+    Y, X = I.shape
+    N, M = int(np.ceil(X * scale)), int(np.ceil(Y * scale))
+    out = np.zeros((M, N), np.float64)
+    if impl == "ref":
+        n, m = C.c_int(0), C.c_int(0)
+        lib("ref_lsd").ref_lsd_sampler(_p(I), X, Y, f64(scale), f64(sigma_scale), _p(out), C.byref(n), C.byref(m))
+        assert (n.value, m.value) == (N, M)
+    else:
+        lib("oracle").orc_lsd_sampler(_p(I), X, Y, f64(scale), f64(sigma_scale), _p(out))
+    return out
+
+
+def lsd_ll_angle(img, threshold=None, n_bins=1024, impl="oracle"):
+    """ll_angle (lsd.c:744-880) -> (angles [Y,X], modgrad [Y,X], list of linear indices x + y*X in list order)."""
+    I = np.ascontiguousarray(img, dtype=np.float64)
+    Y, X = I.shape
+    th = lsd_rho() if threshold is None else float(threshold)
+    ang = np.zeros((Y, X)); mod = np.zeros((Y, X))
+    if impl == "ref":
+        lx = np.zeros(X * Y, np.int32); ly = np.zeros(X * Y, np.int32)
+        fn = lib("ref_lsd").ref_lsd_ll_angle
+        fn.restype = C.c_int
+        n = fn(_p(I), X, Y, f64(th), int(n_bins), _p(ang), _p(mod), _p(lx), _p(ly))
+        return ang, mod, (lx[:n] + ly[:n] * X).astype(np.int32)
+    lst = np.zeros(X * Y, np.int32)
+    fn = lib("oracle").orc_lsd_ll_angle
+    fn.restype = C.c_int
+    n = fn(_p(I), X, Y, f64(th), int(n_bins), _p(ang), _p(mod), _p(lst))
+    return ang, mod, lst[:n].copy()
+
+
+def lsd_detect_ref(img):
+    """The whole reference detector with the Rcpp defaults -> [n, 7] float64."""
+    I = np.ascontiguousarray(img, dtype=np.float64)
+    Y, X = I.shape
+    cap = 200000
+    out = np.zeros((cap, 7))
+    fn = lib("ref_lsd").ref_lsd_detect
+    fn.restype = C.c_int
+    n = fn(_p(I), X, Y, _p(out), cap)
+    return out[:n].copy()
 
 
 def read_pgm_ascii(path):

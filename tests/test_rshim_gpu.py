@@ -17,8 +17,13 @@ def shim(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("shim") / "libshim.so")
     rs = os.path.join(ROOT, "image_b200", "rshim")
     srcs = [os.path.join(rs, f) for f in ("rcpp_harris.cpp", "rcpp_canny.cpp", "rcpp_fhog.cpp", "rcpp_surf.cpp", "rcpp_otsu.cpp")]
+    objs = []
+    for f in ("contour_front.c", "lsd_front.c"):                      # the two plain-C front-end shims
+        o = str(tmp_path_factory.mktemp("obj") / (f + ".o"))
+        subprocess.check_call(["gcc", "-O1", "-fPIC", "-c", "-I" + os.path.join(ROOT, "include"), os.path.join(rs, f), "-o", o])
+        objs.append(o)
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "oracle", "stubs"),
-                           "-I" + os.path.join(ROOT, "include"), "-I" + rs, os.path.join(ROOT, "tests", "rshim_harness.cpp")] + srcs +
+                           "-I" + os.path.join(ROOT, "include"), "-I" + rs, os.path.join(ROOT, "tests", "rshim_harness.cpp")] + srcs + objs +
                           ["-L" + os.path.join(ROOT, "image_b200"), "-lb200feat", "-Wl,-rpath," + os.path.join(ROOT, "image_b200"), "-o", out])
     return C.CDLL(out)
 
@@ -81,3 +86,53 @@ def test_otsu_shim(shim, oracle):
     t = shim.shim_otsu(_p(img.ravel()), 140, 90, 0, _p(out))
     o, ot = oracle.otsu(img.ravel(), 140, 90, 0)
     assert t == ot and np.array_equal(out, o)
+
+
+def test_contour_front_shim_feeds_the_reference_chainer(shim, oracle):
+    """b2f_contour_front (rshim/contour_front.c) rebuilds the planes the reference's sequential chainer reads: Ex / Ey equal
+    the reference's planes everywhere, Gx / Gy at every edge point, and the reference's own chain_edge_points ->
+    simplify_chains -> list_chained_edge_points run on them gives the same curves as on the reference's planes."""
+    from image_b200 import synth
+    Y, X = 150, 230
+    img = synth.frame_shapes(24, Y, X).astype(np.float64)
+    gauss = np.zeros((Y, X)); Gx = np.zeros((Y, X)); Gy = np.zeros((Y, X)); Ex = np.zeros((Y, X)); Ey = np.zeros((Y, X))
+    shim.b2f_contour_front.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double] + [C.c_void_p] * 5
+    assert shim.b2f_contour_front(_p(img), X, Y, 0.0, _p(gauss), _p(Gx), _p(Gy), _p(Ex), _p(Ey)) == 0
+    g = oracle.contour_gaussian(img)
+    assert np.array_equal(gauss, g)
+    r = oracle.contour_edge_points(g)
+    ex = np.full(X * Y, -1.0); ey = np.full(X * Y, -1.0)
+    ex[r["idx"]] = r["Ex"]; ey[r["idx"]] = r["Ey"]
+    assert np.array_equal(Ex.ravel(), ex) and np.array_equal(Ey.ravel(), ey)
+    assert np.array_equal(Gx.ravel()[r["idx"]], r["Gx"]) and np.array_equal(Gy.ravel()[r["idx"]], r["Gy"])
+    if oracle.have_ref("contour"):
+        rEx, rEy, rGx, rGy = oracle.contour_planes_ref(g)
+        a = oracle.contour_chain_ref(Ex, Ey, Gx, Gy)
+        b = oracle.contour_chain_ref(rEx, rEy, rGx, rGy)
+        assert len(b[0]) > 100
+        for u, v in zip(a, b):
+            assert np.array_equal(u, v)
+
+
+def test_lsd_front_shim_builds_the_ordered_chain(shim, oracle):
+    from image_b200 import synth
+
+    class Cell(C.Structure):
+        pass
+    Cell._fields_ = [("x", C.c_int), ("y", C.c_int), ("next", C.POINTER(Cell))]
+    Y, X = 120, 170
+    img = synth.frame_shapes(25, Y, X).astype(np.float64)
+    N, M = int(np.ceil(X * 0.8)), int(np.ceil(Y * 0.8))
+    ang = np.zeros((M, N)); mod = np.zeros((M, N))
+    head = C.POINTER(Cell)(); mem = C.c_void_p()
+    shim.b2f_lsd_front.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.POINTER(C.POINTER(Cell)), C.POINTER(C.c_void_p)]
+    assert shim.b2f_lsd_front(_p(img), X, Y, 0.8, 0.6, 2.0, 22.5, 1024, _p(ang), _p(mod), C.byref(head), C.byref(mem)) == 0
+    a, m, lst = oracle.lsd_ll_angle(oracle.lsd_sampler(img))
+    assert np.array_equal(mod, m) and np.array_equal(ang == -1024.0, a == -1024.0)
+    got, p = [], head
+    while p:
+        got.append(p.contents.x + p.contents.y * N)
+        p = p.contents.next
+    assert np.array_equal(np.array(got, np.int32), lst)
+    C.CDLL(None).free(mem)
