@@ -31,6 +31,10 @@ class HarrisParams(C.Structure):
                 ("verbose", C.c_int), ("exact", C.c_int)]
 
 
+class CannyParams(C.Structure):
+    _fields_ = [("s", C.c_double), ("low_thr", C.c_double), ("high_thr", C.c_double), ("acc_grad", C.c_int)]
+
+
 class SurfPoint(C.Structure):
     _fields_ = [("x", C.c_double), ("y", C.c_double), ("angle", C.c_double), ("scale", C.c_double),
                 ("score", C.c_double), ("laplacian", C.c_double), ("des", C.c_double * 64)]
@@ -82,6 +86,8 @@ def load():
         ("b2f_fhog_dev", [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
         ("b2f_surf_host", [vp, vp, C.c_int, C.c_int, C.c_long, C.c_double, C.POINTER(C.POINTER(SurfPoint)), ip]),
         ("b2f_surf_batch", [vp, vp, C.c_int, C.c_int, C.c_int, C.c_long, C.c_double, C.c_int, vp, vp]),
+        ("b2f_features_batch_rgb", [vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(HarrisParams), C.c_int, vp, vp, vp, vp,
+                                    C.POINTER(CannyParams), vp, vp, C.c_int, C.c_int, C.c_int, vp]),
         ("b2f_lsd_front_size", [C.c_int, C.c_int, C.c_double, ip, ip]),
         ("b2f_lsd_front_host", [vp, vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, vp, vp, vp, ip, vp]),
         ("b2f_lsd_front_dev", [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, vp, vp, vp, vp, vp]),
@@ -156,6 +162,6 @@ EXPORTS = [
     "b2f_harris_response_eps_dev", "b2f_canny_host", "b2f_canny_batch", "b2f_canny_dev",
     "b2f_fhog_size", "b2f_fhog_host", "b2f_fhog_batch", "b2f_fhog_dev", "b2f_surf_host", "b2f_surf_batch",
     "b2f_otsu_host", "b2f_otsu_batch_u8", "b2f_otsu_dev",
-    "b2f_lsd_front_size", "b2f_lsd_front_host", "b2f_lsd_front_dev",
+    "b2f_features_batch_rgb", "b2f_lsd_front_size", "b2f_lsd_front_host", "b2f_lsd_front_dev",
     "b2f_contour_edge_points_host", "b2f_contour_edge_points_batch_u8", "b2f_contour_edge_points_dev",
 ]

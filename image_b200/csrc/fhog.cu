@@ -621,6 +621,21 @@ static int fhog_check(const char *who, int rows, int cols, int cell, int frp, in
   return B2F_OK;
 }
 
+// geometry-free wrappers for features.cu (the combined Harris + Canny + FHOG batch)
+size_t fhog_scratch_simple(int n_frames, int rows, int cols, int cell, int frp, int fcp, int *out_nr, int *out_nc) {
+  FhogGeom g;
+  if (!fhog_geometry(rows, cols, cell, frp, fcp, g)) { *out_nr = *out_nc = 0; return 0; }
+  *out_nr = g.out_nr; *out_nc = g.out_nc;
+  return fhog_scratch_bytes(n_frames, g);
+}
+int fhog_device_simple(b2f_ctx *ctx, const unsigned char *d_frames, int n_frames, int rows, int cols, int cell, int frp, int fcp,
+                       float *d_out, cudaStream_t st) {
+  FhogGeom g;
+  if (!fhog_geometry(rows, cols, cell, frp, fcp, g)) return B2F_OK;
+  return fhog_device(ctx, d_frames, n_frames, g, d_out, st);
+}
+int fhog_check_args(const char *who, int rows, int cols, int cell, int frp, int fcp) { return fhog_check(who, rows, cols, cell, frp, fcp); }
+
 }  // namespace b2f
 
 using namespace b2f;

@@ -151,6 +151,18 @@ int b2f_surf_host(b2f_ctx *ctx, const uint8_t *rgb, int rows, int cols, long max
 int b2f_surf_batch(b2f_ctx *ctx, const uint8_t *frames, int n_frames, int rows, int cols, long max_points,
                    double detection_threshold, int cap, b2f_surf_point *points, int *counts);
 
+/* ------------------------------------------------------------------ combined batch ----
+ * New surface: Harris corners + Canny edge map + FHOG from ONE upload of each interleaved RGB frame (rows x cols x 3).
+ * The grey plane Harris and Canny work on is derived on the device with dlib's rule (r + g + b) / 3 (pixel.h:775-783).
+ * Results are those of the single-detector batch calls on the same frames / that grey plane.  Pass hp = NULL,
+ * cp = NULL or cell_size = 0 to skip a detector.  Harris: raster-ordered corners (strategy 0, precision 0, one scale),
+ * at most corner_cap per frame at [f*corner_cap + i]; Canny: edges rows*cols bytes per frame; FHOG: b2f_fhog_size floats. */
+typedef struct { double s, low_thr, high_thr; int acc_grad; } b2f_canny_params;
+int b2f_features_batch_rgb(b2f_ctx *ctx, const uint8_t *rgb, int n_frames, int rows, int cols,
+                           const b2f_harris_params *hp, int corner_cap, float *cx, float *cy, float *cs, int *ccounts,
+                           const b2f_canny_params *cp, uint8_t *edges, int *nonzero,
+                           int cell_size, int filter_rows_padding, int filter_cols_padding, float *hog);
+
 /* ------------------------------------------------------------------- ContourDetector ----
  * SURVEY.md 8f "next", rank 1: the data-parallel front end of smooth_contours() (image.ContourDetector/src/
  * smooth_contours.c: gaussian_filter :184-262, compute_gradient :339-356, compute_edge_points :427-505).

@@ -101,3 +101,33 @@ def test_three_detectors_from_three_threads(oracle):
     assert np.array_equal(out["fhog"][5], oracle.fhog(rgb[5]))
     for c in ctxs:
         lib.b2f_shutdown(c)
+
+
+def test_combined_rgb_batch_equals_the_single_detector_calls(oracle):
+    """b2f_features_batch_rgb: one upload of the RGB frames, grey derived on the device; results equal the three
+    single-detector batch calls (and therefore the oracle) — also for a frame size whose planes are not 16-byte multiples
+    and with a chunk size that cuts the batch."""
+    from image_b200 import synth, harris_batch_u8, _lib
+    from image_b200.canny import canny_batch
+    from image_b200.dlib import fhog_batch
+    from image_b200.features import features_batch
+    lib = _lib.load()
+    for (rows, cols) in [(216, 320), (131, 203)]:
+        rgb = np.stack([synth.frame_rgb(40 + i, rows, cols) for i in range(5)])
+        grey = (rgb.astype(np.uint16).sum(axis=3) // 3).astype(np.uint8)
+        lib.b2f_set_chunk_bytes(_lib.context(), 2 * rows * cols * 3)
+        try:
+            o = features_batch(rgb, harris=dict(threshold=60.0), canny=dict(s=2.0, low_thr=3.0, high_thr=10.0, accGrad=True), fhog=dict(cell=8))
+        finally:
+            lib.b2f_set_chunk_bytes(_lib.context(), 24 << 20)
+        hs = harris_batch_u8(grey, threshold=60.0)
+        e, nz = canny_batch(grey, accGrad=True)
+        h = fhog_batch(rgb)
+        x, y, s, cnt = o["corners"]
+        for i in range(5):
+            assert cnt[i] == len(hs[i]["x"]) and np.array_equal(x[i, :cnt[i]], hs[i]["x"]) and np.array_equal(y[i, :cnt[i]], hs[i]["y"])
+            assert np.array_equal(s[i, :cnt[i]], hs[i]["strength"])
+        assert np.array_equal(o["edges"], e) and np.array_equal(o["nonzero"], nz)
+        assert np.array_equal(o["hog"], h)
+        ox, oy, os_ = oracle.harris_detect(grey[2], threshold=60.0, gaussian=0, precision=0)
+        assert np.array_equal(x[2, :cnt[2]], ox) and np.array_equal(s[2, :cnt[2]], os_)
