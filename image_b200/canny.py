@@ -64,11 +64,3 @@ def canny_dev(d_frames, n_frames, nx, ny, d_edges, d_nonzero, s=2.0, low_thr=3.0
     _lib.check(lib.b2f_canny_dev(ctx or _lib.context(), _lib.ptr(d_frames), n_frames, nx, ny, float(s), float(low_thr),
                                  float(high_thr), int(bool(accGrad)), _lib.ptr(d_edges), _lib.ptr(d_nonzero),
                                  _lib.ptr(stream) if stream is not None else None))
-
-
-def smoke_check(po):
-    from . import synth
-    img = synth.frame_shapes(2, 80, 120)
-    out = image_canny_edge_detector(img.T)
-    e, nz = po.canny(img, impl="oracle")
-    assert nz == out["pixels_nonzero"] and np.array_equal(out["edges"].T == 255, e == 255), "Canny edge map differs from the oracle"

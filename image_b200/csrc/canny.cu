@@ -1148,12 +1148,11 @@ int canny_device(b2f_ctx *ctx, const unsigned char *d_frames, int n_frames, int 
       canny_blur_rows_kernel<13><<<dim3(ceil_div(ceil_div(nx, 4), 256), ny, n_frames), 256, 0, st>>>(d_frames, rowsum, nx, ny, tx);
       B2F_LAUNCH_CHECK(ctx);
       const size_t csm = sizeof(double) * (size_t)(CC_TH + 26) * CC_TW;
-      static bool cfg2 = false;
-      if (!cfg2) { B2F_CUDA(cudaFuncSetAttribute(canny_blur_cols_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm)); cfg2 = true; }
+      // function attributes are per device: set on every launch, never cached per process
+      B2F_CUDA(cudaFuncSetAttribute(canny_blur_cols_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
       canny_blur_cols_kernel<13><<<dim3(ceil_div(nx, CC_TW), ceil_div(ny, CC_TH), n_frames), 256, csm, st>>>(rowsum, blur, nx, ny, ty);
     } else if (tx.R == 13 && ty.R == 13) {
-      static bool cfg = false;
-      if (!cfg) { B2F_CUDA(cudaFuncSetAttribute(canny_blur_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = true; }
+      B2F_CUDA(cudaFuncSetAttribute(canny_blur_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       canny_blur_kernel<13><<<grid, CB_NT, smem, st>>>(d_frames, blur, nx, ny, tx, ty);
     } else {
       B2F_CUDA(cudaFuncSetAttribute(canny_blur_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1236,10 +1235,11 @@ int b2f_canny_dev(b2f_ctx *ctx, const uint8_t *d_frames, int n_frames, int nx, i
                   double high_thr, int acc_grad, uint8_t *d_edges, int *d_nonzero, void *stream) {
   if (!ctx || !d_frames || !d_edges || !d_nonzero || n_frames <= 0 || nx <= 0 || ny <= 0) { set_error("b2f_canny_dev: bad argument"); return B2F_EINVAL; }
   B2F_CUDA(cudaSetDevice(ctx->device));
-  int rc = arena_reserve(ctx, canny_scratch_bytes(n_frames, nx, ny));
+  cudaStream_t st;
+  int rc = stream_handoff(ctx, stream, &st);
   if (rc != B2F_OK) return rc;
-  return canny_device(ctx, d_frames, n_frames, nx, ny, s, low_thr, high_thr, acc_grad, d_edges, d_nonzero,
-                      stream ? (cudaStream_t)stream : ctx->stream);
+  if ((rc = arena_reserve(ctx, canny_scratch_bytes(n_frames, nx, ny))) != B2F_OK) return rc;
+  return canny_device(ctx, d_frames, n_frames, nx, ny, s, low_thr, high_thr, acc_grad, d_edges, d_nonzero, st);
 }
 
 int b2f_canny_batch(b2f_ctx *ctx, const uint8_t *frames, int n_frames, int nx, int ny, double s, double low_thr,

@@ -55,6 +55,11 @@ struct b2f_ctx {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  // The scratch arena (and the lazily built tables) are shared by every call on this context; a caller may pass its own
+  // stream to the *_dev entry points.  last_stream is the stream the previous call's work was enqueued on: a call on a
+  // different stream first waits for it (stream_handoff), so scratch still in flight is never overwritten.
+  cudaStream_t last_stream = nullptr, pending_stream = nullptr;
+  cudaEvent_t handoff_event = nullptr;
   b2f::Arena arena;       // device scratch
   void *pinned = nullptr; // pinned host staging
   size_t pinned_cap = 0;
@@ -82,6 +87,8 @@ int pinned_reserve(b2f_ctx *ctx, size_t bytes);
 // the download of chunk c-1 overlap (three streams, events between them).  pipe_prepare makes sure the two
 // copy streams and `n_events` events exist and orders the copy-in stream behind whatever the context
 // stream still has in flight.
+// Resolve the stream of a call (NULL = the context's own) and order it behind the previous call's stream when they differ.
+int stream_handoff(b2f_ctx *ctx, void *user_stream, cudaStream_t *out);
 int pipe_prepare(b2f_ctx *ctx, int n_events);
 int pipe_drain(b2f_ctx *ctx);                       // wait for all three streams (also used on error paths)
 inline int frames_per_chunk(const b2f_ctx *ctx, size_t frame_bytes, int n_frames) {

@@ -201,7 +201,8 @@ int b2f_contour_edge_points_dev(b2f_ctx *ctx, const void *d_frames, int is_u8, i
     set_error("b2f_contour_edge_points_dev: bad argument"); return B2F_EINVAL; }
   if ((long long)X * Y >= (1ll << 31)) { set_error("b2f_contour_edge_points_dev: frame too large"); return B2F_EUNSUP; }
   B2F_CUDA(cudaSetDevice(ctx->device));
-  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  cudaStream_t st;
+  { int hrc = stream_handoff(ctx, stream, &st); if (hrc != B2F_OK) return hrc; }
   int rc = arena_reserve(ctx, contour_scratch_bytes(n_frames, X, Y));
   if (rc != B2F_OK) return rc;
   return contour_edge_points_device(ctx, d_frames, is_u8 != 0, n_frames, X, Y, sigma, cap, d_idx, d_ex, d_ey, d_gx, d_gy, d_counts, d_gauss, st);

@@ -14,7 +14,23 @@ void set_error(const char *fmt, ...) {
   va_end(ap);
 }
 
+static int order_behind_last(b2f_ctx *ctx, cudaStream_t st) {
+  if (ctx->last_stream && ctx->last_stream != st) {
+    if (!ctx->handoff_event) B2F_CUDA(cudaEventCreateWithFlags(&ctx->handoff_event, cudaEventDisableTiming));
+    B2F_CUDA(cudaEventRecord(ctx->handoff_event, ctx->last_stream));
+    B2F_CUDA(cudaStreamWaitEvent(st, ctx->handoff_event, 0));
+  }
+  ctx->last_stream = st;
+  return B2F_OK;
+}
+
 int arena_reserve(b2f_ctx *ctx, size_t bytes) {
+  // The arena is about to be rewound: whatever stream this call runs on (the one a *_dev entry point announced through
+  // stream_handoff, else the context's own, as all host / batch forms use) must run behind the previous call's stream.
+  cudaStream_t target = ctx->pending_stream ? ctx->pending_stream : ctx->stream;
+  ctx->pending_stream = nullptr;
+  int hrc = order_behind_last(ctx, target);
+  if (hrc != B2F_OK) return hrc;
   ctx->arena.reset();
   if (bytes <= ctx->arena.cap) return B2F_OK;
   size_t want = bytes + (bytes >> 4) + (1u << 20);
@@ -49,6 +65,13 @@ int pinned_reserve(b2f_ctx *ctx, size_t bytes) {
   ctx->pinned = p;
   ctx->pinned_cap = bytes;
   return B2F_OK;
+}
+
+int stream_handoff(b2f_ctx *ctx, void *user_stream, cudaStream_t *out) {
+  cudaStream_t st = user_stream ? (cudaStream_t)user_stream : ctx->stream;
+  *out = st;
+  ctx->pending_stream = st;
+  return order_behind_last(ctx, st);
 }
 
 int pipe_prepare(b2f_ctx *ctx, int n_events) {
@@ -121,6 +144,7 @@ void b2f_shutdown(b2f_ctx *c) {
   cudaStreamSynchronize(c->stream);
   if (c->arena.base) cudaFree(c->arena.base);
   if (c->pinned) cudaFreeHost(c->pinned);
+  if (c->handoff_event) cudaEventDestroy(c->handoff_event);
   if (c->harris_stats) cudaFree(c->harris_stats);
   if (c->fhog_lut) cudaFree(c->fhog_lut);
   if (c->fhog_tab) cudaFree(c->fhog_tab);

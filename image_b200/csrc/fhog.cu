@@ -661,8 +661,10 @@ int b2f_fhog_dev(b2f_ctx *ctx, const uint8_t *d_frames, int n_frames, int rows, 
   if (!fhog_geometry(rows, cols, cell_size, frp, fcp, g)) return B2F_OK;   // empty output
   if (!d_hog) { set_error("b2f_fhog_dev: NULL output"); return B2F_EINVAL; }
   B2F_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st;
+  if ((rc = stream_handoff(ctx, stream, &st)) != B2F_OK) return rc;
   if ((rc = arena_reserve(ctx, fhog_scratch_bytes(n_frames, g))) != B2F_OK) return rc;
-  return fhog_device(ctx, d_frames, n_frames, g, d_hog, stream ? (cudaStream_t)stream : ctx->stream);
+  return fhog_device(ctx, d_frames, n_frames, g, d_hog, st);
 }
 
 int b2f_fhog_batch(b2f_ctx *ctx, const uint8_t *frames, int n_frames, int rows, int cols, int cell_size, int frp, int fcp,

@@ -277,7 +277,8 @@ int b2f_harris_response_dev(b2f_ctx *ctx, const void *d_frames, int is_u8, int n
                             const b2f_harris_params *p, float *d_R, void *stream) {
   if (!ctx || !d_frames || !p || !d_R || n_frames <= 0 || nx <= 0 || ny <= 0) { set_error("b2f_harris_response_dev: bad argument"); return B2F_EINVAL; }
   B2F_CUDA(cudaSetDevice(ctx->device));
-  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  cudaStream_t st;
+  { int hrc = stream_handoff(ctx, stream, &st); if (hrc != B2F_OK) return hrc; }
   int exact = harris_mode(p) == MODE_STAGED ? 1 : 0;
   if (exact || !harris_fused_supported(nx, ny, p->sigma_d, p->sigma_i, p->gaussian)) {
     int rc = arena_reserve(ctx, harris_scratch_bytes(n_frames, nx, ny, p, 1));
@@ -290,7 +291,8 @@ int b2f_harris_nms_dev(b2f_ctx *ctx, const float *d_R, int n_frames, int nx, int
                        int cap, int *d_xy, float *d_strength, int *d_counts, void *stream) {
   if (!ctx || !d_R || !d_xy || !d_strength || !d_counts || n_frames <= 0 || cap <= 0) { set_error("b2f_harris_nms_dev: bad argument"); return B2F_EINVAL; }
   B2F_CUDA(cudaSetDevice(ctx->device));
-  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  cudaStream_t st;
+  { int hrc = stream_handoff(ctx, stream, &st); if (hrc != B2F_OK) return hrc; }
   if (ny <= 2 * radius + 1 || nx <= 2 * radius + 1) {   // harris.cpp:151
     B2F_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(int) * n_frames, st));
     return B2F_OK;
@@ -384,7 +386,8 @@ int b2f_harris_corners_dev(b2f_ctx *ctx, const void *d_frames, int is_u8, int n_
   if (!ctx || !d_frames || !p || !d_xy || !d_strength || !d_counts || n_frames <= 0 || nx <= 0 || ny <= 0 || cap <= 0) {
     set_error("b2f_harris_corners_dev: bad argument"); return B2F_EINVAL; }
   B2F_CUDA(cudaSetDevice(ctx->device));
-  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  cudaStream_t st;
+  { int hrc = stream_handoff(ctx, stream, &st); if (hrc != B2F_OK) return hrc; }
   const int radius = 2 * p->sigma_i + 0.5;
   if (nx < 3 || ny < 3 || ny <= 2 * radius + 1 || nx <= 2 * radius + 1) {   // harris.cpp:493, :151
     B2F_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(int) * n_frames, st));
@@ -407,7 +410,8 @@ int b2f_harris_response_eps_dev(b2f_ctx *ctx, const void *d_frames, int is_u8, i
   if (!ctx || !d_frames || !p || !d_R || !d_eps || n_frames <= 0 || nx <= 0 || ny <= 0) { set_error("b2f_harris_response_eps_dev: bad argument"); return B2F_EINVAL; }
   if (!harris_fused_supported(nx, ny, p->sigma_d, p->sigma_i, p->gaussian)) { set_error("b2f_harris_response_eps_dev: no fused kernel for these parameters"); return B2F_EUNSUP; }
   B2F_CUDA(cudaSetDevice(ctx->device));
-  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  cudaStream_t st;
+  { int hrc = stream_handoff(ctx, stream, &st); if (hrc != B2F_OK) return hrc; }
   B2F_CUDA(cudaMemsetAsync(d_eps, 0, sizeof(float) * (size_t)n_frames * ((nx + 7) / 8) * ((ny + 7) / 8), st));
   return harris_fused_launch(ctx, d_frames, is_u8 != 0, n_frames, nx, ny, p, d_R, reinterpret_cast<unsigned *>(d_eps), st);
 }

@@ -315,7 +315,8 @@ int b2f_lsd_front_dev(b2f_ctx *ctx, const void *d_frames, int is_u8, int n_frame
   LsdPlan p;
   if ((rc = lsd_plan(X, Y, scale, sigma_scale, p)) != B2F_OK) return rc;
   B2F_CUDA(cudaSetDevice(ctx->device));
-  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  cudaStream_t st;
+  { int hrc = stream_handoff(ctx, stream, &st); if (hrc != B2F_OK) return hrc; }
   if ((rc = arena_reserve(ctx, lsd_scratch_bytes(n_frames, X, Y, p.N, p.M, n_bins))) != B2F_OK) return rc;
   // (the plan's pageable tables are staged by cudaMemcpyAsync before it returns, so `p` may go out of scope)
   return lsd_front_device(ctx, d_frames, is_u8 != 0, n_frames, X, Y, p, lsd_rho(quant, ang_th), n_bins, d_angles, d_modgrad, d_list, d_scaled, st);

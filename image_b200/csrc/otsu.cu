@@ -176,9 +176,10 @@ int b2f_otsu_dev(b2f_ctx *ctx, const uint8_t *d_frames, int n_frames, int width,
   int rc = otsu_check("b2f_otsu_dev", width, height, override_threshold);
   if (rc != B2F_OK) return rc;
   B2F_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st;
+  if ((rc = stream_handoff(ctx, stream, &st)) != B2F_OK) return rc;
   if ((rc = arena_reserve(ctx, otsu_scratch_bytes(n_frames))) != B2F_OK) return rc;
-  return otsu_device<true>(ctx, d_frames, n_frames, width, height, override_threshold, d_out, d_thresholds, nullptr,
-                           stream ? (cudaStream_t)stream : ctx->stream);
+  return otsu_device<true>(ctx, d_frames, n_frames, width, height, override_threshold, d_out, d_thresholds, nullptr, st);
 }
 
 int b2f_otsu_batch_u8(b2f_ctx *ctx, const uint8_t *frames, int n_frames, int width, int height, int override_threshold,

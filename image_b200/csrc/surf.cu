@@ -18,6 +18,8 @@
 //   reference uses — std::sort on reverse iterators (surf.h:268) — cut to max_points and border-tested.
 #include "common.cuh"
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <cmath>
 #include <vector>
 
@@ -379,8 +381,9 @@ size_t surf_scratch_bytes(int n_frames, const SurfGeom &g, int cand_cap, size_t 
 }
 
 // d_rgb: n_frames interleaved RGB frames on the device.  out[f] receives the key points of frame f.
+// *need_cap: raised to the largest per-frame candidate count when cand_cap was too small (the call then returns B2F_ECAP).
 int surf_device(b2f_ctx *ctx, const unsigned char *d_rgb, int n_frames, const SurfGeom &g, long max_points, double thr,
-                int cand_cap, std::vector<std::vector<b2f_surf_point>> &out, cudaStream_t st) {
+                int cand_cap, std::vector<std::vector<b2f_surf_point>> &out, int *need_cap, cudaStream_t st) {
   const int rows = g.rows, cols = g.cols;
   size_t px = (size_t)n_frames * rows * cols;
   int *sat = ctx->arena.get<int>(px);
@@ -413,47 +416,73 @@ int surf_device(b2f_ctx *ctx, const unsigned char *d_rgb, int n_frames, const Su
   B2F_CUDA(cudaMemcpyAsync(h_counts.data(), counts, sizeof(int) * n_frames, cudaMemcpyDeviceToHost, st));
   B2F_CUDA(cudaStreamSynchronize(st));
   out.assign(n_frames, std::vector<b2f_surf_point>());
-  std::vector<SurfKey> keys;
-  std::vector<std::pair<int, int>> key_owner;            // (frame, index in out[frame])
-  std::vector<SurfCand> hc;
+  size_t total_c = 0;
+  std::vector<size_t> c_off(n_frames + 1, 0);
   for (int f = 0; f < n_frames; f++) {
-    int n = h_counts[f];
-    if (n > cand_cap) { set_error("surf: frame %d has %d interest points, above the internal capacity %d", f, n, cand_cap); return B2F_ECAP; }
-    hc.resize(n);
-    if (n) B2F_CUDA(cudaMemcpy(hc.data(), cand + (size_t)f * cand_cap, sizeof(SurfCand) * n, cudaMemcpyDeviceToHost));
-    std::sort(hc.begin(), hc.end(), [](const SurfCand &a, const SurfCand &b) { return a.key < b.key; });   // emission order
+    if (h_counts[f] > cand_cap) { *need_cap = std::max(*need_cap, h_counts[f]); }
+    c_off[f] = total_c;
+    total_c += (size_t)std::min(h_counts[f], cand_cap);
+  }
+  c_off[n_frames] = total_c;
+  if (*need_cap > cand_cap) return B2F_ECAP;               // the caller reruns with the capacity the frames need
+  // all candidate records come back with one synchronisation, into pinned memory
+  int rc = pinned_reserve(ctx, std::max<size_t>(total_c, 1) * sizeof(SurfCand));
+  if (rc != B2F_OK) return rc;
+  SurfCand *hc_all = static_cast<SurfCand *>(ctx->pinned);
+  for (int f = 0; f < n_frames; f++)
+    if (h_counts[f]) B2F_CUDA(cudaMemcpyAsync(hc_all + c_off[f], cand + (size_t)f * cand_cap, sizeof(SurfCand) * h_counts[f], cudaMemcpyDeviceToHost, st));
+  B2F_CUDA(cudaStreamSynchronize(st));
+  // per frame: emission order, then the reference's sort and filters (surf.h:268-285) — frames are independent, a few host threads share them
+  std::vector<std::vector<SurfKey>> fkeys(n_frames);
+  auto tail = [&](int f) {
+    const int n = h_counts[f];
+    SurfCand *hc = hc_all + c_off[f];
+    std::sort(hc, hc + n, [](const SurfCand &a, const SurfCand &b) { return a.key < b.key; });   // emission order
     std::vector<ip_mirror> pts(n);
     for (int k = 0; k < n; k++) pts[k] = ip_mirror{hc[k].x, hc[k].y, hc[k].scale, hc[k].score, hc[k].lap};
     std::sort(pts.rbegin(), pts.rend());                                             // surf.h:268
-    size_t lim = std::min((size_t)max_points, pts.size());
+    const size_t lim = std::min((size_t)max_points, pts.size());
     for (size_t k = 0; k < lim; k++) {
       const unsigned long bsz = (unsigned long)(32 * pts[k].scale);                  // surf.h:275-277
       if (!rect_inside(rows, cols, pts[k].x, pts[k].y, bsz)) continue;
       b2f_surf_point sp;
       memset(&sp, 0, sizeof(sp));
       sp.x = pts[k].x; sp.y = pts[k].y; sp.scale = pts[k].scale; sp.score = pts[k].score; sp.laplacian = pts[k].lap;
-      key_owner.push_back({f, (int)out[f].size()});
       out[f].push_back(sp);
-      keys.push_back(SurfKey{sp.x, sp.y, sp.scale, f, 0});
+      fkeys[f].push_back(SurfKey{sp.x, sp.y, sp.scale, f, 0});
     }
+  };
+  {
+    const int nt = std::max(1, std::min({n_frames, (int)std::thread::hardware_concurrency(), 16}));
+    std::atomic<int> next(0);
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; t++) pool.emplace_back([&] { for (int f; (f = next++) < n_frames;) tail(f); });
+    for (int f; (f = next++) < n_frames;) tail(f);
+    for (std::thread &t : pool) t.join();
   }
+  std::vector<SurfKey> keys;
+  std::vector<size_t> k_off(n_frames + 1, 0);
+  for (int f = 0; f < n_frames; f++) { k_off[f] = keys.size(); keys.insert(keys.end(), fkeys[f].begin(), fkeys[f].end()); }
+  k_off[n_frames] = keys.size();
   if (keys.empty()) return B2F_OK;
-  size_t nk = keys.size();
+  const size_t nk = keys.size();
   SurfKey *d_keys = ctx->arena.get<SurfKey>(nk);
   double *d_ang = ctx->arena.get<double>(nk), *d_des = ctx->arena.get<double>(nk * 64);
   B2F_ARENA_CHECK(ctx);
   B2F_CUDA(cudaMemcpyAsync(d_keys, keys.data(), sizeof(SurfKey) * nk, cudaMemcpyHostToDevice, st));
   surf_describe_kernel<<<(unsigned)nk, 128, 0, st>>>(sat, d_keys, d_ang, d_des, rows, cols);
   B2F_LAUNCH_CHECK(ctx);
-  std::vector<double> h_ang(nk), h_des(nk * 64);
-  B2F_CUDA(cudaMemcpyAsync(h_ang.data(), d_ang, sizeof(double) * nk, cudaMemcpyDeviceToHost, st));
-  B2F_CUDA(cudaMemcpyAsync(h_des.data(), d_des, sizeof(double) * nk * 64, cudaMemcpyDeviceToHost, st));
+  if ((rc = pinned_reserve(ctx, nk * 65 * sizeof(double))) != B2F_OK) return rc;      // (the candidate records are consumed)
+  double *h_ang = static_cast<double *>(ctx->pinned), *h_des = h_ang + nk;
+  B2F_CUDA(cudaMemcpyAsync(h_ang, d_ang, sizeof(double) * nk, cudaMemcpyDeviceToHost, st));
+  B2F_CUDA(cudaMemcpyAsync(h_des, d_des, sizeof(double) * nk * 64, cudaMemcpyDeviceToHost, st));
   B2F_CUDA(cudaStreamSynchronize(st));
-  for (size_t k = 0; k < nk; k++) {
-    b2f_surf_point &sp = out[key_owner[k].first][key_owner[k].second];
-    sp.angle = h_ang[k];
-    memcpy(sp.des, &h_des[k * 64], sizeof(double) * 64);
-  }
+  for (int f = 0; f < n_frames; f++)
+    for (size_t k = k_off[f]; k < k_off[f + 1]; k++) {
+      b2f_surf_point &sp = out[f][k - k_off[f]];
+      sp.angle = h_ang[k];
+      memcpy(sp.des, h_des + k * 64, sizeof(double) * 64);
+    }
   return B2F_OK;
 }
 
@@ -467,21 +496,47 @@ static int surf_check(const char *who, int rows, int cols, long max_points, doub
   return B2F_OK;
 }
 
-static int surf_run(b2f_ctx *ctx, const uint8_t *frames, int n_frames, int rows, int cols, long max_points, double thr,
-                    std::vector<std::vector<b2f_surf_point>> &out) {
+// frames: host memory (uploaded here) or, with on_device, already resident in HBM
+static int surf_run(b2f_ctx *ctx, const uint8_t *frames, bool on_device, int n_frames, int rows, int cols, long max_points, double thr,
+                    std::vector<std::vector<b2f_surf_point>> &out, cudaStream_t st) {
   SurfGeom g;
   surf_geometry(rows, cols, g);
-  // every sample can at most be one candidate per 3x3x3 neighbourhood; bound by a fraction of octave 0
+  // the 3x3x3 test keeps ties, so a flat image can make every sample a candidate: start from a quarter of octave 0
+  // (far above natural frames) and rerun with the capacity the frames ask for when that is exceeded
   int cand_cap = (int)std::min<long long>(std::max<long long>((long long)g.m[0].nr * g.m[0].nc / 4, 1024), 4000000);
-  size_t max_keys = (size_t)n_frames * std::min<long long>(max_points, cand_cap);
   B2F_CUDA(cudaSetDevice(ctx->device));
-  size_t in_bytes = (size_t)n_frames * rows * cols * 3;
-  int rc = arena_reserve(ctx, surf_scratch_bytes(n_frames, g, cand_cap, max_keys) + align256(in_bytes));
-  if (rc != B2F_OK) return rc;
-  unsigned char *d_in = ctx->arena.get<unsigned char>(in_bytes);
-  B2F_ARENA_CHECK(ctx);
-  B2F_CUDA(cudaMemcpyAsync(d_in, frames, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
-  return surf_device(ctx, d_in, n_frames, g, max_points, thr, cand_cap, out, ctx->stream);
+  const size_t in_bytes = (size_t)n_frames * rows * cols * 3;
+  for (int attempt = 0; attempt < 2; attempt++) {
+    const size_t max_keys = (size_t)n_frames * std::min<long long>(max_points, cand_cap);
+    int rc = arena_reserve(ctx, surf_scratch_bytes(n_frames, g, cand_cap, max_keys) + (on_device ? 0 : align256(in_bytes)));
+    if (rc != B2F_OK) return rc;
+    const unsigned char *d_in = frames;
+    if (!on_device) {
+      unsigned char *up = ctx->arena.get<unsigned char>(in_bytes);
+      B2F_ARENA_CHECK(ctx);
+      B2F_CUDA(cudaMemcpyAsync(up, frames, in_bytes, cudaMemcpyHostToDevice, st));
+      d_in = up;
+    }
+    int need = cand_cap;
+    rc = surf_device(ctx, d_in, n_frames, g, max_points, thr, cand_cap, out, &need, st);
+    if (rc != B2F_ECAP || need <= cand_cap) return rc;
+    cand_cap = need;
+  }
+  set_error("surf: candidate capacity could not be established");
+  return B2F_ECAP;
+}
+
+// per-frame vectors -> the caller's padded [n_frames][cap] array + counts
+static int surf_pack(const std::vector<std::vector<b2f_surf_point>> &out, int n_frames, int cap, b2f_surf_point *points, int *counts, const char *who) {
+  bool over = false;
+  for (int f = 0; f < n_frames; f++) {
+    counts[f] = (int)out[f].size();
+    const size_t m = std::min(out[f].size(), (size_t)cap);
+    over |= out[f].size() > (size_t)cap;
+    if (m) memcpy(points + (size_t)f * cap, out[f].data(), sizeof(b2f_surf_point) * m);
+  }
+  if (over) { set_error("%s: at least one frame has more than cap=%d key points", who, cap); return B2F_ECAP; }
+  return B2F_OK;
 }
 
 }  // namespace b2f
@@ -497,7 +552,7 @@ int b2f_surf_host(b2f_ctx *ctx, const uint8_t *rgb, int rows, int cols, long max
   int rc = surf_check("b2f_surf_host", rows, cols, max_points, detection_threshold);
   if (rc != B2F_OK) return rc;
   std::vector<std::vector<b2f_surf_point>> out;
-  if ((rc = surf_run(ctx, rgb, 1, rows, cols, max_points, detection_threshold, out)) != B2F_OK) return rc;
+  if ((rc = surf_run(ctx, rgb, false, 1, rows, cols, max_points, detection_threshold, out, ctx->stream)) != B2F_OK) return rc;
   size_t m = out[0].size();
   b2f_surf_point *p = (b2f_surf_point *)malloc(sizeof(b2f_surf_point) * (m ? m : 1));
   if (!p) { set_error("b2f_surf_host: out of host memory"); return B2F_ENOMEM; }
@@ -512,16 +567,22 @@ int b2f_surf_batch(b2f_ctx *ctx, const uint8_t *frames, int n_frames, int rows, 
   int rc = surf_check("b2f_surf_batch", rows, cols, max_points, detection_threshold);
   if (rc != B2F_OK) return rc;
   std::vector<std::vector<b2f_surf_point>> out;
-  if ((rc = surf_run(ctx, frames, n_frames, rows, cols, max_points, detection_threshold, out)) != B2F_OK) return rc;
-  bool over = false;
-  for (int f = 0; f < n_frames; f++) {
-    counts[f] = (int)out[f].size();
-    size_t m = std::min(out[f].size(), (size_t)cap);
-    over |= out[f].size() > (size_t)cap;
-    if (m) memcpy(points + (size_t)f * cap, out[f].data(), sizeof(b2f_surf_point) * m);
-  }
-  if (over) { set_error("b2f_surf_batch: at least one frame has more than cap=%d key points", cap); return B2F_ECAP; }
-  return B2F_OK;
+  if ((rc = surf_run(ctx, frames, false, n_frames, rows, cols, max_points, detection_threshold, out, ctx->stream)) != B2F_OK) return rc;
+  return surf_pack(out, n_frames, cap, points, counts, "b2f_surf_batch");
+}
+
+// frames already resident in HBM (new surface); results land in host memory like b2f_surf_batch (the sort / filter tail of
+// get_surf_points, surf.h:268-285, is host code)
+int b2f_surf_dev(b2f_ctx *ctx, const uint8_t *d_frames, int n_frames, int rows, int cols, long max_points,
+                 double detection_threshold, int cap, b2f_surf_point *points, int *counts, void *stream) {
+  if (!ctx || !d_frames || !points || !counts || n_frames <= 0 || cap <= 0) { set_error("b2f_surf_dev: bad argument"); return B2F_EINVAL; }
+  int rc = surf_check("b2f_surf_dev", rows, cols, max_points, detection_threshold);
+  if (rc != B2F_OK) return rc;
+  cudaStream_t st;
+  if ((rc = stream_handoff(ctx, stream, &st)) != B2F_OK) return rc;
+  std::vector<std::vector<b2f_surf_point>> out;
+  if ((rc = surf_run(ctx, d_frames, true, n_frames, rows, cols, max_points, detection_threshold, out, st)) != B2F_OK) return rc;
+  return surf_pack(out, n_frames, cap, points, counts, "b2f_surf_dev");
 }
 
 }  // extern "C"

@@ -102,33 +102,35 @@ def image_surf(x, max_points=1000, detection_threshold=30):
     return out
 
 
-def surf_batch(frames, max_points=10000, detection_threshold=30.0, cap=None):
-    """Batch form (new surface): uint8 [n, rows, cols, 3] -> list of dicts like dlib_surf_points."""
+def surf_dev(d_frames, n, rows, cols, max_points=10000, detection_threshold=30.0, cap=None, rec=None, stream=None, ctx=None):
+    """Frames resident in HBM (torch tensor / device pointer) -> (records [n, cap, 70] float64, counts): the raw
+    b2f_surf_point rows (x, y, angle, scale, score, laplacian, 64 descriptor values) in host memory."""
+    lib = _lib.load()
+    cap = int(cap or max_points)
+    rec = rec if rec is not None else np.empty((n, cap, 70), np.float64)
+    cnt = np.zeros(n, np.int32)
+    _lib.check(lib.b2f_surf_dev(ctx or _lib.context(), _lib.ptr(d_frames), n, rows, cols, C.c_long(int(max_points)),
+                                float(detection_threshold), cap, _lib.ptr(rec), _lib.ptr(cnt),
+                                _lib.ptr(stream) if stream is not None else None))
+    return rec, cnt
+
+
+def surf_batch(frames, max_points=10000, detection_threshold=30.0, cap=None, raw=False, rec=None, ctx=None):
+    """Batch form (new surface): uint8 [n, rows, cols, 3] -> list of dicts like dlib_surf_points
+    (raw=True: the padded record array and the counts, no per-frame copies)."""
     lib = _lib.load()
     f = np.ascontiguousarray(frames, dtype=np.uint8)
     n, rows, cols, _ = f.shape
     cap = int(cap or max_points)
-    rec = np.empty((n, cap, 70), np.float64)       # only the first counts[i] rows of a frame are written and read
+    rec = rec if rec is not None else np.empty((n, cap, 70), np.float64)       # only the first counts[i] rows of a frame are written and read
     cnt = np.zeros(n, np.int32)
-    _lib.check(lib.b2f_surf_batch(_lib.context(), _lib.ptr(f), n, rows, cols, C.c_long(int(max_points)),
+    _lib.check(lib.b2f_surf_batch(ctx or _lib.context(), _lib.ptr(f), n, rows, cols, C.c_long(int(max_points)),
                                   float(detection_threshold), cap, _lib.ptr(rec), _lib.ptr(cnt)))
+    if raw:
+        return rec, cnt
     outs = []
     for i in range(n):
         r = rec[i, :cnt[i]]
         outs.append(dict(points=int(cnt[i]), x=r[:, 0].copy(), y=r[:, 1].copy(), angle=r[:, 2].copy(),
                          pyramid_scale=r[:, 3].copy(), score=r[:, 4].copy(), laplacian=r[:, 5].copy(), surf=r[:, 6:].copy()))
     return outs
-
-
-def smoke_check(po):
-    from . import synth
-    img = synth.frame_rgb(3, 72, 104)
-    out = image_fhog(np.ascontiguousarray(img.transpose(2, 1, 0)))
-    ref = po.fhog(img, 8, 1, 1, impl="oracle")
-    assert out["fhog"].shape == ref.shape and np.array_equal(out["fhog"], ref), "FHOG differs from the oracle"
-    blobs = synth.frame_blobs(4, 240, 320)
-    sp = image_surf(np.ascontiguousarray(blobs.transpose(2, 1, 0)), max_points=200, detection_threshold=5)
-    rs = po.surf(blobs, 200, 5.0, impl="oracle")
-    assert sp["points"] == len(rs["x"]) and np.array_equal(sp["x"], rs["x"]) and np.array_equal(sp["score"], rs["score"]), "SURF key points differ"
-    if sp["points"]:
-        np.testing.assert_allclose(sp["surf"], rs["surf"], rtol=1e-4, atol=1e-9)

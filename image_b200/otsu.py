@@ -48,11 +48,3 @@ def otsu_dev(d_frames, n_frames, width, height, d_out, d_thresholds, threshold=0
     lib = _lib.load()
     _lib.check(lib.b2f_otsu_dev(ctx or _lib.context(), _lib.ptr(d_frames), n_frames, width, height, int(threshold),
                                 _lib.ptr(d_out), _lib.ptr(d_thresholds), C.c_void_p(stream) if stream is not None else None))
-
-
-def smoke_check(po):
-    from . import synth
-    img = synth.frame_shapes(6, 70, 90).astype(np.float64)
-    r = image_otsu(img)
-    o, t = po.otsu(img.ravel(order="F"), 90, 70, 0)
-    assert r["threshold"] == t and np.array_equal(r["x"].ravel(order="F"), o), "Otsu differs from the oracle"

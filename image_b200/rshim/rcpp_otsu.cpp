@@ -6,7 +6,9 @@
 
 // [[Rcpp::export]]
 Rcpp::List otsu(Rcpp::NumericVector x, int width, int height, int threshold = 0) {
+  if (width <= 0 || height <= 0) Rcpp::stop("otsu: width and height must be positive");
   const size_t n = (size_t)width * height;
+  if ((size_t)x.size() != n) Rcpp::stop("otsu: x must hold width*height values");   // (the reference reads / writes out of bounds here)
   std::vector<float> in(n), out(n);
   for (long i = 0; i < (long)x.size(); i++) in[i] = (float)x[i];            // same narrowing as the reference (:171)
   int thresh = 0;

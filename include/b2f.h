@@ -150,6 +150,10 @@ int b2f_surf_host(b2f_ctx *ctx, const uint8_t *rgb, int rows, int cols, long max
                   double detection_threshold, b2f_surf_point **points, int *n);
 int b2f_surf_batch(b2f_ctx *ctx, const uint8_t *frames, int n_frames, int rows, int cols, long max_points,
                    double detection_threshold, int cap, b2f_surf_point *points, int *counts);
+/* frames resident in HBM (new surface); the records land in host memory like b2f_surf_batch's (the sort / filter tail
+ * of get_surf_points, surf.h:268-285, runs on the host).  Synchronous. */
+int b2f_surf_dev(b2f_ctx *ctx, const uint8_t *d_frames, int n_frames, int rows, int cols, long max_points,
+                 double detection_threshold, int cap, b2f_surf_point *points, int *counts, void *stream);
 
 /* ------------------------------------------------------------------ combined batch ----
  * New surface: Harris corners + Canny edge map + FHOG from ONE upload of each interleaved RGB frame (rows x cols x 3).
