@@ -44,7 +44,7 @@ def contour_edge_points_batch(frames, cap=None, sigma=0.0, ctx=None):
     lib = _lib.load()
     f = np.ascontiguousarray(frames, dtype=np.uint8)
     n, Y, X = f.shape
-    cap = int(cap or max(1024, X * Y // 8))
+    cap = int(cap or max(1024, X * Y // 2))
     idx = np.zeros((n, cap), np.int32)
     o = [np.zeros((n, cap), np.float64) for _ in range(4)]
     cnt = np.zeros(n, np.int32)

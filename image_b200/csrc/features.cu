@@ -45,12 +45,11 @@ rgb_to_grey_kernel(const unsigned char *__restrict__ rgb, unsigned char *__restr
 
 using namespace b2f;
 
-extern "C" {
-
-int b2f_features_batch_rgb(b2f_ctx *ctx, const uint8_t *rgb, int n_frames, int rows, int cols,
-                           const b2f_harris_params *hp, int corner_cap, float *cx, float *cy, float *cs, int *ccounts,
-                           const b2f_canny_params *cp, uint8_t *edges, int *nonzero,
-                           int cell_size, int frp, int fcp, float *hog) {
+// channels = 3: interleaved RGB frames (grey derived on the device); channels = 1: grey frames (no FHOG)
+static int features_batch(b2f_ctx *ctx, const uint8_t *rgb, int channels, int n_frames, int rows, int cols,
+                          const b2f_harris_params *hp, int corner_cap, float *cx, float *cy, float *cs, int *ccounts,
+                          const b2f_canny_params *cp, uint8_t *edges, int *nonzero,
+                          int cell_size, int frp, int fcp, float *hog) {
   if (!ctx || !rgb || n_frames <= 0 || rows <= 0 || cols <= 0) { set_error("b2f_features_batch_rgb: bad argument"); return B2F_EINVAL; }
   const bool do_h = hp != nullptr, do_c = cp != nullptr, do_f = cell_size > 0;
   if (do_h && (!cx || !cy || !cs || !ccounts || corner_cap <= 0)) { set_error("b2f_features_batch_rgb: Harris outputs missing"); return B2F_EINVAL; }
@@ -63,7 +62,7 @@ int b2f_features_batch_rgb(b2f_ctx *ctx, const uint8_t *rgb, int n_frames, int r
   }
   B2F_CUDA(cudaSetDevice(ctx->device));
   const int nx = cols, ny = rows;
-  const size_t plane = (size_t)nx * ny, fin = plane * 3;
+  const size_t plane = (size_t)nx * ny, fin = plane * channels;
   const int C = frames_per_chunk(ctx, fin, n_frames), NCH = ceil_div(n_frames, C);
   const size_t f_scr = do_f ? fhog_scratch_simple(C, rows, cols, cell_size, frp, fcp, &hnr, &hnc) : 0;
   const size_t fout = (size_t)hnr * hnc * 31;
@@ -77,7 +76,7 @@ int b2f_features_batch_rgb(b2f_ctx *ctx, const uint8_t *rgb, int n_frames, int r
                               2 * align256(rec * 4) + 2 * align256((size_t)n_frames * 4) + 8192);
   if (rc != B2F_OK) return rc;
   unsigned char *d_rgb = ctx->arena.get<unsigned char>(fin * n_frames);
-  unsigned char *d_grey = ctx->arena.get<unsigned char>(plane * C);                     // one chunk of grey planes
+  unsigned char *d_grey = channels == 3 ? ctx->arena.get<unsigned char>(plane * C) : nullptr;   // one chunk of derived grey planes
   unsigned char *d_edges = do_c ? ctx->arena.get<unsigned char>(plane * n_frames) : nullptr;
   float *d_hog = do_f && fout ? ctx->arena.get<float>(fout * n_frames) : nullptr;
   int *d_xy = do_h ? ctx->arena.get<int>(rec) : nullptr;
@@ -94,7 +93,8 @@ int b2f_features_batch_rgb(b2f_ctx *ctx, const uint8_t *rgb, int n_frames, int r
     rc = B2F_OK;
     if (cudaMemcpyAsync(d_rgb + fin * f0, rgb + fin * f0, fin * nf, cudaMemcpyHostToDevice, ctx->s_in) != cudaSuccess ||
         cudaEventRecord(e_in, ctx->s_in) != cudaSuccess || cudaStreamWaitEvent(st, e_in, 0) != cudaSuccess) rc = B2F_ECUDA;
-    if (rc == B2F_OK && (do_h || do_c)) {
+    const unsigned char *d_grey_c = channels == 1 ? d_rgb + fin * f0 : d_grey;     // grey input is used where it landed
+    if (rc == B2F_OK && (do_h || do_c) && channels == 3) {
       const size_t npx = plane * nf;
       const int al = ((reinterpret_cast<uintptr_t>(d_rgb + fin * f0) | reinterpret_cast<uintptr_t>(d_grey)) & 15) == 0;
       rgb_to_grey_kernel<<<(unsigned)((npx + 4095) / 4096), 256, 0, st>>>(d_rgb + fin * f0, d_grey, npx, al);
@@ -104,17 +104,17 @@ int b2f_features_batch_rgb(b2f_ctx *ctx, const uint8_t *rgb, int n_frames, int r
     // the three detectors run one after the other on the context stream and share the scratch arena
     if (rc == B2F_OK && h_runs) {
       ctx->arena.off = mark;
-      if (certified) rc = harris_corners_certified(ctx, d_grey, true, nf, nx, ny, hp, corner_cap, d_xy + (size_t)f0 * corner_cap, d_s + (size_t)f0 * corner_cap, nullptr, d_cnt + f0, nullptr, st);
+      if (certified) rc = harris_corners_certified(ctx, d_grey_c, true, nf, nx, ny, hp, corner_cap, d_xy + (size_t)f0 * corner_cap, d_s + (size_t)f0 * corner_cap, nullptr, d_cnt + f0, nullptr, st);
       else {
         float *d_R = ctx->arena.get<float>(plane * nf);
         if (!d_R) { set_error("internal: scratch arena under-reserved in b2f_features_batch_rgb"); rc = B2F_ENOMEM; }
-        if (rc == B2F_OK) rc = harris_response_device(ctx, d_grey, true, nf, nx, ny, hp, hp->exact == 2 ? 0 : 1, d_R, st);
+        if (rc == B2F_OK) rc = harris_response_device(ctx, d_grey_c, true, nf, nx, ny, hp, hp->exact == 2 ? 0 : 1, d_R, st);
         if (rc == B2F_OK) rc = harris_nms_device(ctx, d_R, nf, nx, ny, hp->threshold, radius, corner_cap, d_xy + (size_t)f0 * corner_cap, d_s + (size_t)f0 * corner_cap, d_cnt + f0, st);
       }
     }
     if (rc == B2F_OK && do_c) {
       ctx->arena.off = mark;
-      rc = canny_device(ctx, d_grey, nf, nx, ny, cp->s, cp->low_thr, cp->high_thr, cp->acc_grad, d_edges + plane * f0, d_nz + f0, st);
+      rc = canny_device(ctx, d_grey_c, nf, nx, ny, cp->s, cp->low_thr, cp->high_thr, cp->acc_grad, d_edges + plane * f0, d_nz + f0, st);
     }
     if (rc == B2F_OK && d_hog) {
       ctx->arena.off = mark;
@@ -163,6 +163,22 @@ int b2f_features_batch_rgb(b2f_ctx *ctx, const uint8_t *rgb, int n_frames, int r
   }
   if (over) { set_error("b2f_features_batch_rgb: at least one frame has more than corner_cap=%d corners", corner_cap); return B2F_ECAP; }
   return B2F_OK;
+}
+
+extern "C" {
+
+int b2f_features_batch_rgb(b2f_ctx *ctx, const uint8_t *rgb, int n_frames, int rows, int cols,
+                           const b2f_harris_params *hp, int corner_cap, float *cx, float *cy, float *cs, int *ccounts,
+                           const b2f_canny_params *cp, uint8_t *edges, int *nonzero,
+                           int cell_size, int frp, int fcp, float *hog) {
+  return features_batch(ctx, rgb, 3, n_frames, rows, cols, hp, corner_cap, cx, cy, cs, ccounts, cp, edges, nonzero, cell_size, frp, fcp, hog);
+}
+
+// grey u8 frames [n][ny][nx]: Harris corners + Canny edge map from one upload (BASELINE.json config 5's stream)
+int b2f_features_batch_grey(b2f_ctx *ctx, const uint8_t *grey, int n_frames, int nx, int ny,
+                            const b2f_harris_params *hp, int corner_cap, float *cx, float *cy, float *cs, int *ccounts,
+                            const b2f_canny_params *cp, uint8_t *edges, int *nonzero) {
+  return features_batch(ctx, grey, 1, n_frames, ny, nx, hp, corner_cap, cx, cy, cs, ccounts, cp, edges, nonzero, 0, 0, 0, nullptr);
 }
 
 }  // extern "C"

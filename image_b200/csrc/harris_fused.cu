@@ -122,15 +122,14 @@ int harris_fused_launch(b2f_ctx *ctx, const void *d_frames, bool u8, int n_frame
     using C = Fused3Cfg<3, 3, 64, 256, 4, 2>;
     return launch_shape<C, false>(ctx, d_frames, u8, grad, n_frames, nx, ny, d_R, d_eps, generic_all, false, kc, st);
   }
-  // tall tiles pay when the frame has many tile rows; TMA needs 16-byte row strides (u8)
-  const int cfg_env = env_int("B2F_HARRIS_TILE", 0), tma_env = env_int("B2F_HARRIS_TMA", -1);
-  const bool tall = cfg_env ? (cfg_env == 48) : false;
-  const bool tma_ok = u8 && aligned && (nx % 16 == 0) && (((size_t)nx * ny) % 16 == 0) && encode_tiled_fn() != nullptr;
-  const bool tma = tma_ok && (tma_env < 0 ? true : tma_env != 0);
-  if (cfg_env == 488) {   // 48-row tiles, stage-D items of 8 outputs (exactly one pass), 2 CTAs / SM
-    using C = Fused3Cfg<3, 7, 48, 256, 8, 2>;
-    return launch_shape<C, false>(ctx, d_frames, u8, grad, n_frames, nx, ny, d_R, d_eps, generic_all, false, kc, st);
-  }
+  // Measured on 16 x 3840x2160 u8 frames (tools/harris_timing.py): 64x48 tiles with 3 CTAs / SM 61 us per
+  // frame, 64x64 tiles with 2 CTAs / SM 64 us, the same with TMA-staged input in a persistent grid 78 us (the resident
+  // CTAs of an SM then walk their tiles in lock step and stop overlapping each other's stages).  Default: 64x48 / 3 CTAs;
+  // B2F_HARRIS_TILE=64 and B2F_HARRIS_TMA=1 select the alternatives (kept because the tests cover every shape).
+  const int cfg_env = env_int("B2F_HARRIS_TILE", 0), tma_env = env_int("B2F_HARRIS_TMA", 0);
+  const bool tall = cfg_env != 64;
+  const bool tma_ok = u8 && aligned && (nx % 16 == 0) && (((size_t)nx * ny) % 16 == 0) && encode_tiled_fn() != nullptr;   // 16-byte row strides
+  const bool tma = tma_ok && tma_env != 0;
   if (tall) {
     using C = Fused3Cfg<3, 7, 48, 256, 4, 3>;
     return launch_shape<C, false>(ctx, d_frames, u8, grad, n_frames, nx, ny, d_R, d_eps, generic_all, false, kc, st);

@@ -10,12 +10,15 @@ from .harris import _params
 
 
 def features_batch(rgb, harris=None, canny=None, fhog=None, corner_cap=65536, out_edges=None, out_hog=None, ctx=None):
-    """rgb: uint8 [n, rows, cols, 3] (host, ideally pinned).  harris / canny / fhog: dicts of parameters (None = skip):
+    """rgb: uint8 [n, rows, cols, 3] (host, ideally pinned), or grey uint8 [n, rows, cols] (then no FHOG).  harris / canny / fhog: dicts of parameters (None = skip):
     harris as harris_batch_u8's keywords, canny dict(s, low_thr, high_thr, accGrad), fhog dict(cell, frp, fcp).
     Returns dict(corners=(x, y, strength, counts) padded [n, corner_cap] arrays, edges, nonzero, hog)."""
     lib = _lib.load()
     f = np.ascontiguousarray(rgb, dtype=np.uint8)
-    n, rows, cols, _ = f.shape
+    grey_in = f.ndim == 3
+    if grey_in and fhog is not None:
+        raise ValueError("FHOG needs RGB frames")
+    n, rows, cols = f.shape[:3]
     out = {}
     hp = cx = cy = cs = cc = None
     if harris is not None:
@@ -35,9 +38,14 @@ def features_batch(rgb, harris=None, canny=None, fhog=None, corner_cap=65536, ou
         nr, nc = C.c_int(0), C.c_int(0)
         _lib.check(lib.b2f_fhog_size(rows, cols, cell, frp, fcp, C.byref(nr), C.byref(nc)))
         hog = out_hog if out_hog is not None else np.zeros((n, nr.value, nc.value, 31), np.float32)
-    _lib.check(lib.b2f_features_batch_rgb(ctx or _lib.context(), _lib.ptr(f), n, rows, cols,
-                                          C.byref(hp) if hp is not None else None, int(corner_cap), _lib.ptr(cx), _lib.ptr(cy), _lib.ptr(cs), _lib.ptr(cc),
-                                          C.byref(cp) if cp is not None else None, _lib.ptr(edges), _lib.ptr(nz), cell, frp, fcp, _lib.ptr(hog)))
+    if grey_in:
+        _lib.check(lib.b2f_features_batch_grey(ctx or _lib.context(), _lib.ptr(f), n, cols, rows,
+                                               C.byref(hp) if hp is not None else None, int(corner_cap), _lib.ptr(cx), _lib.ptr(cy), _lib.ptr(cs), _lib.ptr(cc),
+                                               C.byref(cp) if cp is not None else None, _lib.ptr(edges), _lib.ptr(nz)))
+    else:
+        _lib.check(lib.b2f_features_batch_rgb(ctx or _lib.context(), _lib.ptr(f), n, rows, cols,
+                                              C.byref(hp) if hp is not None else None, int(corner_cap), _lib.ptr(cx), _lib.ptr(cy), _lib.ptr(cs), _lib.ptr(cc),
+                                              C.byref(cp) if cp is not None else None, _lib.ptr(edges), _lib.ptr(nz), cell, frp, fcp, _lib.ptr(hog)))
     if harris is not None:
         out["corners"] = (cx, cy, cs, cc)
     if canny is not None:

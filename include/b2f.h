@@ -166,6 +166,10 @@ int b2f_features_batch_rgb(b2f_ctx *ctx, const uint8_t *rgb, int n_frames, int r
                            const b2f_harris_params *hp, int corner_cap, float *cx, float *cy, float *cs, int *ccounts,
                            const b2f_canny_params *cp, uint8_t *edges, int *nonzero,
                            int cell_size, int filter_rows_padding, int filter_cols_padding, float *hog);
+/* the same for grey u8 frames [n][ny][nx]: Harris + Canny from one upload (BASELINE.json config 5's stream) */
+int b2f_features_batch_grey(b2f_ctx *ctx, const uint8_t *grey, int n_frames, int nx, int ny,
+                            const b2f_harris_params *hp, int corner_cap, float *cx, float *cy, float *cs, int *ccounts,
+                            const b2f_canny_params *cp, uint8_t *edges, int *nonzero);
 
 /* ------------------------------------------------------------------- ContourDetector ----
  * SURVEY.md 8f "next", rank 1: the data-parallel front end of smooth_contours() (image.ContourDetector/src/
