@@ -131,6 +131,7 @@ int b2f_init(int device, b2f_ctx **out) {
   }
   b2f_ctx *c = new b2f_ctx();
   c->device = device;
+  if (const char *cb = getenv("B2F_CHUNK_BYTES")) { const long long v = atoll(cb); if (v > 0) c->chunk_bytes = (size_t)v; }
   c->sm_count = prop.multiProcessorCount;
   e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { b2f::set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); delete c; return B2F_ECUDA; }

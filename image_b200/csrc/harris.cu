@@ -677,7 +677,8 @@ harris_exact_patch_kernel(const void *__restrict__ frames, const float *__restri
     const int p = cand_xy[(size_t)f * cap + ci];
     const bool certain = cand_flag[(size_t)f * cap + ci] != 0;
     const int x = p % nx, y = p / nx;
-    const int m = certain ? (M9 ? 1 : 0) : radius;
+    // exact R on the (2m+1)^2 patch around (x, y) -> sO (all threads; ends with a barrier)
+    auto exact_patch = [&](const int m) {
     const int W = 2 * m + 1, PW = W + 2 * RI;
     // real coordinate ranges (every reflected / replicated coordinate falls inside them)
     const int ix0 = max(0, x - m - RI - 1), ix1 = min(nx - 1, x + m + RI + 1), isw = ix1 - ix0 + 1;
@@ -754,11 +755,22 @@ harris_exact_patch_kernel(const void *__restrict__ frames, const float *__restri
       sO[i] = corner_measure(v[0], v[1], v[2], k, measure);
     }
     __syncthreads();
+    };
+    // certain candidates need their own value (and the 3x3 of the sub-pixel fit); undecided ones first their own exact
+    // value — most of them sit beside strong edges, where the bound is wide and the exact response is far below the
+    // threshold — and the whole window only if that value passes the threshold
+    int m = certain ? (M9 ? 1 : 0) : 0;
+    exact_patch(m);
+    if (!certain && !(sO[0] < Th)) {
+      m = radius;
+      exact_patch(m);
+    }
+    const int W = 2 * m + 1;
     if (tid == 0) {
       const float val = sO[m * W + m];
       bool ok = true;
       if (!certain) {                                          // the reference's predicate on exact values (harris.cpp:161-243)
-        ok = !(val < Th);
+        ok = !(val < Th);                                      // (m == 0 here means exactly that this test failed)
         for (int dy = -m; dy <= m && ok; dy++)
           for (int dx = -m; dx <= m && ok; dx++) {
             const float q = sO[(m + dy) * W + m + dx];
@@ -767,7 +779,7 @@ harris_exact_patch_kernel(const void *__restrict__ frames, const float *__restri
             else if (dx < 0) ok = val >= q;
             else if (dx > 0) ok = val > q;
           }
-        if (ok && x == radius && sO[m * W + m - 1] >= val) ok = false;   // harris.cpp:173
+        if (ok && m > 0 && x == radius && sO[m * W + m - 1] >= val) ok = false;   // harris.cpp:173
       }
       const size_t o = (size_t)f * cap + ci;
       strength[o] = val;

@@ -45,7 +45,7 @@ def test_full_size_4k_frame(oracle):
     from image_b200 import synth
     from image_b200.contour import contour_edge_points_batch
     f = synth.frame_shapes(77, 2160, 3840)
-    outs = contour_edge_points_batch(np.stack([f, f]), cap=2000000)
+    outs = contour_edge_points_batch(np.stack([f, f]), cap=3840 * 2160 // 2)
     _check(outs[0], outs[1])
     r = oracle.contour_edge_points(oracle.contour_gaussian(f))
     assert len(r["idx"]) > 10000
