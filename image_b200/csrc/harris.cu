@@ -1060,6 +1060,16 @@ int harris_decimate2(b2f_ctx *ctx, const float *d_src, float *d_dst, int nx, int
   return B2F_OK;
 }
 
+__global__ void double_to_float_kernel(const double *__restrict__ s, float *__restrict__ d, size_t n) {   // I[i] = (float)x[i], rcpp_harris.cpp:35
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) d[i] = __double2float_rn(s[i]);
+}
+int harris_double_to_float(b2f_ctx *ctx, const double *s, float *d, size_t n, cudaStream_t st) {
+  double_to_float_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s, d, n);
+  B2F_LAUNCH_CHECK(ctx);
+  return B2F_OK;
+}
+
 int harris_u8_to_float(b2f_ctx *ctx, const unsigned char *s, float *d, size_t n, cudaStream_t st) {
   u8_to_float<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s, d, n);
   B2F_LAUNCH_CHECK(ctx);

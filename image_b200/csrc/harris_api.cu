@@ -247,30 +247,50 @@ void b2f_harris_default_params(b2f_harris_params *p) {   // rcpp_harris.cpp:19-3
   p->Nscales = 1; p->precision = 1; p->cells = 10; p->verbose = 0; p->exact = 0;
 }
 
-int b2f_harris_host(b2f_ctx *ctx, const float *img, int nx, int ny, const b2f_harris_params *p,
-                    float **x, float **y, float **strength, int *n) {
-  if (!ctx || !img || !p || !x || !y || !strength || !n) { set_error("b2f_harris_host: NULL argument"); return B2F_EINVAL; }
-  if (nx <= 0 || ny <= 0) { set_error("b2f_harris_host: bad size %dx%d", nx, ny); return B2F_EINVAL; }
+// img_f (floats, as the reference narrows them) or img_d (R's doubles, narrowed on the device): exactly one is non-NULL
+static int harris_host_any(b2f_ctx *ctx, const float *img_f, const double *img_d, int nx, int ny, const b2f_harris_params *p,
+                           float **x, float **y, float **strength, int *n, const char *who) {
+  if (!ctx || (!img_f && !img_d) || !p || !x || !y || !strength || !n) { set_error("%s: NULL argument", who); return B2F_EINVAL; }
+  if (nx <= 0 || ny <= 0) { set_error("%s: bad size %dx%d", who, nx, ny); return B2F_EINVAL; }
   *x = *y = *strength = nullptr; *n = 0;
   B2F_CUDA(cudaSetDevice(ctx->device));
   size_t plane = (size_t)nx * ny;
   int cap = (nx / 2 + 1) * (ny / 2 + 1);
   // pyramid levels share the arena: bound by 2x the finest level
-  int rc = arena_reserve(ctx, 2 * harris_scratch_bytes(1, nx, ny, p, cap) + align256(plane * 4));
+  int rc = arena_reserve(ctx, 2 * harris_scratch_bytes(1, nx, ny, p, cap) + align256(plane * 4) + (img_d ? align256(plane * 8) : 0));
   if (rc != B2F_OK) return rc;
   float *d_I = ctx->arena.get<float>(plane);
   B2F_ARENA_CHECK(ctx);
-  B2F_CUDA(cudaMemcpyAsync(d_I, img, plane * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  if (img_f) B2F_CUDA(cudaMemcpyAsync(d_I, img_f, plane * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  else {
+    const size_t mark = ctx->arena.off;
+    double *d_raw = ctx->arena.get<double>(plane);
+    B2F_ARENA_CHECK(ctx);
+    B2F_CUDA(cudaMemcpyAsync(d_raw, img_d, plane * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = harris_double_to_float(ctx, d_raw, d_I, plane, ctx->stream)) != B2F_OK) return rc;
+    ctx->arena.off = mark;                                          // (stream order keeps the staging plane alive until it is read)
+  }
   std::vector<Corner> c;
   rc = harris_scale(ctx, d_I, nx, ny, p, p->Nscales, p->sigma_i, harris_mode(p), c);
   if (rc != B2F_OK) return rc;
   size_t m = c.size();
   float *ox = (float *)malloc(sizeof(float) * (m ? m : 1)), *oy = (float *)malloc(sizeof(float) * (m ? m : 1)),
         *os = (float *)malloc(sizeof(float) * (m ? m : 1));
-  if (!ox || !oy || !os) { free(ox); free(oy); free(os); set_error("b2f_harris_host: out of host memory"); return B2F_ENOMEM; }
+  if (!ox || !oy || !os) { free(ox); free(oy); free(os); set_error("%s: out of host memory", who); return B2F_ENOMEM; }
   for (size_t i = 0; i < m; i++) { ox[i] = c[i].x; oy[i] = c[i].y; os[i] = c[i].R; }
   *x = ox; *y = oy; *strength = os; *n = (int)m;
   return B2F_OK;
+}
+
+int b2f_harris_host(b2f_ctx *ctx, const float *img, int nx, int ny, const b2f_harris_params *p,
+                    float **x, float **y, float **strength, int *n) {
+  return harris_host_any(ctx, img, nullptr, nx, ny, p, x, y, strength, n, "b2f_harris_host");
+}
+
+// detect_corners' NumericVector as it is (rcpp_harris.cpp:19-35): the doubles are uploaded and narrowed on the device
+int b2f_harris_host_r64(b2f_ctx *ctx, const double *img, int nx, int ny, const b2f_harris_params *p,
+                        float **x, float **y, float **strength, int *n) {
+  return harris_host_any(ctx, nullptr, img, nx, ny, p, x, y, strength, n, "b2f_harris_host_r64");
 }
 
 int b2f_harris_response_dev(b2f_ctx *ctx, const void *d_frames, int is_u8, int n_frames, int nx, int ny,

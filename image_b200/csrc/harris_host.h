@@ -23,6 +23,7 @@ int harris_nms_device(b2f_ctx *ctx, const float *d_R, int n_frames, int nx, int 
 int mask_row_offsets(b2f_ctx *ctx, const unsigned *mask, int *row_off, int *d_counts, int n_frames, int ny, int wpr, cudaStream_t st);
 int harris_gather3x3(b2f_ctx *ctx, const float *d_R, const int *d_xy, float *d_M, int n, int nx, cudaStream_t st);
 int harris_decimate2(b2f_ctx *ctx, const float *d_src, float *d_dst, int nx, int ny, cudaStream_t st);
+int harris_double_to_float(b2f_ctx *ctx, const double *s, float *d, size_t n, cudaStream_t st);
 int harris_u8_to_float(b2f_ctx *ctx, const unsigned char *s, float *d, size_t n, cudaStream_t st);
 size_t harris_scratch_bytes(int n_frames, int nx, int ny, const b2f_harris_params *p, int cap);
 }  // namespace b2f

@@ -1,4 +1,4 @@
-// b2f_r_context.h — shared by the four Rcpp shims: one lazily created libb200feat context per R
+// b2f_r_context.h — shared by the Rcpp shims: one lazily created libb200feat context per R
 // session (R calls .Call from its main thread only), torn down from R_unload_<pkg> / .onUnload.
 // Errors of the C ABI become R errors through Rcpp::stop (BEGIN_RCPP/END_RCPP in RcppExports.cpp
 // turns the exception into an R condition, like every other Rcpp export of the reference).
@@ -23,12 +23,5 @@ inline b2f_ctx *b2f_r_ctx() {
 inline void b2f_r_shutdown() { b2f_ctx *&c = b2f_r_ctx_slot(); if (c) { b2f_shutdown(c); c = nullptr; } }
 inline void b2f_r_check(int rc) { if (rc != B2F_OK) Rcpp::stop(std::string("libb200feat: ") + b2f_last_error()); }
 
-// Interleaved RGB ints as the R wrappers pass them -> bytes, narrowed like rgb_pixel(...) does in the reference glue.
-inline std::vector<unsigned char> b2f_r_rgb_bytes(const std::vector<int> &v, int rows, int cols, const char *who) {
-  if (v.size() != (size_t)rows * cols * 3) Rcpp::stop(std::string(who) + ": x must hold 3*rows*cols values");
-  std::vector<unsigned char> b(v.size());
-  for (size_t i = 0; i < v.size(); i++) b[i] = (unsigned char)v[i];
-  return b;
-}
 // A malloc'ed float array returned by the C ABI -> std::vector (Rcpp wraps it as a numeric vector); frees the array.
 inline std::vector<float> b2f_r_take(float *p, int n) { std::vector<float> v(p, p + n); b2f_free(p); return v; }

@@ -10,10 +10,10 @@ Rcpp::List canny_edge_detector(Rcpp::IntegerVector image, int X, int Y, double s
   using Rcpp::Named;
   const size_t width = (size_t)X, height = (size_t)Y, pixels = width * height;
   if ((size_t)image.size() != pixels) Rcpp::stop("canny_edge_detector: image length differs from X*Y");
-  std::vector<unsigned char> grey(pixels), edges(pixels);
-  for (size_t q = 0; q < pixels; q++) grey[q] = (unsigned char)image[(long)q];      // the reference narrows the ints like this (:137)
+  std::vector<unsigned char> edges(pixels);
   int on = 0;
-  b2f_r_check(b2f_canny_host(b2f_r_ctx(), grey.data(), X, Y, s, low_thr, high_thr, accGrad ? 1 : 0, edges.data(), &on));
+  // R's ints go up as they are; the (unsigned char) narrowing of the reference (:137) happens on the device
+  b2f_r_check(b2f_canny_host_r32(b2f_r_ctx(), &image[0], X, Y, s, low_thr, high_thr, accGrad ? 1 : 0, edges.data(), &on));
   Rcpp::NumericMatrix map(Rcpp::Dimension(width, height));                          // same linear order as the input
   for (size_t q = 0; q < pixels; q++) map[(long)q] = edges[q];
   return Rcpp::List::create(Named("edges") = map, Named("pixels_nonzero") = on, Named("nx") = width, Named("ny") = height,

@@ -7,13 +7,14 @@
 // [[Rcpp::export]]
 Rcpp::List dlib_fhog(std::vector<int> x, int rows, int cols, const int cell_size = 8, const int filter_rows_padding = 1, const int filter_cols_padding = 1) {
   using Rcpp::Named;
-  const std::vector<unsigned char> pixels = b2f_r_rgb_bytes(x, rows, cols, "dlib_fhog");
+  if (x.size() != (size_t)rows * cols * 3) Rcpp::stop("dlib_fhog: x must hold 3*rows*cols values");
   int height = 0, width = 0;                      // of the feature map, paddings included
   b2f_r_check(b2f_fhog_size(rows, cols, cell_size, filter_rows_padding, filter_cols_padding, &height, &width));
   const size_t cells = (size_t)height * width;
   std::vector<float> cellmajor(cells * 31);       // [y][x][31], the layout of b2f_fhog_host
   if (cells)
-    b2f_r_check(b2f_fhog_host(b2f_r_ctx(), pixels.data(), rows, cols, cell_size, filter_rows_padding, filter_cols_padding, cellmajor.data()));
+    // the ints go up as they are; rgb_pixel(...)'s narrowing (rcpp_fhog.cpp:21-22) happens on the device
+    b2f_r_check(b2f_fhog_host_r32(b2f_r_ctx(), x.data(), rows, cols, cell_size, filter_rows_padding, filter_cols_padding, cellmajor.data()));
   // R reads the vector as array(dim = c(hog_height, hog_width, 31)): feature planes, each column-major
   Rcpp::NumericVector planes((long)(cells * 31));
   for (size_t cell = 0; cell < cells; cell++) {

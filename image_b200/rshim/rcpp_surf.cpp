@@ -7,10 +7,11 @@
 // [[Rcpp::export]]
 Rcpp::List dlib_surf_points(std::vector<int> x, int rows, int cols, long max_points = 10000, double detection_threshold = 30.0) {
   using Rcpp::Named;
-  const std::vector<unsigned char> pixels = b2f_r_rgb_bytes(x, rows, cols, "dlib_surf_points");
+  if (x.size() != (size_t)rows * cols * 3) Rcpp::stop("dlib_surf_points: x must hold 3*rows*cols values");
   b2f_surf_point *kp = nullptr;
   int count = 0;
-  b2f_r_check(b2f_surf_host(b2f_r_ctx(), pixels.data(), rows, cols, max_points, detection_threshold, &kp, &count));
+  // the ints go up as they are; rgb_pixel(...)'s narrowing (rcpp_surf.cpp:21-22) happens on the device
+  b2f_r_check(b2f_surf_host_r32(b2f_r_ctx(), x.data(), rows, cols, max_points, detection_threshold, &kp, &count));
   // one numeric vector per scalar field, and the descriptors as a count x 64 matrix (column-major, like R)
   double b2f_surf_point::*const field[6] = {&b2f_surf_point::x, &b2f_surf_point::y, &b2f_surf_point::angle,
                                             &b2f_surf_point::scale, &b2f_surf_point::score, &b2f_surf_point::laplacian};

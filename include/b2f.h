@@ -49,7 +49,7 @@ void b2f_free(void *p);
 void *b2f_stream(b2f_ctx *ctx);
 /* kernels launched by this context since creation (bench.py reports it as gpu_launches) */
 long long b2f_launch_count(b2f_ctx *ctx);
-/* The host batch calls (*_batch) cut their frames into chunks of about `bytes` input bytes (default 24 MiB)
+/* The host batch calls (*_batch) cut their frames into chunks of about `bytes` input bytes (default 48 MiB)
  * so that the upload of chunk c+1, the kernels of chunk c and the download of chunk c-1 overlap. */
 int b2f_set_chunk_bytes(b2f_ctx *ctx, size_t bytes);
 
@@ -154,6 +154,20 @@ int b2f_surf_batch(b2f_ctx *ctx, const uint8_t *frames, int n_frames, int rows, 
  * of get_surf_points, surf.h:268-285, runs on the host).  Synchronous. */
 int b2f_surf_dev(b2f_ctx *ctx, const uint8_t *d_frames, int n_frames, int rows, int cols, long max_points,
                  double detection_threshold, int cap, b2f_surf_point *points, int *counts, void *stream);
+
+/* ---------------------------------------------------------------- R payloads as they are ----
+ * the vectors the reference's Rcpp exports receive (R `double` for detect_corners, rcpp_harris.cpp:19-35;
+ * R `integer` for canny_edge_detector :122-137, dlib_fhog rcpp_fhog.cpp:10-24, dlib_surf_points rcpp_surf.cpp:10-24) are
+ * uploaded untouched and narrowed ON THE DEVICE with the reference's conversions ((float)double, (unsigned char)int)
+ * instead of in scalar host loops.  Same results as the *_host forms on the narrowed data. */
+int b2f_harris_host_r64(b2f_ctx *ctx, const double *img, int nx, int ny, const b2f_harris_params *p,
+                        float **x, float **y, float **strength, int *n);
+int b2f_canny_host_r32(b2f_ctx *ctx, const int32_t *image, int nx, int ny, double s, double low_thr, double high_thr,
+                       int acc_grad, uint8_t *edges, int *nonzero);
+int b2f_fhog_host_r32(b2f_ctx *ctx, const int32_t *x, int rows, int cols, int cell_size, int filter_rows_padding,
+                      int filter_cols_padding, float *hog);
+int b2f_surf_host_r32(b2f_ctx *ctx, const int32_t *x, int rows, int cols, long max_points, double detection_threshold,
+                      b2f_surf_point **points, int *n);
 
 /* ------------------------------------------------------------------ combined batch ----
  * New surface: Harris corners + Canny edge map + FHOG from ONE upload of each interleaved RGB frame (rows x cols x 3).

@@ -119,7 +119,7 @@ def test_combined_rgb_batch_equals_the_single_detector_calls(oracle):
         try:
             o = features_batch(rgb, harris=dict(threshold=60.0), canny=dict(s=2.0, low_thr=3.0, high_thr=10.0, accGrad=True), fhog=dict(cell=8))
         finally:
-            lib.b2f_set_chunk_bytes(_lib.context(), 24 << 20)
+            lib.b2f_set_chunk_bytes(_lib.context(), 48 << 20)
         hs = harris_batch_u8(grey, threshold=60.0)
         e, nz = canny_batch(grey, accGrad=True)
         h = fhog_batch(rgb)
