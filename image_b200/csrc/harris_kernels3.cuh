@@ -220,6 +220,62 @@ harris_fused3_kernel(const void *__restrict__ frames, float *__restrict__ Rout, 
     const bool generic = generic_all || !harris3_tile_is_interior<C>(x0, y0, nx, ny);
     float mloc = 0.f;
 
+    // ---- stages A+B fused (interior u8 tiles, register-staged): the sigma_d row blur straight from the u8 words ----
+    // A thread takes (row pair, 4 output columns): three 4-byte words per row cover its 4 + 2*RD + OFF input columns;
+    // consecutive lanes = consecutive column groups, so the loads of a warp are contiguous and the row-pair stores are
+    // 16 contiguous bytes per lane.  Bytes become floats with one PRMT into the mantissa of 2^23 and one packed subtract
+    // (no I2F, no float input tile in shared memory: a quarter of the kernel's shared-memory traffic goes away).
+    constexpr bool FUSED_AB = U8 && !TMA;
+    if (FUSED_AB && !generic) {
+      constexpr int GROUPS = C::R1_W / 4;                      // 20
+      constexpr int OFF = C::HALO - C::G - RD;                 // R1 col j uses input cols j+OFF .. j+OFF+2RD
+      constexpr int NW = (4 + 2 * RD + OFF + 3) / 4;           // words per row and item (3)
+      constexpr int RPS = C::R1_H / 2, ITEMS = RPS * GROUPS, PER = (ITEMS + C::NT - 1) / C::NT;
+      static_assert(4 * (GROUPS - 1) + 4 * NW <= C::IN_W, "the last item's words stay inside the input tile");
+      const unsigned char *base = static_cast<const unsigned char *>(frames) + fofs + (size_t)(y0 - C::HALO) * nx + (x0 - C::HALO);
+      unsigned wa[PER][NW], wb[PER][NW];
+#pragma unroll
+      for (int k = 0; k < PER; k++) {
+        const int it = min(tid + k * C::NT, ITEMS - 1), rp = it / GROUPS, g = it - rp * GROUPS;
+        const unsigned *p = reinterpret_cast<const unsigned *>(base + (size_t)(2 * rp) * nx + 4 * g);
+#pragma unroll
+        for (int q = 0; q < NW; q++) { wa[k][q] = __ldg(p + q); wb[k][q] = __ldg(p + q + (nx >> 2)); }
+      }
+      unsigned mx = 0;
+#pragma unroll
+      for (int k = 0; k < PER; k++) {
+        const int it = tid + k * C::NT;
+        if (it < ITEMS) {
+          const int rp = it / GROUPS, g = it - rp * GROUPS;
+          float2 v[4 * NW];                                    // (row 2rp, row 2rp+1) per input column
+#pragma unroll
+          for (int q = 0; q < NW; q++) {
+            mx = __vmaxu4(mx, __vmaxu4(wa[k][q], wb[k][q]));
+#pragma unroll
+            for (int bsel = 0; bsel < 4; bsel++) {
+              const float lo = __uint_as_float(__byte_perm(wa[k][q], 0x4B000000u, 0x7540 + bsel));
+              const float hi = __uint_as_float(__byte_perm(wb[k][q], 0x4B000000u, 0x7540 + bsel));
+              v[4 * q + bsel] = __fadd2_rn(f2(lo, hi), f2s(-8388608.f));
+            }
+          }
+          float2 o[4];
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const int c = j + OFF + RD;
+            float2 acc = __fmul2_rn(f2s(kc.wd[0]), v[c]);
+#pragma unroll
+            for (int t = 1; t <= RD; t++) acc = __ffma2_rn(f2s(kc.wd[t]), __fadd2_rn(v[c - t], v[c + t]), acc);
+            o[j] = acc;
+          }
+          float *d = sR1 + (2 * rp) * C::R1_P + 4 * g;
+          *reinterpret_cast<float4 *>(d) = make_float4(o[0].x, o[1].x, o[2].x, o[3].x);
+          *reinterpret_cast<float4 *>(d + C::R1_P + 2) = make_float4(o[0].y, o[1].y, o[2].y, o[3].y);
+        }
+      }
+      mloc = (float)max(max(mx & 0xff, (mx >> 8) & 0xff), max((mx >> 16) & 0xff, mx >> 24));
+      for (int o = 16; o; o >>= 1) mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, o));
+      if ((tid & 31) == 0) sM[tid >> 5] = mloc;
+    } else {
     // ---- stage A: tile (+12 halo) -> row-pair interleaved float2 tile --------------------------------
     if (!generic) {
       if (TMA) {
@@ -385,6 +441,7 @@ harris_fused3_kernel(const void *__restrict__ frames, float *__restrict__ Rout, 
         }
       }
     }
+    }   // separate stages A and B
     __syncthreads();
 
     // ---- stage C: column blur sigma_d, packed over column pairs -> sISp (row-pair interleaved) -------
