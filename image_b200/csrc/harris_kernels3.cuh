@@ -241,7 +241,6 @@ harris_fused3_kernel(const void *__restrict__ frames, float *__restrict__ Rout, 
 #pragma unroll
         for (int q = 0; q < NW; q++) { wa[k][q] = __ldg(p + q); wb[k][q] = __ldg(p + q + (nx >> 2)); }
       }
-      unsigned mx = 0;
 #pragma unroll
       for (int k = 0; k < PER; k++) {
         const int it = tid + k * C::NT;
@@ -250,7 +249,6 @@ harris_fused3_kernel(const void *__restrict__ frames, float *__restrict__ Rout, 
           float2 v[4 * NW];                                    // (row 2rp, row 2rp+1) per input column
 #pragma unroll
           for (int q = 0; q < NW; q++) {
-            mx = __vmaxu4(mx, __vmaxu4(wa[k][q], wb[k][q]));
 #pragma unroll
             for (int bsel = 0; bsel < 4; bsel++) {
               const float lo = __uint_as_float(__byte_perm(wa[k][q], 0x4B000000u, 0x7540 + bsel));
@@ -272,9 +270,8 @@ harris_fused3_kernel(const void *__restrict__ frames, float *__restrict__ Rout, 
           *reinterpret_cast<float4 *>(d + C::R1_P + 2) = make_float4(o[0].y, o[1].y, o[2].y, o[3].y);
         }
       }
-      mloc = (float)max(max(mx & 0xff, (mx >> 8) & 0xff), max((mx >> 16) & 0xff, mx >> 24));
-      for (int o = 16; o; o >>= 1) mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, o));
-      if ((tid & 31) == 0) sM[tid >> 5] = mloc;
+      if ((tid & 31) == 0) sM[tid >> 5] = 255.f;               // largest |pixel| a u8 tile can hold (the bound's M; a byte-wise maximum
+                                                               // costs more integer instructions than the bound gains in dark tiles)
     } else {
     // ---- stage A: tile (+12 halo) -> row-pair interleaved float2 tile --------------------------------
     if (!generic) {
@@ -458,14 +455,21 @@ harris_fused3_kernel(const void *__restrict__ frames, float *__restrict__ Rout, 
         int rg, cp;
         if (it < MAIN) { rg = it >> 5; cp = it & 31; }
         else { const int u = it - MAIN; rg = u / TAILW; cp = 32 + (u - rg * TAILW); }
-        const int row0 = rg * RB + OFFR;                       // parity of row0 + q is compile-time per q (RB even)
+        const int row0 = rg * RB + OFFR;                       // rg * RB is even: the parity of row0 + q is known per q
+        constexpr bool OVERRUN = RGS * RB + OFFR + 2 * RD > C::R1_H;   // does the last group read past the tile?
+        const float *col = sR1 + row0 * C::R1_P + 2 * cp;
         float2 acc[RB];
 #pragma unroll
         for (int j = 0; j < RB; j++) acc[j] = f2s(0.f);
 #pragma unroll
         for (int q = 0; q < RB + 2 * RD; q++) {
-          const int row = min(row0 + q, C::R1_H - 1);          // clamp (last group overruns)
-          const float2 v = *reinterpret_cast<const float2 *>(sR1 + row * C::R1_P + ((row & 1) << 1) + 2 * cp);
+          float2 v;
+          if (OVERRUN) {
+            const int row = min(row0 + q, C::R1_H - 1);        // clamp (the overrun rows feed outputs that are not stored)
+            v = *reinterpret_cast<const float2 *>(sR1 + row * C::R1_P + ((row & 1) << 1) + 2 * cp);
+          } else {
+            v = *reinterpret_cast<const float2 *>(col + q * C::R1_P + (((OFFR + q) & 1) << 1));
+          }
 #pragma unroll
           for (int j = 0; j < RB; j++) {
             const int t = q - j - RD;
