@@ -662,36 +662,42 @@ harris_fused3_kernel(const void *__restrict__ frames, float *__restrict__ Rout, 
         }
         const int gx = x0 + 2 * cp, gy0 = y0 + r0;
         float *dst = Rout + fofs + (size_t)gy0 * nx + gx;
-        const int blk0 = gy0 >> 3;                             // the item's rows lie in eps block rows blk0, blk0+1
-        float t0 = 0.f, t1 = 0.f;
+        float2 rr[RB];
+        float tmax = 0.f;                                      // largest trace of the item's 2 x RB pixels
 #pragma unroll
         for (int j = 0; j < RB; j++) {
-          float2 r;
           const float2 tr = __fadd2_rn(aa[j], ac[j]);
           if (kc.measure == 0) {                               // Harris: (A*C - B*B) - (k*tr)*tr, each op rounded (harris.cpp:100-103)
             const float2 det = sub2(__fmul2_rn(aa[j], ac[j]), __fmul2_rn(ab[j], ab[j]));
-            r = sub2(det, __fmul2_rn(__fmul2_rn(f2s(kc.k), tr), tr));
+            rr[j] = sub2(det, __fmul2_rn(__fmul2_rn(f2s(kc.k), tr), tr));
           } else {
-            r = f2(corner_measure(aa[j].x, ab[j].x, ac[j].x, kc.k, kc.measure), corner_measure(aa[j].y, ab[j].y, ac[j].y, kc.k, kc.measure));
+            rr[j] = f2(corner_measure(aa[j].x, ab[j].x, ac[j].x, kc.k, kc.measure), corner_measure(aa[j].y, ab[j].y, ac[j].y, kc.k, kc.measure));
           }
-          const float tm = fmaxf(tr.x, tr.y);
-          if (((gy0 + j) >> 3) == blk0) t0 = fmaxf(t0, tm); else t1 = fmaxf(t1, tm);
-          if (!generic) {
-            *reinterpret_cast<float2 *>(dst + (size_t)j * nx) = r;
-          } else if (gy0 + j < ny) {
-            if (gx < nx) dst[(size_t)j * nx] = r.x;
-            if (gx + 1 < nx) dst[(size_t)j * nx + 1] = r.y;
-          }
+          tmax = fmaxf(tmax, fmaxf(tr.x, tr.y));
+        }
+        if (!generic) {
+#pragma unroll
+          for (int j = 0; j < RB; j++) *reinterpret_cast<float2 *>(dst + (size_t)j * nx) = rr[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < RB; j++)
+            if (gy0 + j < ny) {
+              if (gx < nx) dst[(size_t)j * nx] = rr[j].x;
+              if (gx + 1 < nx) dst[(size_t)j * nx + 1] = rr[j].y;
+            }
         }
         if (eps_blk) {
-          // 4 lanes = 8 columns = one eps block column; non-negative floats order like their bit patterns
-          t0 = fmaxf(t0, __shfl_xor_sync(0xffffffffu, t0, 1)); t0 = fmaxf(t0, __shfl_xor_sync(0xffffffffu, t0, 2));
-          t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 1)); t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 2));
-          const int bx = gx >> 3;
+          // The item's RB <= 8 rows touch at most two 8-row eps blocks; both receive the bound of the item's largest trace
+          // (a block's bound may then include a few rows of its neighbour: larger, never smaller).  4 lanes = 8 columns =
+          // one eps block column; non-negative floats order like their bit patterns.
+          tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 1));
+          tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 2));
+          const int bx = gx >> 3, blk0 = gy0 >> 3, blk1 = (gy0 + RB - 1) >> 3;
           if ((cp & 3) == 0 && bx < ebx) {
+            const unsigned e32 = __float_as_uint(harris_eps(tmax, Mtile, kc.k));
             unsigned *e = eps_blk + ((size_t)frame * eby + blk0) * ebx + bx;
-            if (blk0 < eby) atomicMax(e, __float_as_uint(harris_eps(t0, Mtile, kc.k)));
-            if (blk0 + 1 < eby && ((gy0 + RB - 1) >> 3) != blk0) atomicMax(e + ebx, __float_as_uint(harris_eps(t1, Mtile, kc.k)));
+            if (blk0 < eby) atomicMax(e, e32);
+            if (blk1 != blk0 && blk1 < eby) atomicMax(e + ebx, e32);
           }
         }
       }
