@@ -232,20 +232,30 @@ harris_fused3_kernel(const void *__restrict__ frames, float *__restrict__ Rout, 
       constexpr int NW = (4 + 2 * RD + OFF + 3) / 4;           // words per row and item (3)
       constexpr int RPS = C::R1_H / 2, ITEMS = RPS * GROUPS, PER = (ITEMS + C::NT - 1) / C::NT;
       static_assert(4 * (GROUPS - 1) + 4 * NW <= C::IN_W, "the last item's words stay inside the input tile");
-      const unsigned char *base = static_cast<const unsigned char *>(frames) + fofs + (size_t)(y0 - C::HALO) * nx + (x0 - C::HALO);
+      static_assert(C::NT % GROUPS + GROUPS - 1 < 2 * GROUPS, "one carry per step");
+      // 32-bit word offsets from the tile origin; item k of a thread is item k-1 plus NT: (rp, g) advance by
+      // (NT / GROUPS, NT % GROUPS) with one carry — no division per item
+      const unsigned *org = reinterpret_cast<const unsigned *>(static_cast<const unsigned char *>(frames) + fofs + (size_t)(y0 - C::HALO) * nx + (x0 - C::HALO));
+      const int nxw = nx >> 2;                                 // words per frame row
+      constexpr int DRP = C::NT / GROUPS, DG = C::NT % GROUPS;
+      const int rp0 = tid / GROUPS, g0 = tid - rp0 * GROUPS;
       unsigned wa[PER][NW], wb[PER][NW];
+      {
+        int rp = rp0, g = g0;
 #pragma unroll
-      for (int k = 0; k < PER; k++) {
-        const int it = min(tid + k * C::NT, ITEMS - 1), rp = it / GROUPS, g = it - rp * GROUPS;
-        const unsigned *p = reinterpret_cast<const unsigned *>(base + (size_t)(2 * rp) * nx + 4 * g);
+        for (int k = 0; k < PER; k++) {
+          const int rpc = min(rp, RPS - 1);                    // (threads past the last item re-read the last row pair)
+          const unsigned *p = org + (2 * rpc) * nxw + g;
 #pragma unroll
-        for (int q = 0; q < NW; q++) { wa[k][q] = __ldg(p + q); wb[k][q] = __ldg(p + q + (nx >> 2)); }
+          for (int q = 0; q < NW; q++) { wa[k][q] = __ldg(p + q); wb[k][q] = __ldg(p + q + nxw); }
+          g += DG; rp += DRP;
+          if (g >= GROUPS) { g -= GROUPS; rp++; }
+        }
       }
+      int rp = rp0, g = g0;
 #pragma unroll
       for (int k = 0; k < PER; k++) {
-        const int it = tid + k * C::NT;
-        if (it < ITEMS) {
-          const int rp = it / GROUPS, g = it - rp * GROUPS;
+        if (rp < RPS) {
           float2 v[4 * NW];                                    // (row 2rp, row 2rp+1) per input column
 #pragma unroll
           for (int q = 0; q < NW; q++) {
@@ -269,6 +279,8 @@ harris_fused3_kernel(const void *__restrict__ frames, float *__restrict__ Rout, 
           *reinterpret_cast<float4 *>(d) = make_float4(o[0].x, o[1].x, o[2].x, o[3].x);
           *reinterpret_cast<float4 *>(d + C::R1_P + 2) = make_float4(o[0].y, o[1].y, o[2].y, o[3].y);
         }
+        g += DG; rp += DRP;
+        if (g >= GROUPS) { g -= GROUPS; rp++; }
       }
       if ((tid & 31) == 0) sM[tid >> 5] = 255.f;               // largest |pixel| a u8 tile can hold (the bound's M; a byte-wise maximum
                                                                // costs more integer instructions than the bound gains in dark tiles)
