@@ -241,7 +241,9 @@ def main():
                          "(use --impl reference for the CPU reference arm)")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        # (a rank that dies must not leave the others waiting for the default ten minutes)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
     lib = _lib.load()
     ctx = _lib.context(local)
     B = args.batch or wl["batch"]
@@ -427,6 +429,16 @@ def main():
     # ---- sensitivity: the same step on structure-rich frames (the C2 rectangles + discs recipe at this size: thousands of
     #      corners and long edge chains per frame instead of ~60 corners) — NMS vote-outs, certification, hysteresis and the
     #      Canny fp64 fallback are content dependent
+    def timed_local(fn, k):                   # this rank only: no collective inside (used where ranks may diverge)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(k):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
     sens = None
     if args.workload == "composite" and rank == 0:
         try:
@@ -436,9 +448,9 @@ def main():
             step_dev(rich)
             torch.cuda.synchronize()
             ks = max(3, K // 2)
-            ms = timed(lambda: step_dev(rich), ks) / ks
+            ms = timed_local(lambda: step_dev(rich), ks) / ks
             sens = {"frames": "rectangles + discs + noise (SURVEY.md 8d C2 recipe) at %dx%d, grey replicated to RGB" % (NX, NY),
-                    "value": mpix(ms), "unit": "Mpixels/s", "ms_per_step": ms,
+                    "value": mpix(ms), "unit": "Mpixels/s", "ms_per_step": ms, "scope": "rank 0's GPU only",
                     "corners_per_frame": float(d_cnt.float().mean()), "edge_pixel_fraction": float(d_nz.float().mean()) / (NX * NY)}
             del rich
         except Exception as ex:
@@ -446,12 +458,13 @@ def main():
 
     # ---- end to end through the public host API (pinned host in, results back on the host)
     e2e = None
+    e2e_error = None
+    h2d = d2h = 0
     try:
         from image_b200.features import features_batch
         pin_edges = torch.empty((B, NY, NX), dtype=torch.uint8).pin_memory().numpy() if "canny" in dets else None
         pin_hog = torch.empty((B, hnr, hnc, 31), dtype=torch.float32).pin_memory().numpy() if "fhog" in dets else None
         np_host = {k: v.numpy() for k, v in host.items()}
-        h2d = d2h = 0
 
         def step_e2e():
             nonlocal h2d, d2h
@@ -468,22 +481,34 @@ def main():
             d2h = int(o["corners"][3].sum()) * 8 + 8 * B + pin_edges.nbytes + (pin_hog.nbytes if pin_hog is not None else 0)
         for _ in range(2):
             step_e2e()
-        barrier()
-        t0 = time.perf_counter()
-        ke = max(2, K // 2)
-        for _ in range(ke):
-            step_e2e()
-        torch.cuda.synchronize()
-        dt = torch.tensor([(time.perf_counter() - t0) / ke], device="cuda")
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e_ready = True
+    except Exception as ex:   # keep the device-timed line even if the host path fails
+        e2e_ready = False
+        e2e_error = str(ex)
+    # collectives stay outside the try blocks: a rank that failed still takes part in them
+    barrier()
+    ke = max(2, K // 2)
+    dt_local = float("inf")
+    if e2e_ready:
+        try:
+            t0 = time.perf_counter()
+            for _ in range(ke):
+                step_e2e()
+            torch.cuda.synchronize()
+            dt_local = (time.perf_counter() - t0) / ke
+        except Exception as ex:
+            e2e_error = str(ex)
+    dt = torch.tensor([dt_local], device="cuda")
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    if np.isfinite(float(dt.item())):
         api = "surf_batch (b2f_surf_batch)" if "surf" in dets else \
               ("features_batch (b2f_features_batch_rgb: one upload of the RGB frames, grey derived on the device; chunked, three streams)" if "fhog" in dets
                else "features_batch (b2f_features_batch_grey: one upload of the grey frames; chunked, three streams)")
         e2e = {"value": world * B * NX * NY / float(dt.item()) / 1e6, "unit": "Mpixels/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "api": api + ", pinned host buffers"}
-    except Exception as ex:   # keep the device-timed line even if the host path fails
-        e2e = {"value": None, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": str(ex)}
+    else:
+        e2e = {"value": None, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": e2e_error if not e2e_ready or dt_local == float("inf") else "another rank failed"}
 
     # ---- CPU baseline (rank 0, N=1 only): the reference's own code on a bounded sample, in a child process so that its
     #      OpenMP team size and memory stay its own
