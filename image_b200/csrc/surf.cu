@@ -255,13 +255,12 @@ surf_points_kernel(const double *__restrict__ pyr, SurfCand *__restrict__ cand, 
 }
 
 // ------------------------------------------------------------------------------------------ orientation + descriptor
-struct SurfKey { double x, y, scale; int frame; int pad; };
+struct SurfKey { double x, y, scale, score, lap; int frame; int pad; };
 
 __device__ __forceinline__ long long round_half_up(double v) { return (long long)floor(__dadd_rn(v, 0.5)); }   // vector.h:147-148
 
 __global__ void __launch_bounds__(128)
-surf_describe_kernel(const int *__restrict__ sat, const SurfKey *__restrict__ keys, double *__restrict__ angle_out,
-                     double *__restrict__ des_out, int rows, int cols) {
+surf_describe_kernel(const int *__restrict__ sat, const SurfKey *__restrict__ keys, double *__restrict__ rec_out, int rows, int cols) {
   __shared__ double sx[112], sy[112], sang[112];
   __shared__ double wlen[48], wang[48];
   __shared__ double ux[16 * 49], uy[16 * 49];
@@ -356,8 +355,10 @@ surf_describe_kernel(const int *__restrict__ sat, const SurfKey *__restrict__ ke
     s_inv = __ddiv_rn(1.0, len);                                                   // des/len == des * (1/len)
   }
   __syncthreads();
-  if (tid < 64) des_out[(size_t)blockIdx.x * 64 + tid] = __dmul_rn(des[tid], s_inv);
-  if (tid == 0) angle_out[blockIdx.x] = angle;
+  // one complete b2f_surf_point record (70 doubles: x, y, angle, scale, score, laplacian, des[64]) per key point
+  double *rec = rec_out + (size_t)blockIdx.x * 70;
+  if (tid < 64) rec[6 + tid] = __dmul_rn(des[tid], s_inv);
+  if (tid == 0) { rec[0] = kp.x; rec[1] = kp.y; rec[2] = angle; rec[3] = kp.scale; rec[4] = kp.score; rec[5] = kp.lap; }
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -377,13 +378,16 @@ static bool rect_inside(int rows, int cols, double cx, double cy, unsigned long 
 size_t surf_scratch_bytes(int n_frames, const SurfGeom &g, int cand_cap, size_t max_keys) {
   size_t px = (size_t)n_frames * g.rows * g.cols;
   return align256(px * 4) + align256((size_t)n_frames * (g.rows / 96 + 1) * g.cols * 4) /*SAT segment sums*/ + align256((size_t)n_frames * g.pyr_per_frame * 8) + align256((size_t)n_frames * cand_cap * sizeof(SurfCand)) +
-         align256(n_frames * 4) + align256(max_keys * sizeof(SurfKey)) + align256(max_keys * 8) + align256(max_keys * 64 * 8) + (1 << 16);
+         align256(n_frames * 4) + align256(max_keys * sizeof(SurfKey)) + align256(max_keys * 70 * 8) + (1 << 16);
 }
 
 // d_rgb: n_frames interleaved RGB frames on the device.  out[f] receives the key points of frame f.
 // *need_cap: raised to the largest per-frame candidate count when cand_cap was too small (the call then returns B2F_ECAP).
+// Results: counts[f] key points of frame f, the first min(counts[f], cap) of them copied to points + f*cap when `points`
+// is given; with `grow` (single-frame host form) *grow receives a malloc'ed array of exactly counts[0] records instead.
+static_assert(sizeof(b2f_surf_point) == 70 * sizeof(double), "records are 70 packed doubles");
 int surf_device(b2f_ctx *ctx, const unsigned char *d_rgb, int n_frames, const SurfGeom &g, long max_points, double thr,
-                int cand_cap, std::vector<std::vector<b2f_surf_point>> &out, int *need_cap, cudaStream_t st) {
+                int cand_cap, b2f_surf_point *points, int cap, int *counts_out, b2f_surf_point **grow, int *need_cap, cudaStream_t st) {
   const int rows = g.rows, cols = g.cols;
   size_t px = (size_t)n_frames * rows * cols;
   int *sat = ctx->arena.get<int>(px);
@@ -415,7 +419,6 @@ int surf_device(b2f_ctx *ctx, const unsigned char *d_rgb, int n_frames, const Su
   std::vector<int> h_counts(n_frames);
   B2F_CUDA(cudaMemcpyAsync(h_counts.data(), counts, sizeof(int) * n_frames, cudaMemcpyDeviceToHost, st));
   B2F_CUDA(cudaStreamSynchronize(st));
-  out.assign(n_frames, std::vector<b2f_surf_point>());
   size_t total_c = 0;
   std::vector<size_t> c_off(n_frames + 1, 0);
   for (int f = 0; f < n_frames; f++) {
@@ -445,11 +448,7 @@ int surf_device(b2f_ctx *ctx, const unsigned char *d_rgb, int n_frames, const Su
     for (size_t k = 0; k < lim; k++) {
       const unsigned long bsz = (unsigned long)(32 * pts[k].scale);                  // surf.h:275-277
       if (!rect_inside(rows, cols, pts[k].x, pts[k].y, bsz)) continue;
-      b2f_surf_point sp;
-      memset(&sp, 0, sizeof(sp));
-      sp.x = pts[k].x; sp.y = pts[k].y; sp.scale = pts[k].scale; sp.score = pts[k].score; sp.laplacian = pts[k].lap;
-      out[f].push_back(sp);
-      fkeys[f].push_back(SurfKey{sp.x, sp.y, sp.scale, f, 0});
+      fkeys[f].push_back(SurfKey{pts[k].x, pts[k].y, pts[k].scale, pts[k].score, pts[k].lap, f, 0});
     }
   };
   {
@@ -464,25 +463,28 @@ int surf_device(b2f_ctx *ctx, const unsigned char *d_rgb, int n_frames, const Su
   std::vector<size_t> k_off(n_frames + 1, 0);
   for (int f = 0; f < n_frames; f++) { k_off[f] = keys.size(); keys.insert(keys.end(), fkeys[f].begin(), fkeys[f].end()); }
   k_off[n_frames] = keys.size();
+  for (int f = 0; f < n_frames; f++) counts_out[f] = (int)fkeys[f].size();
+  if (grow) *grow = nullptr;
   if (keys.empty()) return B2F_OK;
   const size_t nk = keys.size();
   SurfKey *d_keys = ctx->arena.get<SurfKey>(nk);
-  double *d_ang = ctx->arena.get<double>(nk), *d_des = ctx->arena.get<double>(nk * 64);
+  double *d_rec = ctx->arena.get<double>(nk * 70);
   B2F_ARENA_CHECK(ctx);
   B2F_CUDA(cudaMemcpyAsync(d_keys, keys.data(), sizeof(SurfKey) * nk, cudaMemcpyHostToDevice, st));
-  surf_describe_kernel<<<(unsigned)nk, 128, 0, st>>>(sat, d_keys, d_ang, d_des, rows, cols);
+  surf_describe_kernel<<<(unsigned)nk, 128, 0, st>>>(sat, d_keys, d_rec, rows, cols);
   B2F_LAUNCH_CHECK(ctx);
-  if ((rc = pinned_reserve(ctx, nk * 65 * sizeof(double))) != B2F_OK) return rc;      // (the candidate records are consumed)
-  double *h_ang = static_cast<double *>(ctx->pinned), *h_des = h_ang + nk;
-  B2F_CUDA(cudaMemcpyAsync(h_ang, d_ang, sizeof(double) * nk, cudaMemcpyDeviceToHost, st));
-  B2F_CUDA(cudaMemcpyAsync(h_des, d_des, sizeof(double) * nk * 64, cudaMemcpyDeviceToHost, st));
-  B2F_CUDA(cudaStreamSynchronize(st));
-  for (int f = 0; f < n_frames; f++)
-    for (size_t k = k_off[f]; k < k_off[f + 1]; k++) {
-      b2f_surf_point &sp = out[f][k - k_off[f]];
-      sp.angle = h_ang[k];
-      memcpy(sp.des, h_des + k * 64, sizeof(double) * 64);
+  // the records go straight into the caller's array: no host-side gather
+  if (grow) {
+    *grow = (b2f_surf_point *)malloc(sizeof(b2f_surf_point) * nk);
+    if (!*grow) { set_error("surf: out of host memory"); return B2F_ENOMEM; }
+    B2F_CUDA(cudaMemcpyAsync(*grow, d_rec, sizeof(double) * 70 * nk, cudaMemcpyDeviceToHost, st));
+  } else {
+    for (int f = 0; f < n_frames; f++) {
+      const size_t m = std::min<size_t>(fkeys[f].size(), (size_t)cap);
+      if (m) B2F_CUDA(cudaMemcpyAsync(points + (size_t)f * cap, d_rec + k_off[f] * 70, sizeof(double) * 70 * m, cudaMemcpyDeviceToHost, st));
     }
+  }
+  B2F_CUDA(cudaStreamSynchronize(st));
   return B2F_OK;
 }
 
@@ -498,7 +500,7 @@ static int surf_check(const char *who, int rows, int cols, long max_points, doub
 
 // frames: host memory (uploaded here) or, with on_device, already resident in HBM
 static int surf_run(b2f_ctx *ctx, const uint8_t *frames, bool on_device, int n_frames, int rows, int cols, long max_points, double thr,
-                    std::vector<std::vector<b2f_surf_point>> &out, cudaStream_t st) {
+                    b2f_surf_point *points, int cap, int *counts, b2f_surf_point **grow, cudaStream_t st) {
   SurfGeom g;
   surf_geometry(rows, cols, g);
   // the 3x3x3 test keeps ties, so a flat image can make every sample a candidate: start from a quarter of octave 0
@@ -518,7 +520,7 @@ static int surf_run(b2f_ctx *ctx, const uint8_t *frames, bool on_device, int n_f
       d_in = up;
     }
     int need = cand_cap;
-    rc = surf_device(ctx, d_in, n_frames, g, max_points, thr, cand_cap, out, &need, st);
+    rc = surf_device(ctx, d_in, n_frames, g, max_points, thr, cand_cap, points, cap, counts, grow, &need, st);
     if (rc != B2F_ECAP || need <= cand_cap) return rc;
     cand_cap = need;
   }
@@ -526,16 +528,10 @@ static int surf_run(b2f_ctx *ctx, const uint8_t *frames, bool on_device, int n_f
   return B2F_ECAP;
 }
 
-// per-frame vectors -> the caller's padded [n_frames][cap] array + counts
-static int surf_pack(const std::vector<std::vector<b2f_surf_point>> &out, int n_frames, int cap, b2f_surf_point *points, int *counts, const char *who) {
-  bool over = false;
-  for (int f = 0; f < n_frames; f++) {
-    counts[f] = (int)out[f].size();
-    const size_t m = std::min(out[f].size(), (size_t)cap);
-    over |= out[f].size() > (size_t)cap;
-    if (m) memcpy(points + (size_t)f * cap, out[f].data(), sizeof(b2f_surf_point) * m);
-  }
-  if (over) { set_error("%s: at least one frame has more than cap=%d key points", who, cap); return B2F_ECAP; }
+// B2F_ECAP when a frame produced more key points than the caller's array holds (counts carry the true numbers)
+static int surf_cap_check(const int *counts, int n_frames, int cap, const char *who) {
+  for (int f = 0; f < n_frames; f++)
+    if (counts[f] > cap) { set_error("%s: at least one frame has more than cap=%d key points", who, cap); return B2F_ECAP; }
   return B2F_OK;
 }
 
@@ -551,13 +547,12 @@ int b2f_surf_host(b2f_ctx *ctx, const uint8_t *rgb, int rows, int cols, long max
   *points = nullptr; *n = 0;
   int rc = surf_check("b2f_surf_host", rows, cols, max_points, detection_threshold);
   if (rc != B2F_OK) return rc;
-  std::vector<std::vector<b2f_surf_point>> out;
-  if ((rc = surf_run(ctx, rgb, false, 1, rows, cols, max_points, detection_threshold, out, ctx->stream)) != B2F_OK) return rc;
-  size_t m = out[0].size();
-  b2f_surf_point *p = (b2f_surf_point *)malloc(sizeof(b2f_surf_point) * (m ? m : 1));
+  int count = 0;
+  b2f_surf_point *p = nullptr;
+  if ((rc = surf_run(ctx, rgb, false, 1, rows, cols, max_points, detection_threshold, nullptr, 0, &count, &p, ctx->stream)) != B2F_OK) { free(p); return rc; }
+  if (!p) p = (b2f_surf_point *)malloc(sizeof(b2f_surf_point));       // a valid pointer for b2f_free even when nothing was found
   if (!p) { set_error("b2f_surf_host: out of host memory"); return B2F_ENOMEM; }
-  if (m) memcpy(p, out[0].data(), sizeof(b2f_surf_point) * m);
-  *points = p; *n = (int)m;
+  *points = p; *n = count;
   return B2F_OK;
 }
 
@@ -566,9 +561,8 @@ int b2f_surf_batch(b2f_ctx *ctx, const uint8_t *frames, int n_frames, int rows, 
   if (!ctx || !frames || !points || !counts || n_frames <= 0 || cap <= 0) { set_error("b2f_surf_batch: bad argument"); return B2F_EINVAL; }
   int rc = surf_check("b2f_surf_batch", rows, cols, max_points, detection_threshold);
   if (rc != B2F_OK) return rc;
-  std::vector<std::vector<b2f_surf_point>> out;
-  if ((rc = surf_run(ctx, frames, false, n_frames, rows, cols, max_points, detection_threshold, out, ctx->stream)) != B2F_OK) return rc;
-  return surf_pack(out, n_frames, cap, points, counts, "b2f_surf_batch");
+  if ((rc = surf_run(ctx, frames, false, n_frames, rows, cols, max_points, detection_threshold, points, cap, counts, nullptr, ctx->stream)) != B2F_OK) return rc;
+  return surf_cap_check(counts, n_frames, cap, "b2f_surf_batch");
 }
 
 // frames already resident in HBM (new surface); results land in host memory like b2f_surf_batch (the sort / filter tail of
@@ -580,9 +574,8 @@ int b2f_surf_dev(b2f_ctx *ctx, const uint8_t *d_frames, int n_frames, int rows, 
   if (rc != B2F_OK) return rc;
   cudaStream_t st;
   if ((rc = stream_handoff(ctx, stream, &st)) != B2F_OK) return rc;
-  std::vector<std::vector<b2f_surf_point>> out;
-  if ((rc = surf_run(ctx, d_frames, true, n_frames, rows, cols, max_points, detection_threshold, out, st)) != B2F_OK) return rc;
-  return surf_pack(out, n_frames, cap, points, counts, "b2f_surf_dev");
+  if ((rc = surf_run(ctx, d_frames, true, n_frames, rows, cols, max_points, detection_threshold, points, cap, counts, nullptr, st)) != B2F_OK) return rc;
+  return surf_cap_check(counts, n_frames, cap, "b2f_surf_dev");
 }
 
 }  // extern "C"
