@@ -64,3 +64,11 @@ def canny_dev(d_frames, n_frames, nx, ny, d_edges, d_nonzero, s=2.0, low_thr=3.0
     _lib.check(lib.b2f_canny_dev(ctx or _lib.context(), _lib.ptr(d_frames), n_frames, nx, ny, float(s), float(low_thr),
                                  float(high_thr), int(bool(accGrad)), _lib.ptr(d_edges), _lib.ptr(d_nonzero),
                                  _lib.ptr(stream) if stream is not None else None))
+
+
+def canny_tier2_pixels(ctx=None):
+    """Pixels of this context's Canny calls that went to the exact fp64 tier (b2f_canny_stats)."""
+    lib = _lib.load()
+    n = C.c_ulonglong(0)
+    _lib.check(lib.b2f_canny_stats(ctx or _lib.context(), C.byref(n)))
+    return int(n.value)

@@ -1182,9 +1182,12 @@ int canny_device(b2f_ctx *ctx, const unsigned char *d_frames, int n_frames, int 
         blur, cls, nx, ny, acc_grad ? 1 : 0, (int)low_thr, (int)high_thr);   // thresholds truncate like rcpp_canny.cpp:180
   else
   {
-    static const bool stats = getenv("B2F_CANNY_STATS") != nullptr;
-    unsigned long long *fc = stats ? reinterpret_cast<unsigned long long *>(flags + 8) : nullptr;
-    if (stats) B2F_CUDA(cudaMemsetAsync(fc, 0, 8, st));
+    // pixels sent to the exact tier since the context was created (one atomicAdd per tile that has any): b2f_canny_stats
+    if (!ctx->canny_stats) {
+      B2F_CUDA(cudaMalloc(&ctx->canny_stats, 8));
+      B2F_CUDA(cudaMemsetAsync(ctx->canny_stats, 0, 8, st));
+    }
+    unsigned long long *fc = static_cast<unsigned long long *>(ctx->canny_stats);
     static const bool spec1 = getenv("B2F_CANNY_SPEC1") != nullptr;
     if (spec1)
       canny_grad_nms_spec_kernel<<<dim3(TX, TY, n_frames), CG_NT, 0, st>>>(
@@ -1193,12 +1196,6 @@ int canny_device(b2f_ctx *ctx, const unsigned char *d_frames, int n_frames, int 
       canny_grad_nms_spec2_kernel<true><<<dim3(TX, TY, n_frames), CG_NT, 0, st>>>(blur, cls, nx, ny, (int)low_thr, (int)high_thr, fc);
     else
       canny_grad_nms_spec2_kernel<false><<<dim3(TX, TY, n_frames), CG_NT, 0, st>>>(blur, cls, nx, ny, (int)low_thr, (int)high_thr, fc);
-    if (stats) {
-      unsigned long long h = 0;
-      B2F_CUDA(cudaMemcpyAsync(&h, fc, 8, cudaMemcpyDeviceToHost, st));
-      B2F_CUDA(cudaStreamSynchronize(st));
-      fprintf(stderr, "[b2f] canny tier-2 pixels: %llu of %zu (%.3f %%)\n", h, n, 100.0 * (double)h / (double)n);
-    }
   }
   B2F_LAUNCH_CHECK(ctx);
   B2F_CUDA(cudaMemsetAsync(d_nonzero, 0, sizeof(int) * n_frames, st));
@@ -1230,6 +1227,16 @@ int canny_device(b2f_ctx *ctx, const unsigned char *d_frames, int n_frames, int 
 using namespace b2f;
 
 extern "C" {
+
+int b2f_canny_stats(b2f_ctx *ctx, unsigned long long *tier2_pixels) {
+  if (!ctx || !tier2_pixels) { set_error("b2f_canny_stats: NULL argument"); return B2F_EINVAL; }
+  *tier2_pixels = 0;
+  if (!ctx->canny_stats) return B2F_OK;
+  B2F_CUDA(cudaSetDevice(ctx->device));
+  B2F_CUDA(cudaMemcpyAsync(tier2_pixels, ctx->canny_stats, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  B2F_CUDA(cudaStreamSynchronize(ctx->stream));
+  return B2F_OK;
+}
 
 int b2f_canny_dev(b2f_ctx *ctx, const uint8_t *d_frames, int n_frames, int nx, int ny, double s, double low_thr,
                   double high_thr, int acc_grad, uint8_t *d_edges, int *d_nonzero, void *stream) {

@@ -64,6 +64,7 @@ struct b2f_ctx {
   void *pinned = nullptr; // pinned host staging
   size_t pinned_cap = 0;
   long long launches = 0;
+  void *canny_stats = nullptr;    // device counter (canny.cu): pixels decided by the exact fp64 tier since the context was created
   void *harris_stats = nullptr;   // device PatchStats (harris.cu): certification counters since the context was created
   void *fhog_lut = nullptr;   // 511x511 orientation-snap table (fhog.cu), built on first use
   // FHOG vote tables of the last geometry (fhog.cu): one device block, rebuilt when (rows, cols, cell) changes

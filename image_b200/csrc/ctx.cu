@@ -146,6 +146,7 @@ void b2f_shutdown(b2f_ctx *c) {
   if (c->arena.base) cudaFree(c->arena.base);
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->handoff_event) cudaEventDestroy(c->handoff_event);
+  if (c->canny_stats) cudaFree(c->canny_stats);
   if (c->harris_stats) cudaFree(c->harris_stats);
   if (c->fhog_lut) cudaFree(c->fhog_lut);
   if (c->fhog_tab) cudaFree(c->fhog_tab);

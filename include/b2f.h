@@ -119,6 +119,9 @@ int b2f_canny_dev(b2f_ctx *ctx, const uint8_t *d_frames, int n_frames, int nx, i
                   double low_thr, double high_thr, int acc_grad, uint8_t *d_edges, int *d_nonzero,
                   void *stream);
 
+/* pixels of this context's Canny calls that the fp32 tier could not certify and the exact fp64 tier decided (since b2f_init) */
+int b2f_canny_stats(b2f_ctx *ctx, unsigned long long *tier2_pixels);
+
 /* -------------------------------------------------------------------------------- FHOG ----
  * dlib_fhog: rgb = rows*cols*3 interleaved u8 (x[3*c + 3*cols*r + ch], rcpp_fhog.cpp:19-23).
  * Output `hog` is [hog_nr][hog_nc][31] floats (row, col, feature) — the element order of

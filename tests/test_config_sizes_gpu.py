@@ -81,6 +81,9 @@ def test_canny_4k_against_the_oracle(oracle):
     from image_b200.canny import canny_batch
     rgb = synth.frame_rgb(2000, 2160, 3840)
     grey = (rgb.astype(np.uint16).sum(axis=2) // 3).astype(np.uint8)
+    from image_b200.canny import canny_tier2_pixels
+    before = canny_tier2_pixels()
     edges, nz = canny_batch(grey[None])
     e, cnt = oracle.canny(grey)
     assert int(nz[0]) == cnt and np.array_equal(edges[0], e)
+    assert canny_tier2_pixels() > before, "the exact fp64 tier was never exercised on the bench frame"
