@@ -75,6 +75,7 @@ struct b2f_ctx {
   // chunked host batches (*_batch): copy-in / copy-out streams beside `stream`, and their events
   size_t chunk_bytes = (size_t)48 << 20;   // input bytes per chunk (b2f_set_chunk_bytes, B2F_CHUNK_BYTES); measured 24 / 50 / 100 MiB: 11.1 / 12.4 / 10.6 Gpixel/s end to end
   cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaStream_t s_aux[2] = {nullptr, nullptr};   // the combined batch (features.cu) runs its three detectors side by side: context stream + these two
   std::vector<cudaEvent_t> events;
 };
 

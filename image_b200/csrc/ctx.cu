@@ -92,7 +92,10 @@ int pipe_prepare(b2f_ctx *ctx, int n_events) {
 int pipe_drain(b2f_ctx *ctx) {
   cudaError_t a = ctx->s_in ? cudaStreamSynchronize(ctx->s_in) : cudaSuccess;
   cudaError_t b = cudaStreamSynchronize(ctx->stream);
-  cudaError_t c = ctx->s_out ? cudaStreamSynchronize(ctx->s_out) : cudaSuccess;
+  cudaError_t c = cudaSuccess;
+  for (cudaStream_t s : ctx->s_aux)
+    if (s) { cudaError_t x = cudaStreamSynchronize(s); if (c == cudaSuccess) c = x; }
+  if (ctx->s_out) { cudaError_t x = cudaStreamSynchronize(ctx->s_out); if (c == cudaSuccess) c = x; }
   cudaError_t e = a != cudaSuccess ? a : (b != cudaSuccess ? b : c);
   if (e != cudaSuccess) { cudaGetLastError(); set_error("CUDA error while draining a batch: %s", cudaGetErrorString(e)); return B2F_ECUDA; }
   return B2F_OK;
@@ -152,6 +155,8 @@ void b2f_shutdown(b2f_ctx *c) {
   if (c->fhog_tab) cudaFree(c->fhog_tab);
   if (c->s_in) { cudaStreamSynchronize(c->s_in); cudaStreamDestroy(c->s_in); }
   if (c->s_out) { cudaStreamSynchronize(c->s_out); cudaStreamDestroy(c->s_out); }
+  for (cudaStream_t s : c->s_aux)
+    if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
   for (cudaEvent_t e : c->events) cudaEventDestroy(e);
   cudaStreamDestroy(c->stream);
   delete c;

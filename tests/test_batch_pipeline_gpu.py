@@ -131,3 +131,29 @@ def test_combined_rgb_batch_equals_the_single_detector_calls(oracle):
         assert np.array_equal(o["hog"], h)
         ox, oy, os_ = oracle.harris_detect(grey[2], threshold=60.0, gaussian=0, precision=0)
         assert np.array_equal(x[2, :cnt[2]], ox) and np.array_equal(s[2, :cnt[2]], os_)
+
+
+def test_combined_batch_long_corner_lists_and_uneven_chunk_schedules(oracle):
+    """The chunk schedule (half-size first and last chunk) over batch sizes that do not divide, and corner lists longer
+    than the head that rides home with each chunk (4096 entries): the lists still equal the single-detector call."""
+    from image_b200 import synth, harris_batch_u8, _lib
+    from image_b200.canny import canny_batch
+    from image_b200.features import features_batch
+    lib = _lib.load()
+    rows, cols = 480, 800
+    for n, per_chunk in [(7, 3), (5, 2), (1, 4), (6, 4), (3, 1)]:
+        grey = np.stack([synth.frame_shapes(70 + i, rows, cols) for i in range(n)])
+        grey[0] = np.random.default_rng(7).integers(0, 256, (rows, cols), dtype=np.uint8)     # noise: thousands of corners
+        lib.b2f_set_chunk_bytes(_lib.context(), per_chunk * rows * cols)
+        try:
+            o = features_batch(grey, harris=dict(threshold=1.0, sigma_i=1.0), canny=dict(s=2.0, low_thr=3.0, high_thr=10.0, accGrad=True), corner_cap=60000)
+        finally:
+            lib.b2f_set_chunk_bytes(_lib.context(), 48 << 20)
+        hs = harris_batch_u8(grey, threshold=1.0, sigma_i=1.0, cap=60000)
+        e, nz = canny_batch(grey, accGrad=True)
+        x, y, s, cnt = o["corners"]
+        assert cnt[0] > 4096, cnt
+        for i in range(n):
+            assert cnt[i] == len(hs[i]["x"]) and np.array_equal(x[i, :cnt[i]], hs[i]["x"]) and np.array_equal(y[i, :cnt[i]], hs[i]["y"])
+            assert np.array_equal(s[i, :cnt[i]], hs[i]["strength"])
+        assert np.array_equal(o["edges"], e) and np.array_equal(o["nonzero"], nz)
