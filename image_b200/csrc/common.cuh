@@ -63,6 +63,8 @@ struct b2f_ctx {
   b2f::Arena arena;       // device scratch
   void *pinned = nullptr; // pinned host staging
   size_t pinned_cap = 0;
+  void *pinned_aux[3] = {nullptr, nullptr, nullptr};   // further pinned blocks with their own lifetimes (surf.cu: key staging of the two chunks in flight, counters)
+  size_t pinned_aux_cap[3] = {0, 0, 0};
   long long launches = 0;
   void *canny_stats = nullptr;    // device counter (canny.cu): pixels decided by the exact fp64 tier since the context was created
   void *harris_stats = nullptr;   // device PatchStats (harris.cu): certification counters since the context was created
@@ -85,6 +87,7 @@ namespace b2f {
 // upper bound of its scratch need, then carves buffers with ctx->arena.get<T>(n).
 int arena_reserve(b2f_ctx *ctx, size_t bytes);
 int pinned_reserve(b2f_ctx *ctx, size_t bytes);
+int pinned_reserve_aux(b2f_ctx *ctx, int which, size_t bytes);   // grows block `which` only; the caller knows nothing reads it any more
 // Host batches are cut into chunks of frames so that the upload of chunk c+1, the kernels of chunk c and
 // the download of chunk c-1 overlap (three streams, events between them).  pipe_prepare makes sure the two
 // copy streams and `n_events` events exist and orders the copy-in stream behind whatever the context

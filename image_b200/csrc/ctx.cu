@@ -67,6 +67,23 @@ int pinned_reserve(b2f_ctx *ctx, size_t bytes) {
   return B2F_OK;
 }
 
+int pinned_reserve_aux(b2f_ctx *ctx, int which, size_t bytes) {
+  if (bytes <= ctx->pinned_aux_cap[which]) return B2F_OK;
+  if (ctx->pinned_aux[which]) B2F_CUDA(cudaFreeHost(ctx->pinned_aux[which]));
+  ctx->pinned_aux[which] = nullptr;
+  ctx->pinned_aux_cap[which] = 0;
+  bytes += bytes / 4 + 4096;          // headroom: the next chunk rarely needs a new block
+  void *p = nullptr;
+  cudaError_t e = cudaMallocHost(&p, bytes);
+  if (e != cudaSuccess) {
+    set_error("cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    return B2F_ENOMEM;
+  }
+  ctx->pinned_aux[which] = p;
+  ctx->pinned_aux_cap[which] = bytes;
+  return B2F_OK;
+}
+
 int stream_handoff(b2f_ctx *ctx, void *user_stream, cudaStream_t *out) {
   cudaStream_t st = user_stream ? (cudaStream_t)user_stream : ctx->stream;
   *out = st;
@@ -148,6 +165,8 @@ void b2f_shutdown(b2f_ctx *c) {
   cudaStreamSynchronize(c->stream);
   if (c->arena.base) cudaFree(c->arena.base);
   if (c->pinned) cudaFreeHost(c->pinned);
+  for (void *q : c->pinned_aux)
+    if (q) cudaFreeHost(q);
   if (c->handoff_event) cudaEventDestroy(c->handoff_event);
   if (c->canny_stats) cudaFree(c->canny_stats);
   if (c->harris_stats) cudaFree(c->harris_stats);

@@ -17,6 +17,7 @@
 //   Host (S5, tiny): candidates are put back into emission order, sorted with the very call the
 //   reference uses — std::sort on reverse iterators (surf.h:268) — cut to max_points and border-tested.
 #include "common.cuh"
+#include <chrono>
 #include <algorithm>
 #include <atomic>
 #include <thread>
@@ -108,22 +109,27 @@ __global__ void surf_colsum_kernel(const int *__restrict__ sat, int *__restrict_
   for (; r < r1; r++) acc += __ldg(p + (size_t)r * cols);
   segsum[((size_t)f * nseg + sgm) * cols + c] = acc;
 }
-__global__ void surf_colscan(int *__restrict__ sat, const int *__restrict__ segsum, int rows, int cols, int nseg) {
+// The finished table is written twice: in place (the descriptor pass reads it) and as `split`, where every row holds its
+// even columns first and its odd columns after them (pitch 2 * half).  The pyramid samples sit on an even lattice, so the
+// 32 lanes of a warp read 32 columns of ONE parity: consecutive words in the split copy, every other word in the plain one.
+__global__ void surf_colscan(int *__restrict__ sat, int *__restrict__ split, const int *__restrict__ segsum, int rows, int cols, int nseg) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x, sgm = blockIdx.y, f = blockIdx.z;
   if (c >= cols) return;
   int acc = 0;
   for (int k = 0; k < sgm; k++) acc += __ldg(segsum + ((size_t)f * nseg + k) * cols + c);
   const int r0 = sgm * SEG_ROWS, r1 = min(r0 + SEG_ROWS, rows);
   int *p = sat + (size_t)f * rows * (size_t)cols + c;
+  const int half = (cols + 1) >> 1;
+  int *q = split + (size_t)f * rows * (size_t)(2 * half) + (c & 1) * half + (c >> 1);
   int r = r0;
   for (; r + 8 <= r1; r += 8) {
     int v[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) v[k] = p[(size_t)(r + k) * cols];
 #pragma unroll
-    for (int k = 0; k < 8; k++) { acc += v[k]; p[(size_t)(r + k) * cols] = acc; }
+    for (int k = 0; k < 8; k++) { acc += v[k]; p[(size_t)(r + k) * cols] = acc; q[(size_t)(r + k) * (2 * half)] = acc; }
   }
-  for (; r < r1; r++) { acc += p[(size_t)r * cols]; p[(size_t)r * cols] = acc; }
+  for (; r < r1; r++) { acc += p[(size_t)r * cols]; p[(size_t)r * cols] = acc; q[(size_t)r * (2 * half)] = acc; }
 }
 
 __device__ __forceinline__ int sat_box(const int *__restrict__ S, int nc, int l, int t, int r, int b) {
@@ -151,27 +157,44 @@ __device__ __forceinline__ int sat_haar_y(const int *S, int nc, int px, int py, 
 }
 
 // ------------------------------------------------------------------------------------------ pyramid
+// Sum over columns [l, r], rows [t, b] from the split table; the caller guarantees l >= 1 and t >= 1 (pyramid samples keep a
+// border of 1.5 filter widths, hessian_pyramid.h:118-121, so no box of theirs touches row or column 0).
+struct SplitSat {
+  const int *S;
+  int pitch, half;
+  __device__ __forceinline__ int col(int c) const { return (c & 1) * half + (c >> 1); }
+  __device__ __forceinline__ int box(int l, int t, int r, int b) const {
+    const int cl = col(l - 1), cr = col(r);
+    const int *top = S + (size_t)(t - 1) * pitch, *bot = S + (size_t)b * pitch;
+    return __ldg(bot + cr) - __ldg(bot + cl) - __ldg(top + cr) + __ldg(top + cl);   // br - bl - tr + tl, integral_image.h:64-96
+  }
+  __device__ __forceinline__ int centered(int x, int y, int w, int h) const {
+    const int l = x - w / 2, t = y - h / 2;
+    return box(l, t, l + w - 1, t + h - 1);
+  }
+};
+
 __global__ void __launch_bounds__(256)
-surf_pyramid_kernel(const int *__restrict__ sat, double *__restrict__ pyr, const __grid_constant__ SurfGeom g) {
+surf_pyramid_kernel(const int *__restrict__ split, double *__restrict__ pyr, const __grid_constant__ SurfGeom g) {
   const SurfMap &m = g.m[blockIdx.y];
-  const int *S = sat + (size_t)blockIdx.z * g.rows * (size_t)g.cols;
+  const int half = (g.cols + 1) >> 1;
+  const SplitSat S{split + (size_t)blockIdx.z * g.rows * (size_t)(2 * half), 2 * half, half};
   double *out = pyr + (size_t)blockIdx.z * g.pyr_per_frame + m.off;
   // valid samples: map rows [border, rmax), cols [border, cmax) with r*step < rows - border*step
   const int rmax = (g.rows - m.border * m.step + m.step - 1) / m.step, cmax = (g.cols - m.border * m.step + m.step - 1) / m.step;
   const int wr = rmax - m.border, wc = cmax - m.border;
   if (wr <= 0 || wc <= 0) return;
-  const long long total = (long long)wr * wc;
+  const unsigned total = (unsigned)wr * (unsigned)wc;          // < 2^31: rows * cols * 255 fits int32 (surf_check)
   const int lobe = m.lobe, off = lobe / 2 + 1;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int ri = (int)(idx / wc) + m.border, ci = (int)(idx % wc) + m.border;
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const unsigned q = idx / (unsigned)wc;
+    const int ri = (int)q + m.border, ci = (int)(idx - q * (unsigned)wc) + m.border;
     const int r = ri * m.step, c = ci * m.step;
-    double Dxx = __dsub_rn((double)sat_box_centered(S, g.cols, c, r, lobe * 3, 2 * lobe - 1),
-                           __dmul_rn((double)sat_box_centered(S, g.cols, c, r, lobe, 2 * lobe - 1), 3.0));
-    double Dyy = __dsub_rn((double)sat_box_centered(S, g.cols, c, r, 2 * lobe - 1, lobe * 3),
-                           __dmul_rn((double)sat_box_centered(S, g.cols, c, r, 2 * lobe - 1, lobe), 3.0));
+    double Dxx = __dsub_rn((double)S.centered(c, r, lobe * 3, 2 * lobe - 1), __dmul_rn((double)S.centered(c, r, lobe, 2 * lobe - 1), 3.0));
+    double Dyy = __dsub_rn((double)S.centered(c, r, 2 * lobe - 1, lobe * 3), __dmul_rn((double)S.centered(c, r, 2 * lobe - 1, lobe), 3.0));
     // int32 arithmetic like the reference (value_type sums): bl + tr - tl - br
-    int dxy = sat_box_centered(S, g.cols, c - off, r + off, lobe, lobe) + sat_box_centered(S, g.cols, c + off, r - off, lobe, lobe) -
-              sat_box_centered(S, g.cols, c - off, r - off, lobe, lobe) - sat_box_centered(S, g.cols, c + off, r + off, lobe, lobe);
+    int dxy = S.centered(c - off, r + off, lobe, lobe) + S.centered(c + off, r - off, lobe, lobe) -
+              S.centered(c - off, r - off, lobe, lobe) - S.centered(c + off, r + off, lobe, lobe);
     double Dxy = (double)dxy;
     Dxx = __dmul_rn(Dxx, m.area_inv); Dyy = __dmul_rn(Dyy, m.area_inv); Dxy = __dmul_rn(Dxy, m.area_inv);
     double sign = (__dadd_rn(Dxx, Dyy) < 0) ? -1.0 : 1.0;
@@ -200,9 +223,10 @@ surf_points_kernel(const double *__restrict__ pyr, SurfCand *__restrict__ cand, 
   const int b = mh.border;                                                         // get_border_size(i+1)
   const int wr = m.nr - 2 * b - 2, wc = m.nc - 2 * b - 2;
   if (wr <= 0 || wc <= 0) return;
-  const long long total = (long long)wr * wc;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int r = (int)(idx / wc) + b + 1, c = (int)(idx % wc) + b + 1;
+  const unsigned total = (unsigned)wr * (unsigned)wc;
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const unsigned qr = idx / (unsigned)wc;
+    const int r = (int)qr + b + 1, c = (int)(idx - qr * (unsigned)wc) + b + 1;
     const double val = pval(P, m, r, c);
     if (!(val >= thr)) continue;
     bool is_max = true;
@@ -375,116 +399,156 @@ static bool rect_inside(int rows, int cols, double cx, double cy, unsigned long 
   return l >= 0 && t >= 0 && r <= cols - 1 && b <= rows - 1;
 }
 
+// scratch of ONE chunk of n_frames frames (two chunks are in flight)
 size_t surf_scratch_bytes(int n_frames, const SurfGeom &g, int cand_cap, size_t max_keys) {
   size_t px = (size_t)n_frames * g.rows * g.cols;
-  return align256(px * 4) + align256((size_t)n_frames * (g.rows / 96 + 1) * g.cols * 4) /*SAT segment sums*/ + align256((size_t)n_frames * g.pyr_per_frame * 8) + align256((size_t)n_frames * cand_cap * sizeof(SurfCand)) +
-         align256(n_frames * 4) + align256(max_keys * sizeof(SurfKey)) + align256(max_keys * 70 * 8) + (1 << 16);
+  return align256(px * 4) + align256((size_t)n_frames * g.rows * (size_t)(g.cols + 1) * 4) /*split SAT*/ + align256((size_t)n_frames * (g.rows / SEG_ROWS + 1) * g.cols * 4) /*SAT segment sums*/ +
+         align256((size_t)n_frames * g.pyr_per_frame * 8) + align256((size_t)n_frames * cand_cap * sizeof(SurfCand)) +
+         align256(n_frames * 4) + align256(max_keys * sizeof(SurfKey)) + align256(max_keys * 70 * 8) + (1 << 12);
 }
 
-// d_rgb: n_frames interleaved RGB frames on the device.  out[f] receives the key points of frame f.
-// *need_cap: raised to the largest per-frame candidate count when cand_cap was too small (the call then returns B2F_ECAP).
-// Results: counts[f] key points of frame f, the first min(counts[f], cap) of them copied to points + f*cap when `points`
-// is given; with `grow` (single-frame host form) *grow receives a malloc'ed array of exactly counts[0] records instead.
 static_assert(sizeof(b2f_surf_point) == 70 * sizeof(double), "records are 70 packed doubles");
-int surf_device(b2f_ctx *ctx, const unsigned char *d_rgb, int n_frames, const SurfGeom &g, long max_points, double thr,
-                int cand_cap, b2f_surf_point *points, int cap, int *counts_out, b2f_surf_point **grow, int *need_cap, cudaStream_t st) {
-  const int rows = g.rows, cols = g.cols;
-  size_t px = (size_t)n_frames * rows * cols;
-  int *sat = ctx->arena.get<int>(px);
-  double *pyr = ctx->arena.get<double>((size_t)n_frames * g.pyr_per_frame);
-  SurfCand *cand = ctx->arena.get<SurfCand>((size_t)n_frames * cand_cap);
-  int *counts = ctx->arena.get<int>(n_frames);
-  B2F_ARENA_CHECK(ctx);
-  surf_grey_rowscan<<<dim3(ceil_div(rows, 8), n_frames), 256, 0, st>>>(d_rgb, sat, rows, cols);
-  B2F_LAUNCH_CHECK(ctx);
-  {
-    const int nseg = ceil_div(rows, SEG_ROWS);
-    int *segsum = ctx->arena.get<int>((size_t)n_frames * nseg * cols);
-    B2F_ARENA_CHECK(ctx);
-    surf_colsum_kernel<<<dim3(ceil_div(cols, 128), nseg, n_frames), 128, 0, st>>>(sat, segsum, rows, cols, nseg);
-    B2F_LAUNCH_CHECK(ctx);
-    surf_colscan<<<dim3(ceil_div(cols, 128), nseg, n_frames), 128, 0, st>>>(sat, segsum, rows, cols, nseg);
-    B2F_LAUNCH_CHECK(ctx);
-  }
-  B2F_CUDA(cudaMemsetAsync(pyr, 0, sizeof(double) * (size_t)n_frames * g.pyr_per_frame, st));   // the unread rim
-  B2F_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * n_frames, st));
-  {
-    long long biggest = (long long)g.m[0].nr * g.m[0].nc;
-    int bx = (int)std::min<long long>((biggest + 255) / 256, 4096);
-    surf_pyramid_kernel<<<dim3(bx, S_MAPS, n_frames), 256, 0, st>>>(sat, pyr, g);
-    B2F_LAUNCH_CHECK(ctx);
-    surf_points_kernel<<<dim3(bx, S_OCT * (S_INT - 2), n_frames), 256, 0, st>>>(pyr, cand, counts, cand_cap, thr, g);
-    B2F_LAUNCH_CHECK(ctx);
-  }
-  std::vector<int> h_counts(n_frames);
-  B2F_CUDA(cudaMemcpyAsync(h_counts.data(), counts, sizeof(int) * n_frames, cudaMemcpyDeviceToHost, st));
-  B2F_CUDA(cudaStreamSynchronize(st));
-  size_t total_c = 0;
-  std::vector<size_t> c_off(n_frames + 1, 0);
-  for (int f = 0; f < n_frames; f++) {
-    if (h_counts[f] > cand_cap) { *need_cap = std::max(*need_cap, h_counts[f]); }
-    c_off[f] = total_c;
-    total_c += (size_t)std::min(h_counts[f], cand_cap);
-  }
-  c_off[n_frames] = total_c;
-  if (*need_cap > cand_cap) return B2F_ECAP;               // the caller reruns with the capacity the frames need
-  // all candidate records come back with one synchronisation, into pinned memory
-  int rc = pinned_reserve(ctx, std::max<size_t>(total_c, 1) * sizeof(SurfCand));
+
+struct SurfSlot {   // device scratch of one chunk
+  int *sat, *split, *segsum, *counts;
+  double *pyr, *d_rec;
+  SurfCand *cand;
+  SurfKey *d_keys;
+};
+
+// The frames of a call go through in chunks of C frames, two chunks in flight:
+//   A(c)  SAT, Hessian pyramid, interest points on the GPU, candidate counts to the host
+//   T(c)  host: candidates back, the reference's sort / cut / border filter per frame (surf.h:268-285), a few threads
+//   B(c)  key points to the GPU, orientation + descriptors, records into the caller's array
+// queued as A(0) A(1) B(0) A(2) B(1) ... so the host tail T(c) runs while the GPU works on A(c+1), and (host input) the
+// upload of every chunk — all queued up front on the copy stream — overlaps the chunks before it.
+// d_rgb: all n_frames interleaved RGB frames on the device (e_up[c]: upload of chunk c done, or nullptr).
+// *need_cap: raised when a frame had more candidates than cand_cap (the call then returns B2F_ECAP and the caller reruns).
+// Results: counts_out[f] key points of frame f, the first min(counts_out[f], cap) of them at points + f*cap when `points` is
+// given; with `grow` (single-frame host form) *grow receives a malloc'ed array of exactly counts_out[0] records instead.
+static int surf_pipeline(b2f_ctx *ctx, const unsigned char *d_rgb, const cudaEvent_t *e_up, const cudaEvent_t *e_a, int n_frames, int C,
+                         const SurfGeom &g, long max_points, double thr, int cand_cap, size_t slot_keys, SurfSlot slot[2],
+                         b2f_surf_point *points, int cap, int *counts_out, b2f_surf_point **grow, int *need_cap, cudaStream_t st) {
+  const int rows = g.rows, cols = g.cols, NCH = ceil_div(n_frames, C);
+  const size_t frame_bytes = (size_t)rows * cols * 3;
+  const bool trace = getenv("B2F_SURF_TRACE") != nullptr;   // host-side times of the pipeline on stderr
+  const auto t_enter = std::chrono::steady_clock::now();
+  auto host_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_enter).count(); };
+  int rc = pinned_reserve_aux(ctx, 2, sizeof(int) * (size_t)n_frames);
   if (rc != B2F_OK) return rc;
-  SurfCand *hc_all = static_cast<SurfCand *>(ctx->pinned);
-  for (int f = 0; f < n_frames; f++)
-    if (h_counts[f]) B2F_CUDA(cudaMemcpyAsync(hc_all + c_off[f], cand + (size_t)f * cand_cap, sizeof(SurfCand) * h_counts[f], cudaMemcpyDeviceToHost, st));
-  B2F_CUDA(cudaStreamSynchronize(st));
-  // per frame: emission order, then the reference's sort and filters (surf.h:268-285) — frames are independent, a few host threads share them
-  std::vector<std::vector<SurfKey>> fkeys(n_frames);
-  auto tail = [&](int f) {
-    const int n = h_counts[f];
-    SurfCand *hc = hc_all + c_off[f];
-    std::sort(hc, hc + n, [](const SurfCand &a, const SurfCand &b) { return a.key < b.key; });   // emission order
-    std::vector<ip_mirror> pts(n);
-    for (int k = 0; k < n; k++) pts[k] = ip_mirror{hc[k].x, hc[k].y, hc[k].scale, hc[k].score, hc[k].lap};
-    std::sort(pts.rbegin(), pts.rend());                                             // surf.h:268
-    const size_t lim = std::min((size_t)max_points, pts.size());
-    for (size_t k = 0; k < lim; k++) {
-      const unsigned long bsz = (unsigned long)(32 * pts[k].scale);                  // surf.h:275-277
-      if (!rect_inside(rows, cols, pts[k].x, pts[k].y, bsz)) continue;
-      fkeys[f].push_back(SurfKey{pts[k].x, pts[k].y, pts[k].scale, pts[k].score, pts[k].lap, f, 0});
-    }
+  int *h_counts = static_cast<int *>(ctx->pinned_aux[2]);
+  if (grow) *grow = nullptr;
+
+  auto launch_a = [&](int c) -> int {
+    const SurfSlot &s = slot[c & 1];
+    const int f0 = c * C, nf = std::min(C, n_frames - f0);
+    if (e_up) B2F_CUDA(cudaStreamWaitEvent(st, e_up[c], 0));
+    surf_grey_rowscan<<<dim3(ceil_div(rows, 8), nf), 256, 0, st>>>(d_rgb + frame_bytes * f0, s.sat, rows, cols);
+    B2F_LAUNCH_CHECK(ctx);
+    const int nseg = ceil_div(rows, SEG_ROWS);
+    surf_colsum_kernel<<<dim3(ceil_div(cols, 128), nseg, nf), 128, 0, st>>>(s.sat, s.segsum, rows, cols, nseg);
+    B2F_LAUNCH_CHECK(ctx);
+    surf_colscan<<<dim3(ceil_div(cols, 128), nseg, nf), 128, 0, st>>>(s.sat, s.split, s.segsum, rows, cols, nseg);
+    B2F_LAUNCH_CHECK(ctx);
+    B2F_CUDA(cudaMemsetAsync(s.pyr, 0, sizeof(double) * (size_t)nf * g.pyr_per_frame, st));   // the rim no sample is computed for
+    B2F_CUDA(cudaMemsetAsync(s.counts, 0, sizeof(int) * nf, st));
+    const long long biggest = (long long)g.m[0].nr * g.m[0].nc;
+    const int bx = (int)std::min<long long>((biggest + 255) / 256, 4096);
+    surf_pyramid_kernel<<<dim3(bx, S_MAPS, nf), 256, 0, st>>>(s.split, s.pyr, g);
+    B2F_LAUNCH_CHECK(ctx);
+    surf_points_kernel<<<dim3(bx, S_OCT * (S_INT - 2), nf), 256, 0, st>>>(s.pyr, s.cand, s.counts, cand_cap, thr, g);
+    B2F_LAUNCH_CHECK(ctx);
+    B2F_CUDA(cudaMemcpyAsync(h_counts + f0, s.counts, sizeof(int) * nf, cudaMemcpyDeviceToHost, st));
+    B2F_CUDA(cudaEventRecord(e_a[c], st));
+    return B2F_OK;
   };
-  {
-    const int nt = std::max(1, std::min({n_frames, (int)std::thread::hardware_concurrency(), 16}));
+
+  // T(c): fkeys[f] = the key points of frame f0 + f in output order
+  auto host_tail = [&](int c, std::vector<std::vector<SurfKey>> &fkeys) -> int {
+    const SurfSlot &s = slot[c & 1];
+    const int f0 = c * C, nf = std::min(C, n_frames - f0);
+    B2F_CUDA(cudaEventSynchronize(e_a[c]));
+    size_t total_c = 0;
+    std::vector<size_t> c_off(nf + 1, 0);
+    for (int f = 0; f < nf; f++) {
+      if (h_counts[f0 + f] > cand_cap) *need_cap = std::max(*need_cap, h_counts[f0 + f]);
+      c_off[f] = total_c;
+      total_c += (size_t)std::min(h_counts[f0 + f], cand_cap);
+    }
+    c_off[nf] = total_c;
+    if (*need_cap > cand_cap) return B2F_ECAP;               // the caller reruns with a capacity no frame can exceed
+    // all candidate records of the chunk come back with one synchronisation, into pinned memory, on the copy-out stream
+    // (the compute stream is already busy with the next chunk)
+    if ((rc = pinned_reserve(ctx, std::max<size_t>(total_c, 1) * sizeof(SurfCand))) != B2F_OK) return rc;
+    SurfCand *hc_all = static_cast<SurfCand *>(ctx->pinned);
+    B2F_CUDA(cudaStreamWaitEvent(ctx->s_out, e_a[c], 0));
+    for (int f = 0; f < nf; f++)
+      if (h_counts[f0 + f]) B2F_CUDA(cudaMemcpyAsync(hc_all + c_off[f], s.cand + (size_t)f * cand_cap, sizeof(SurfCand) * h_counts[f0 + f], cudaMemcpyDeviceToHost, ctx->s_out));
+    B2F_CUDA(cudaStreamSynchronize(ctx->s_out));
+    fkeys.assign(nf, {});
+    auto tail = [&](int f) {
+      const int n = h_counts[f0 + f];
+      SurfCand *hc = hc_all + c_off[f];
+      std::sort(hc, hc + n, [](const SurfCand &x, const SurfCand &y) { return x.key < y.key; });   // emission order
+      std::vector<ip_mirror> pts(n);
+      for (int k = 0; k < n; k++) pts[k] = ip_mirror{hc[k].x, hc[k].y, hc[k].scale, hc[k].score, hc[k].lap};
+      std::sort(pts.rbegin(), pts.rend());                                             // surf.h:268
+      const size_t lim = std::min((size_t)max_points, pts.size());
+      for (size_t k = 0; k < lim; k++) {
+        const unsigned long bsz = (unsigned long)(32 * pts[k].scale);                  // surf.h:275-277
+        if (!rect_inside(rows, cols, pts[k].x, pts[k].y, bsz)) continue;
+        fkeys[f].push_back(SurfKey{pts[k].x, pts[k].y, pts[k].scale, pts[k].score, pts[k].lap, f, 0});
+      }
+    };
+    const int nt = std::max(1, std::min({nf, (int)std::thread::hardware_concurrency(), 16}));
     std::atomic<int> next(0);
     std::vector<std::thread> pool;
-    for (int t = 1; t < nt; t++) pool.emplace_back([&] { for (int f; (f = next++) < n_frames;) tail(f); });
-    for (int f; (f = next++) < n_frames;) tail(f);
+    for (int t = 1; t < nt; t++) pool.emplace_back([&] { for (int f; (f = next++) < nf;) tail(f); });
+    for (int f; (f = next++) < nf;) tail(f);
     for (std::thread &t : pool) t.join();
-  }
-  std::vector<SurfKey> keys;
-  std::vector<size_t> k_off(n_frames + 1, 0);
-  for (int f = 0; f < n_frames; f++) { k_off[f] = keys.size(); keys.insert(keys.end(), fkeys[f].begin(), fkeys[f].end()); }
-  k_off[n_frames] = keys.size();
-  for (int f = 0; f < n_frames; f++) counts_out[f] = (int)fkeys[f].size();
-  if (grow) *grow = nullptr;
-  if (keys.empty()) return B2F_OK;
-  const size_t nk = keys.size();
-  SurfKey *d_keys = ctx->arena.get<SurfKey>(nk);
-  double *d_rec = ctx->arena.get<double>(nk * 70);
-  B2F_ARENA_CHECK(ctx);
-  B2F_CUDA(cudaMemcpyAsync(d_keys, keys.data(), sizeof(SurfKey) * nk, cudaMemcpyHostToDevice, st));
-  surf_describe_kernel<<<(unsigned)nk, 128, 0, st>>>(sat, d_keys, d_rec, rows, cols);
-  B2F_LAUNCH_CHECK(ctx);
-  // the records go straight into the caller's array: no host-side gather
-  if (grow) {
-    *grow = (b2f_surf_point *)malloc(sizeof(b2f_surf_point) * nk);
-    if (!*grow) { set_error("surf: out of host memory"); return B2F_ENOMEM; }
-    B2F_CUDA(cudaMemcpyAsync(*grow, d_rec, sizeof(double) * 70 * nk, cudaMemcpyDeviceToHost, st));
-  } else {
-    for (int f = 0; f < n_frames; f++) {
-      const size_t m = std::min<size_t>(fkeys[f].size(), (size_t)cap);
-      if (m) B2F_CUDA(cudaMemcpyAsync(points + (size_t)f * cap, d_rec + k_off[f] * 70, sizeof(double) * 70 * m, cudaMemcpyDeviceToHost, st));
+    return B2F_OK;
+  };
+
+  auto launch_b = [&](int c, const std::vector<std::vector<SurfKey>> &fkeys) -> int {
+    const SurfSlot &s = slot[c & 1];
+    const int f0 = c * C, nf = std::min(C, n_frames - f0);
+    size_t nk = 0;
+    for (int f = 0; f < nf; f++) { counts_out[f0 + f] = (int)fkeys[f].size(); nk += fkeys[f].size(); }
+    if (!nk) return B2F_OK;
+    if (nk > slot_keys) { set_error("internal: surf key buffer under-reserved (%zu > %zu)", nk, slot_keys); return B2F_ENOMEM; }
+    // the pinned staging block of this slot was last read by B(c-2), which the wait for A(c) has seen complete
+    if ((rc = pinned_reserve_aux(ctx, c & 1, nk * sizeof(SurfKey))) != B2F_OK) return rc;
+    SurfKey *hk = static_cast<SurfKey *>(ctx->pinned_aux[c & 1]);
+    std::vector<size_t> k_off(nf + 1, 0);
+    for (int f = 0; f < nf; f++) { std::copy(fkeys[f].begin(), fkeys[f].end(), hk + k_off[f]); k_off[f + 1] = k_off[f] + fkeys[f].size(); }
+    B2F_CUDA(cudaMemcpyAsync(s.d_keys, hk, sizeof(SurfKey) * nk, cudaMemcpyHostToDevice, st));
+    surf_describe_kernel<<<(unsigned)nk, 128, 0, st>>>(s.sat, s.d_keys, s.d_rec, rows, cols);
+    B2F_LAUNCH_CHECK(ctx);
+    // the records go straight into the caller's array: no host-side gather
+    if (grow) {
+      *grow = (b2f_surf_point *)malloc(sizeof(b2f_surf_point) * nk);
+      if (!*grow) { set_error("surf: out of host memory"); return B2F_ENOMEM; }
+      B2F_CUDA(cudaMemcpyAsync(*grow, s.d_rec, sizeof(double) * 70 * nk, cudaMemcpyDeviceToHost, st));
+    } else {
+      for (int f = 0; f < nf; f++) {
+        const size_t m = std::min<size_t>(fkeys[f].size(), (size_t)cap);
+        if (m) B2F_CUDA(cudaMemcpyAsync(points + (size_t)(f0 + f) * cap, s.d_rec + k_off[f] * 70, sizeof(double) * 70 * m, cudaMemcpyDeviceToHost, st));
+      }
     }
+    return B2F_OK;
+  };
+
+  if ((rc = launch_a(0)) != B2F_OK) return rc;
+  std::vector<std::vector<SurfKey>> fkeys;
+  for (int c = 0; c < NCH; c++) {
+    if (c + 1 < NCH && (rc = launch_a(c + 1)) != B2F_OK) return rc;
+    if ((rc = host_tail(c, fkeys)) != B2F_OK) return rc;
+    const double t_tail = host_ms();
+    if ((rc = launch_b(c, fkeys)) != B2F_OK) return rc;
+    if (trace) fprintf(stderr, "surf chunk %d: host tail done %.3f ms, descriptors queued %.3f\n", c, t_tail, host_ms());
   }
   B2F_CUDA(cudaStreamSynchronize(st));
+  if (trace) fprintf(stderr, "surf %d frames in %d chunk(s): done %.3f ms\n", n_frames, NCH, host_ms());
   return B2F_OK;
 }
 
@@ -498,31 +562,65 @@ static int surf_check(const char *who, int rows, int cols, long max_points, doub
   return B2F_OK;
 }
 
-// frames: host memory (uploaded here) or, with on_device, already resident in HBM
+// frames: host memory (uploaded here, chunk by chunk on the copy stream) or, with on_device, already resident in HBM
 static int surf_run(b2f_ctx *ctx, const uint8_t *frames, bool on_device, int n_frames, int rows, int cols, long max_points, double thr,
                     b2f_surf_point *points, int cap, int *counts, b2f_surf_point **grow, cudaStream_t st) {
   SurfGeom g;
   surf_geometry(rows, cols, g);
-  // the 3x3x3 test keeps ties, so a flat image can make every sample a candidate: start from a quarter of octave 0
-  // (far above natural frames) and rerun with the capacity the frames ask for when that is exceeded
+  // The 3x3x3 test keeps ties, so a flat image can make every interior sample a candidate.  Start from a quarter of octave 0
+  // (far above natural frames); when a frame exceeds it, rerun with the number of interior samples, which no frame can exceed.
   int cand_cap = (int)std::min<long long>(std::max<long long>((long long)g.m[0].nr * g.m[0].nc / 4, 1024), 4000000);
+  long long all_samples = 0;
+  for (int o = 0; o < S_OCT; o++)
+    for (int i = 1; i < S_INT - 1; i++) all_samples += (long long)g.m[o * S_INT + i].nr * g.m[o * S_INT + i].nc;
   B2F_CUDA(cudaSetDevice(ctx->device));
-  const size_t in_bytes = (size_t)n_frames * rows * cols * 3;
+  const size_t frame_bytes = (size_t)rows * cols * 3, in_bytes = frame_bytes * n_frames;
+  // chunks of twice the usual input bytes: the host tail of a chunk (one thread per frame) has to fit under the GPU time of the next
+  const int C = frames_per_chunk(ctx, (frame_bytes + 1) / 2, n_frames), NCH = ceil_div(n_frames, C);
   for (int attempt = 0; attempt < 2; attempt++) {
-    const size_t max_keys = (size_t)n_frames * std::min<long long>(max_points, cand_cap);
-    int rc = arena_reserve(ctx, surf_scratch_bytes(n_frames, g, cand_cap, max_keys) + (on_device ? 0 : align256(in_bytes)));
+    const size_t slot_keys = (size_t)C * std::min<long long>(max_points, cand_cap);
+    const size_t slot_bytes = surf_scratch_bytes(C, g, cand_cap, slot_keys);
+    int rc = arena_reserve(ctx, 2 * slot_bytes + (on_device ? 0 : align256(in_bytes)) + 4096);
     if (rc != B2F_OK) return rc;
+    if ((rc = pipe_prepare(ctx, 2 * NCH)) != B2F_OK) return rc;
+    const cudaEvent_t *e_a = ctx->events.data(), *e_up = nullptr;
     const unsigned char *d_in = frames;
     if (!on_device) {
       unsigned char *up = ctx->arena.get<unsigned char>(in_bytes);
       B2F_ARENA_CHECK(ctx);
-      B2F_CUDA(cudaMemcpyAsync(up, frames, in_bytes, cudaMemcpyHostToDevice, st));
+      e_up = ctx->events.data() + NCH;
+      for (int c = 0; c < NCH; c++) {
+        const int f0 = c * C, nf = std::min(C, n_frames - f0);
+        if (cudaMemcpyAsync(up + frame_bytes * f0, frames + frame_bytes * f0, frame_bytes * nf, cudaMemcpyHostToDevice, ctx->s_in) != cudaSuccess ||
+            cudaEventRecord(e_up[c], ctx->s_in) != cudaSuccess) {
+          set_error("surf: upload of chunk %d failed: %s", c, cudaGetErrorString(cudaGetLastError()));
+          pipe_drain(ctx);
+          return B2F_ECUDA;
+        }
+      }
       d_in = up;
     }
+    SurfSlot slot[2];
+    for (SurfSlot &s : slot) {
+      s.sat = ctx->arena.get<int>((size_t)C * rows * cols);
+      s.split = ctx->arena.get<int>((size_t)C * rows * (size_t)(2 * ((cols + 1) / 2)));
+      s.segsum = ctx->arena.get<int>((size_t)C * ceil_div(rows, SEG_ROWS) * cols);
+      s.pyr = ctx->arena.get<double>((size_t)C * g.pyr_per_frame);
+      s.cand = ctx->arena.get<SurfCand>((size_t)C * cand_cap);
+      s.counts = ctx->arena.get<int>(C);
+      s.d_keys = ctx->arena.get<SurfKey>(slot_keys);
+      s.d_rec = ctx->arena.get<double>(slot_keys * 70);
+    }
+    B2F_ARENA_CHECK(ctx);
     int need = cand_cap;
-    rc = surf_device(ctx, d_in, n_frames, g, max_points, thr, cand_cap, points, cap, counts, grow, &need, st);
+    rc = surf_pipeline(ctx, d_in, e_up, e_a, n_frames, C, g, max_points, thr, cand_cap, slot_keys, slot, points, cap, counts, grow, &need, st);
+    if (rc != B2F_OK) {            // nothing of this call may still be in flight when the arena is rewound or the caller reads its arrays
+      cudaStreamSynchronize(st);
+      pipe_drain(ctx);
+      if (grow && *grow) { free(*grow); *grow = nullptr; }
+    }
     if (rc != B2F_ECAP || need <= cand_cap) return rc;
-    cand_cap = need;
+    cand_cap = (int)std::min<long long>(std::max<long long>(need, all_samples), 2147483647LL);
   }
   set_error("surf: candidate capacity could not be established");
   return B2F_ECAP;

@@ -157,3 +157,36 @@ def test_combined_batch_long_corner_lists_and_uneven_chunk_schedules(oracle):
             assert cnt[i] == len(hs[i]["x"]) and np.array_equal(x[i, :cnt[i]], hs[i]["x"]) and np.array_equal(y[i, :cnt[i]], hs[i]["y"])
             assert np.array_equal(s[i, :cnt[i]], hs[i]["strength"])
         assert np.array_equal(o["edges"], e) and np.array_equal(o["nonzero"], nz)
+
+
+def test_surf_batch_chunked_equals_oracle(oracle):
+    """b2f_surf_batch / b2f_surf_dev run their frames through a two-deep chunk pipeline (GPU stages of chunk c+1 under the host
+    tail of chunk c): 5 frames in chunks of 2, 2, 1 give the oracle's lists, and the same records as one chunk."""
+    from image_b200 import synth, _lib
+    from image_b200.dlib import surf_batch
+    lib = _lib.load()
+    rows, cols = 300, 417
+    frames = np.stack([synth.frame_blobs(700 + i, rows, cols) for i in range(5)])
+    ctx = _lib.new_context()
+    try:
+        _lib.check(lib.b2f_set_chunk_bytes(ctx, rows * cols * 3))       # SURF takes twice the usual chunk: 2 frames
+        rec_a, cnt_a = surf_batch(frames, 10000, 10.0, raw=True, ctx=ctx)
+    finally:
+        lib.b2f_shutdown(ctx)
+    rec_b, cnt_b = surf_batch(frames, 10000, 10.0, raw=True)
+    assert np.array_equal(cnt_a, cnt_b) and cnt_a.min() > 0
+    for i in range(5):
+        assert np.array_equal(rec_a[i, :cnt_a[i]], rec_b[i, :cnt_b[i]])
+        ref = oracle.surf(frames[i], 10000, 10.0)
+        assert cnt_a[i] == len(ref["x"]) and np.array_equal(rec_a[i, :cnt_a[i], 0], ref["x"]) and np.array_equal(rec_a[i, :cnt_a[i], 4], ref["score"])
+
+
+def test_surf_flat_frames_rerun_with_a_larger_candidate_capacity(oracle, small_chunks):
+    """A constant image makes every interior sample a 3x3x3 'maximum' (ties survive, hessian_pyramid.h:343-356) when the
+    threshold is 0: far more candidates than the first capacity guess; the call reruns and returns what dlib returns."""
+    from image_b200.dlib import surf_batch
+    frames = np.full((3, 150, 210, 3), 90, np.uint8)
+    outs = surf_batch(frames, 50, 0.0, ctx=small_chunks)
+    ref = oracle.surf(frames[0], 50, 0.0)
+    for o in outs:
+        assert o["points"] == len(ref["x"]) and np.array_equal(o["x"], ref["x"]) and np.array_equal(o["y"], ref["y"])
