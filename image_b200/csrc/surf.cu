@@ -157,51 +157,136 @@ __device__ __forceinline__ int sat_haar_y(const int *S, int nc, int px, int py, 
 }
 
 // ------------------------------------------------------------------------------------------ pyramid
-// Sum over columns [l, r], rows [t, b] from the split table; the caller guarantees l >= 1 and t >= 1 (pyramid samples keep a
-// border of 1.5 filter widths, hessian_pyramid.h:118-121, so no box of theirs touches row or column 0).
-struct SplitSat {
-  const int *S;
-  int pitch, half;
-  __device__ __forceinline__ int col(int c) const { return (c & 1) * half + (c >> 1); }
-  __device__ __forceinline__ int box(int l, int t, int r, int b) const {
-    const int cl = col(l - 1), cr = col(r);
-    const int *top = S + (size_t)(t - 1) * pitch, *bot = S + (size_t)b * pitch;
-    return __ldg(bot + cr) - __ldg(bot + cl) - __ldg(top + cr) + __ldg(top + cl);   // br - bl - tr + tl, integral_image.h:64-96
-  }
-  __device__ __forceinline__ int centered(int x, int y, int w, int h) const {
-    const int l = x - w / 2, t = y - h / 2;
-    return box(l, t, l + w - 1, t + h - 1);
-  }
-};
-
+// The pyramid reads the split table.  Its samples keep a border of 1.5 filter widths (hessian_pyramid.h:118-121), so no
+// box of theirs touches row or column 0 and get_sum_of_area (integral_image.h:64-96) is always its four-corner form.
+// One CTA works on tiles of 2 map rows x 128 map columns.  The 32 table corners of a sample (8 boxes) sit at offsets from
+// the sample's own position that depend on the map only, so they are formed once per thread, before the tile loop; a
+// sample then costs one pointer, 32 loads and the arithmetic (ncu: the first version spent 460 instructions per sample,
+// most of them on 64-bit addressing).
 __global__ void __launch_bounds__(256)
-surf_pyramid_kernel(const int *__restrict__ split, double *__restrict__ pyr, const __grid_constant__ SurfGeom g) {
-  const SurfMap &m = g.m[blockIdx.y];
-  const int half = (g.cols + 1) >> 1;
-  const SplitSat S{split + (size_t)blockIdx.z * g.rows * (size_t)(2 * half), 2 * half, half};
+surf_pyramid_kernel(const int *__restrict__ split, double *__restrict__ pyr, const __grid_constant__ SurfGeom g, int first_map) {
+  const SurfMap &m = g.m[first_map + blockIdx.y];
+  const int half = (g.cols + 1) >> 1, pitch = 2 * half;
+  const int *S = split + (size_t)blockIdx.z * g.rows * (size_t)pitch;
   double *out = pyr + (size_t)blockIdx.z * g.pyr_per_frame + m.off;
   // valid samples: map rows [border, rmax), cols [border, cmax) with r*step < rows - border*step
   const int rmax = (g.rows - m.border * m.step + m.step - 1) / m.step, cmax = (g.cols - m.border * m.step + m.step - 1) / m.step;
   const int wr = rmax - m.border, wc = cmax - m.border;
   if (wr <= 0 || wc <= 0) return;
-  const unsigned total = (unsigned)wr * (unsigned)wc;          // < 2^31: rows * cols * 255 fits int32 (surf_check)
   const int lobe = m.lobe, off = lobe / 2 + 1;
-  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    const unsigned q = idx / (unsigned)wc;
-    const int ri = (int)q + m.border, ci = (int)(idx - q * (unsigned)wc) + m.border;
-    const int r = ri * m.step, c = ci * m.step;
-    double Dxx = __dsub_rn((double)S.centered(c, r, lobe * 3, 2 * lobe - 1), __dmul_rn((double)S.centered(c, r, lobe, 2 * lobe - 1), 3.0));
-    double Dyy = __dsub_rn((double)S.centered(c, r, 2 * lobe - 1, lobe * 3), __dmul_rn((double)S.centered(c, r, 2 * lobe - 1, lobe), 3.0));
-    // int32 arithmetic like the reference (value_type sums): bl + tr - tl - br
-    int dxy = S.centered(c - off, r + off, lobe, lobe) + S.centered(c + off, r - off, lobe, lobe) -
-              S.centered(c - off, r - off, lobe, lobe) - S.centered(c + off, r + off, lobe, lobe);
-    double Dxy = (double)dxy;
-    Dxx = __dmul_rn(Dxx, m.area_inv); Dyy = __dmul_rn(Dyy, m.area_inv); Dxy = __dmul_rn(Dxy, m.area_inv);
-    double sign = (__dadd_rn(Dxx, Dyy) < 0) ? -1.0 : 1.0;
+  // corner (kc, kr) relative to a sample at an EVEN column c (every step is even): parity of c + kc is that of kc, and
+  // (c + kc) >> 1 = c / 2 + (kc >> 1)
+  int o[32];
+  {
+    auto corner = [&](int kc, int kr) { return kr * pitch + (kc & 1) * half + (kc >> 1); };
+    auto centered = [&](int *q, int dx, int dy, int w, int h) {      // centered_rect + get_sum_of_area's four corners
+      const int l = dx - w / 2, t = dy - h / 2, r = l + w - 1, bt = t + h - 1;
+      q[0] = corner(r, bt); q[1] = corner(l - 1, bt); q[2] = corner(r, t - 1); q[3] = corner(l - 1, t - 1);
+    };
+    centered(o + 0, 0, 0, lobe * 3, 2 * lobe - 1);
+    centered(o + 4, 0, 0, lobe, 2 * lobe - 1);
+    centered(o + 8, 0, 0, 2 * lobe - 1, lobe * 3);
+    centered(o + 12, 0, 0, 2 * lobe - 1, lobe);
+    centered(o + 16, -off, off, lobe, lobe);
+    centered(o + 20, off, -off, lobe, lobe);
+    centered(o + 24, -off, -off, lobe, lobe);
+    centered(o + 28, off, off, lobe, lobe);
+  }
+  const int tiles_x = (wc + 127) >> 7, tiles = tiles_x * ((wr + 1) >> 1);
+  const int lx = threadIdx.x & 127, ly = threadIdx.x >> 7;
+  const double area_inv = m.area_inv;
+  for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const int ty = t / tiles_x, tx = t - ty * tiles_x;
+    const int ri = m.border + 2 * ty + ly, ci = m.border + (tx << 7) + lx;
+    if (ri >= rmax || ci >= cmax) continue;
+    const int *P = S + (size_t)(ri * m.step) * pitch + ((ci * m.step) >> 1);
+    int bx[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) bx[j] = __ldg(P + o[4 * j]) - __ldg(P + o[4 * j + 1]) - __ldg(P + o[4 * j + 2]) + __ldg(P + o[4 * j + 3]);   // br - bl - tr + tl
+    double Dxx = __dsub_rn((double)bx[0], __dmul_rn((double)bx[1], 3.0));
+    double Dyy = __dsub_rn((double)bx[2], __dmul_rn((double)bx[3], 3.0));
+    double Dxy = (double)(bx[4] + bx[5] - bx[6] - bx[7]);      // int32 arithmetic like the reference (value_type sums): bl + tr - tl - br
+    Dxx = __dmul_rn(Dxx, area_inv); Dyy = __dmul_rn(Dyy, area_inv); Dxy = __dmul_rn(Dxy, area_inv);
+    const double sign = (__dadd_rn(Dxx, Dyy) < 0) ? -1.0 : 1.0;
     double det = __dsub_rn(__dmul_rn(Dxx, Dyy), __dmul_rn(__dmul_rn(0.81, Dxy), Dxy));
     if (det < 0) det = 0;
     out[(size_t)ri * m.nc + ci] = __dmul_rn(sign, det);
   }
+}
+
+// ---- octave 0 (three quarters of all samples): the six maps of a 64 x 128 pixel tile from ONE shared-memory copy of the table.
+// The generic kernel above is bound by L2 -> L1 traffic (ncu: L1 hit rate 41 %, ~75 B per sample from L2): a sample's 32
+// corners lie on 10 rows that no neighbouring sample row shares.  Here a CTA stages the tile plus a 20-pixel rim
+// (3 * 13 / 2 + 1, the largest filter of the octave) once, 68 KB in the same even / odd column split, and evaluates all six
+// filter sizes from it: ~6 B per sample from L2, and every corner is a conflict-free LDS at a compile-time offset.
+constexpr int P0_SR = 32, P0_SC = 64;              // samples per tile: rows x columns (step 2 -> 64 x 128 pixels)
+constexpr int P0_RIM = 20;
+constexpr int P0_ROWS = 2 * (P0_SR - 1) + 1 + P0_RIM + (P0_RIM - 1);   // rows r0-20 .. r0+62+19 -> 102
+constexpr int P0_HALFW = 84;                       // 83 even + 83 odd columns (c0-20 .. c0+126+19), padded
+constexpr int P0_PITCH = 2 * P0_HALFW;
+constexpr int P0_SMEM = P0_ROWS * P0_PITCH * 4;    // 68 544 B -> 3 CTAs / SM
+static_assert(P0_ROWS == 102, "tile rows");
+
+__host__ __device__ constexpr int p0_off(int kc, int kr) {   // corner (kc, kr) relative to a sample; >> on negative kc floors (arithmetic shift)
+  return kr * P0_PITCH + (kc & 1) * P0_HALFW + (kc >> 1);
+}
+template <int DX, int DY, int W, int H>
+__device__ __forceinline__ int p0_box(const int *__restrict__ q) {       // centered_rect + get_sum_of_area: br - bl - tr + tl
+  constexpr int l = DX - W / 2, t = DY - H / 2, r = l + W - 1, b = t + H - 1;
+  return q[p0_off(r, b)] - q[p0_off(l - 1, b)] - q[p0_off(r, t - 1)] + q[p0_off(l - 1, t - 1)];
+}
+template <int L>
+__device__ __forceinline__ void p0_interval(const int *__restrict__ tile, double *__restrict__ out, const SurfMap &m, int rows, int cols,
+                                            int r0s, int c0s) {        // r0s, c0s: the tile's first sample in map units
+  static_assert(3 * L / 2 + 1 <= P0_RIM, "rim too small for this filter");
+  constexpr int OFF = L / 2 + 1;
+  const int rmax = (rows - m.border * m.step + m.step - 1) / m.step, cmax = (cols - m.border * m.step + m.step - 1) / m.step;
+  const int q = threadIdx.x & (P0_SC - 1), jg = threadIdx.x / P0_SC;
+  const int ci = c0s + q;
+  if (ci < m.border || ci >= cmax) return;
+  const double area_inv = m.area_inv;
+#pragma unroll 2
+  for (int jj = 0; jj < P0_SR / 4; jj++) {
+    const int j = jg * (P0_SR / 4) + jj, ri = r0s + j;
+    if (ri < m.border || ri >= rmax) continue;
+    const int *p = tile + (P0_RIM + 2 * j) * P0_PITCH + P0_RIM / 2 + q;
+    double Dxx = __dsub_rn((double)p0_box<0, 0, 3 * L, 2 * L - 1>(p), __dmul_rn((double)p0_box<0, 0, L, 2 * L - 1>(p), 3.0));
+    double Dyy = __dsub_rn((double)p0_box<0, 0, 2 * L - 1, 3 * L>(p), __dmul_rn((double)p0_box<0, 0, 2 * L - 1, L>(p), 3.0));
+    // int32 arithmetic like the reference (value_type sums): bl + tr - tl - br
+    double Dxy = (double)(p0_box<-OFF, OFF, L, L>(p) + p0_box<OFF, -OFF, L, L>(p) - p0_box<-OFF, -OFF, L, L>(p) - p0_box<OFF, OFF, L, L>(p));
+    Dxx = __dmul_rn(Dxx, area_inv); Dyy = __dmul_rn(Dyy, area_inv); Dxy = __dmul_rn(Dxy, area_inv);
+    const double sign = (__dadd_rn(Dxx, Dyy) < 0) ? -1.0 : 1.0;
+    double det = __dsub_rn(__dmul_rn(Dxx, Dyy), __dmul_rn(__dmul_rn(0.81, Dxy), Dxy));
+    if (det < 0) det = 0;
+    out[m.off + (size_t)ri * m.nc + ci] = __dmul_rn(sign, det);
+  }
+}
+
+__global__ void __launch_bounds__(256, 3)
+surf_pyramid0_kernel(const int *__restrict__ split, double *__restrict__ pyr, const __grid_constant__ SurfGeom g, int tiles_x) {
+  extern __shared__ __align__(16) int p0_tile[];
+  const int half = (g.cols + 1) >> 1, pitch = 2 * half;
+  const int *S = split + (size_t)blockIdx.z * g.rows * (size_t)pitch;
+  double *out = pyr + (size_t)blockIdx.z * g.pyr_per_frame;
+  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+  const int r0s = ty * P0_SR, c0s = tx * P0_SC;                 // first sample (map units); pixels: 2 * r0s, 2 * c0s
+  const int prow0 = 2 * r0s - P0_RIM, pcol0 = 2 * c0s - P0_RIM;  // pixel of tile word (0, 0); pcol0 is even
+  // ---- stage: tile row = 83 even-column words, then (at P0_HALFW) 83 odd-column words, both runs contiguous in the split table
+  for (int it = threadIdx.x; it < P0_ROWS * P0_PITCH; it += 256) {
+    const int tr = it / P0_PITCH, w = it - tr * P0_PITCH;
+    const int par = w >= P0_HALFW, k = w - par * P0_HALFW;
+    const int R = prow0 + tr, Cc = pcol0 + 2 * k + par;
+    int v = 0;
+    if (R >= 0 && R < g.rows && Cc >= 0 && Cc < g.cols && k < P0_HALFW - 1) v = __ldg(S + (size_t)R * pitch + par * half + (Cc >> 1));
+    p0_tile[it] = v;
+  }
+  __syncthreads();
+  p0_interval<3>(p0_tile, out, g.m[0], g.rows, g.cols, r0s, c0s);
+  p0_interval<5>(p0_tile, out, g.m[1], g.rows, g.cols, r0s, c0s);
+  p0_interval<7>(p0_tile, out, g.m[2], g.rows, g.cols, r0s, c0s);
+  p0_interval<9>(p0_tile, out, g.m[3], g.rows, g.cols, r0s, c0s);
+  p0_interval<11>(p0_tile, out, g.m[4], g.rows, g.cols, r0s, c0s);
+  p0_interval<13>(p0_tile, out, g.m[5], g.rows, g.cols, r0s, c0s);
 }
 
 // ------------------------------------------------------------------------------------------ interest points
@@ -214,6 +299,9 @@ __device__ __forceinline__ double pval(const double *__restrict__ P, const SurfM
   return fabs(__ldg(P + m.off + (size_t)r * m.nc + c));
 }
 
+// One CTA works on tiles of 8 map rows x 128 map columns; a thread takes 4 rows of one column and fetches its 4 values
+// before it looks at any of them (ncu on the one-sample-per-iteration version: 73 % of the cycles without an eligible warp,
+// every warp waiting for its single load).  Few samples pass the threshold; those run the 3x3x3 test and the refinement.
 __global__ void __launch_bounds__(256)
 surf_points_kernel(const double *__restrict__ pyr, SurfCand *__restrict__ cand, int *__restrict__ counts, int cap,
                    double thr, const __grid_constant__ SurfGeom g) {
@@ -223,11 +311,20 @@ surf_points_kernel(const double *__restrict__ pyr, SurfCand *__restrict__ cand, 
   const int b = mh.border;                                                         // get_border_size(i+1)
   const int wr = m.nr - 2 * b - 2, wc = m.nc - 2 * b - 2;
   if (wr <= 0 || wc <= 0) return;
-  const unsigned total = (unsigned)wr * (unsigned)wc;
-  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    const unsigned qr = idx / (unsigned)wc;
-    const int r = (int)qr + b + 1, c = (int)(idx - qr * (unsigned)wc) + b + 1;
-    const double val = pval(P, m, r, c);
+  constexpr int PR = 4;
+  const int tiles_x = (wc + 127) >> 7, tiles = tiles_x * ((wr + 2 * PR - 1) / (2 * PR));
+  const int lx = threadIdx.x & 127, ly = threadIdx.x >> 7;
+  for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const int ty = t / tiles_x, tx = t - ty * tiles_x;
+    const int c = (tx << 7) + lx + b + 1, r0 = (2 * ty + ly) * PR + b + 1;
+    if (c - b - 1 >= wc) continue;
+    double vals[PR];
+#pragma unroll
+    for (int k = 0; k < PR; k++) vals[k] = (r0 + k - b - 1 < wr) ? pval(P, m, r0 + k, c) : -1.0;
+#pragma unroll
+    for (int kr = 0; kr < PR; kr++) {
+    const int r = r0 + kr;
+    const double val = vals[kr];
     if (!(val >= thr)) continue;
     bool is_max = true;
     for (int rr = r - 1; rr <= r + 1 && is_max; rr++)
@@ -275,6 +372,7 @@ surf_points_kernel(const double *__restrict__ pyr, SurfCand *__restrict__ cand, 
     q.key = (((long long)(o * S_INT + i) << 40) | ((long long)r << 20) | (long long)c);
     int slot = atomicAdd(&counts[blockIdx.z], 1);
     if (slot < cap) cand[(size_t)blockIdx.z * cap + slot] = q;
+    }
   }
 }
 
@@ -450,12 +548,19 @@ static int surf_pipeline(b2f_ctx *ctx, const unsigned char *d_rgb, const cudaEve
     B2F_LAUNCH_CHECK(ctx);
     surf_colscan<<<dim3(ceil_div(cols, 128), nseg, nf), 128, 0, st>>>(s.sat, s.split, s.segsum, rows, cols, nseg);
     B2F_LAUNCH_CHECK(ctx);
-    B2F_CUDA(cudaMemsetAsync(s.pyr, 0, sizeof(double) * (size_t)nf * g.pyr_per_frame, st));   // the rim no sample is computed for
+    // (the rim of every map, which surf_pyramid_kernel does not compute, is never read: surf_points_kernel stays one
+    //  sample inside the largest border of the three maps it compares)
     B2F_CUDA(cudaMemsetAsync(s.counts, 0, sizeof(int) * nf, st));
     const long long biggest = (long long)g.m[0].nr * g.m[0].nc;
     const int bx = (int)std::min<long long>((biggest + 255) / 256, 4096);
-    surf_pyramid_kernel<<<dim3(bx, S_MAPS, nf), 256, 0, st>>>(s.split, s.pyr, g);
-    B2F_LAUNCH_CHECK(ctx);
+    {   // octave 0 from shared-memory tiles, octaves 1-3 (a quarter of the samples, filters up to 97 pixels) straight from the table
+      const int tiles_x = ceil_div(g.m[0].nc, P0_SC), tiles_y = ceil_div(g.m[0].nr, P0_SR);
+      B2F_CUDA(cudaFuncSetAttribute(surf_pyramid0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P0_SMEM));
+      if (tiles_x > 0 && tiles_y > 0) surf_pyramid0_kernel<<<dim3(tiles_x * tiles_y, 1, nf), 256, P0_SMEM, st>>>(s.split, s.pyr, g, tiles_x);
+      B2F_LAUNCH_CHECK(ctx);
+      surf_pyramid_kernel<<<dim3(std::max(1, bx / 4), S_MAPS - S_INT, nf), 256, 0, st>>>(s.split, s.pyr, g, S_INT);
+      B2F_LAUNCH_CHECK(ctx);
+    }
     surf_points_kernel<<<dim3(bx, S_OCT * (S_INT - 2), nf), 256, 0, st>>>(s.pyr, s.cand, s.counts, cand_cap, thr, g);
     B2F_LAUNCH_CHECK(ctx);
     B2F_CUDA(cudaMemcpyAsync(h_counts + f0, s.counts, sizeof(int) * nf, cudaMemcpyDeviceToHost, st));
