@@ -68,6 +68,7 @@ struct b2f_ctx {
   long long launches = 0;
   void *canny_stats = nullptr;    // device counter (canny.cu): pixels decided by the exact fp64 tier since the context was created
   void *harris_stats = nullptr;   // device PatchStats (harris.cu): certification counters since the context was created
+  void *surf_gauss = nullptr; // 109 Gaussian weights of the SURF orientation samples (surf.cu), built on first use
   void *fhog_lut = nullptr;   // 511x511 orientation-snap table (fhog.cu), built on first use
   // FHOG vote tables of the last geometry (fhog.cu): one device block, rebuilt when (rows, cols, cell) changes
   void *fhog_tab = nullptr;

@@ -170,6 +170,7 @@ void b2f_shutdown(b2f_ctx *c) {
   if (c->handoff_event) cudaEventDestroy(c->handoff_event);
   if (c->canny_stats) cudaFree(c->canny_stats);
   if (c->harris_stats) cudaFree(c->harris_stats);
+  if (c->surf_gauss) cudaFree(c->surf_gauss);
   if (c->fhog_lut) cudaFree(c->fhog_lut);
   if (c->fhog_tab) cudaFree(c->fhog_tab);
   if (c->s_in) { cudaStreamSynchronize(c->s_in); cudaStreamDestroy(c->s_in); }

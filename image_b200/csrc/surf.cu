@@ -299,10 +299,11 @@ __device__ __forceinline__ double pval(const double *__restrict__ P, const SurfM
   return fabs(__ldg(P + m.off + (size_t)r * m.nc + c));
 }
 
-// One CTA works on tiles of 8 map rows x 128 map columns; a thread takes 4 rows of one column and fetches its 4 values
-// before it looks at any of them (ncu on the one-sample-per-iteration version: 73 % of the cycles without an eligible warp,
-// every warp waiting for its single load).  Few samples pass the threshold; those run the 3x3x3 test and the refinement.
-__global__ void __launch_bounds__(256)
+// One CTA works on tiles of 8 map rows x 128 map columns.  Scan: a thread takes 4 rows of one column and fetches its 4
+// values before it looks at any of them (ncu on the one-sample-per-iteration version: 73 % of the cycles without an eligible
+// warp, every warp waiting for its single load); the few samples at or above the threshold go into a shared list.  Then the
+// CTA's threads share the list: 3x3x3 test (one map row = 9 independent loads at a time) and the refinement.
+__global__ void __launch_bounds__(256, 4)
 surf_points_kernel(const double *__restrict__ pyr, SurfCand *__restrict__ cand, int *__restrict__ counts, int cap,
                    double thr, const __grid_constant__ SurfGeom g) {
   const int o = blockIdx.y / (S_INT - 2), i = blockIdx.y % (S_INT - 2) + 1;       // i = 1..4
@@ -311,25 +312,37 @@ surf_points_kernel(const double *__restrict__ pyr, SurfCand *__restrict__ cand, 
   const int b = mh.border;                                                         // get_border_size(i+1)
   const int wr = m.nr - 2 * b - 2, wc = m.nc - 2 * b - 2;
   if (wr <= 0 || wc <= 0) return;
-  constexpr int PR = 4;
-  const int tiles_x = (wc + 127) >> 7, tiles = tiles_x * ((wr + 2 * PR - 1) / (2 * PR));
+  constexpr int PR = 4, TROWS = 2 * PR;
+  __shared__ unsigned short s_pos[TROWS * 128];       // (row in tile) << 7 | column in tile
+  __shared__ int s_n;
+  const int tiles_x = (wc + 127) >> 7, tiles = tiles_x * ((wr + TROWS - 1) / TROWS);
   const int lx = threadIdx.x & 127, ly = threadIdx.x >> 7;
   for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
     const int ty = t / tiles_x, tx = t - ty * tiles_x;
-    const int c = (tx << 7) + lx + b + 1, r0 = (2 * ty + ly) * PR + b + 1;
-    if (c - b - 1 >= wc) continue;
-    double vals[PR];
+    const int tc0 = (tx << 7) + b + 1, tr0 = ty * TROWS + b + 1;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    if ((tx << 7) + lx < wc) {
+      double vals[PR];
 #pragma unroll
-    for (int k = 0; k < PR; k++) vals[k] = (r0 + k - b - 1 < wr) ? pval(P, m, r0 + k, c) : -1.0;
+      for (int k = 0; k < PR; k++) vals[k] = (ty * TROWS + ly * PR + k < wr) ? pval(P, m, tr0 + ly * PR + k, tc0 + lx) : -1.0;
 #pragma unroll
-    for (int kr = 0; kr < PR; kr++) {
-    const int r = r0 + kr;
-    const double val = vals[kr];
-    if (!(val >= thr)) continue;
+      for (int k = 0; k < PR; k++)
+        if (vals[k] >= thr) s_pos[atomicAdd(&s_n, 1)] = (unsigned short)(((ly * PR + k) << 7) | lx);
+    }
+    __syncthreads();
+    const int n_list = s_n;
+    for (int li = threadIdx.x; li < n_list; li += 256) {
+    const int r = tr0 + (s_pos[li] >> 7), c = tc0 + (s_pos[li] & 127);
+    const double val = pval(P, m, r, c);
     bool is_max = true;
-    for (int rr = r - 1; rr <= r + 1 && is_max; rr++)
-      for (int cc = c - 1; cc <= c + 1; cc++)
-        if (pval(P, ml, rr, cc) > val || pval(P, m, rr, cc) > val || pval(P, mh, rr, cc) > val) { is_max = false; break; }
+    for (int rr = r - 1; rr <= r + 1 && is_max; rr++) {
+      double nb[9];
+#pragma unroll
+      for (int q = 0; q < 3; q++) { nb[q] = pval(P, ml, rr, c - 1 + q); nb[3 + q] = pval(P, m, rr, c - 1 + q); nb[6 + q] = pval(P, mh, rr, c - 1 + q); }
+#pragma unroll
+      for (int q = 0; q < 9; q++) is_max = is_max && !(nb[q] > val);
+    }
     if (!is_max) continue;
     // interpolate_point (hessian_pyramid.h:360-446)
     const double vxp = pval(P, m, r, c + 1), vxm = pval(P, m, r, c - 1), vyp = pval(P, m, r + 1, c), vym = pval(P, m, r - 1, c);
@@ -373,6 +386,7 @@ surf_points_kernel(const double *__restrict__ pyr, SurfCand *__restrict__ cand, 
     int slot = atomicAdd(&counts[blockIdx.z], 1);
     if (slot < cap) cand[(size_t)blockIdx.z * cap + slot] = q;
     }
+    __syncthreads();           // the list is rewritten by the next tile
   }
 }
 
@@ -381,35 +395,49 @@ struct SurfKey { double x, y, scale, score, lap; int frame; int pad; };
 
 __device__ __forceinline__ long long round_half_up(double v) { return (long long)floor(__dadd_rn(v, 0.5)); }   // vector.h:147-148
 
+// The 109 sample offsets of compute_dominant_angle (surf.h:99-115): (r, c) in [-6, 6]^2 with r^2 + c^2 < 36, raster order.
+struct DomOffsets { signed char r[112], c[112]; };
+static constexpr DomOffsets make_dom_offsets() {
+  DomOffsets t{};
+  int n = 0;
+  for (int r = -6; r <= 6; r++)
+    for (int c = -6; c <= 6; c++)
+      if (r * r + c * c < 36) { t.r[n] = (signed char)r; t.c[n] = (signed char)c; n++; }
+  return t;
+}
+__constant__ DomOffsets c_dom = make_dom_offsets();
+
+// Their Gaussian weights (sigma 2.5) depend on the offset only: one table per context, built by the device's own exp()
+// with the operation order the descriptor kernel used to run per key point.
+__global__ void surf_gauss_table_kernel(double *__restrict__ tab) {
+  const int tid = threadIdx.x;
+  if (tid >= 109) return;
+  const double x = (double)c_dom.c[tid], y = (double)c_dom.r[tid], sig = 2.5;
+  tab[tid] = __dmul_rn(__ddiv_rn(1.0, __dmul_rn(sig, 2.5066282746310002416123552393401041626930)),
+                       exp(__ddiv_rn(-__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(__dmul_rn(2.0, sig), sig))));
+}
+
 __global__ void __launch_bounds__(128)
-surf_describe_kernel(const int *__restrict__ sat, const SurfKey *__restrict__ keys, double *__restrict__ rec_out, int rows, int cols) {
+surf_describe_kernel(const int *__restrict__ sat, const SurfKey *__restrict__ keys, const double *__restrict__ gauss_tab,
+                     double *__restrict__ rec_out, int rows, int cols) {
   __shared__ double sx[112], sy[112], sang[112];
   __shared__ double wlen[48], wang[48];
   __shared__ double ux[16 * 49], uy[16 * 49];
   __shared__ double des[64];
-  __shared__ double s_angle, s_inv;
+  __shared__ double s_angle, s_inv, s_rot[4];
   const SurfKey kp = keys[blockIdx.x];
   const int *S = sat + (size_t)kp.frame * rows * (size_t)cols;
   const double PI = 3.1415926535897932384626433832795;
   const int tid = threadIdx.x;
   const long long sc = (long long)__dadd_rn(kp.scale, 0.5);
-  // ---- samples of compute_dominant_angle (surf.h:99-115): (r,c) in [-6,6]^2 with r^2+c^2 < 36, raster order
-  if (tid < 112) {
-    // enumerate: the tid-th valid offset
-    int n = 0, rr = 0, cc = 0;
-    bool found = false;
-    for (int r = -6; r <= 6 && !found; r++)
-      for (int c = -6; c <= 6; c++)
-        if (r * r + c * c < 36) { if (n == tid) { rr = r; cc = c; found = true; break; } n++; }
-    if (found) {
-      const double x = (double)cc, y = (double)rr, sig = 2.5;
-      const double gauss = __dmul_rn(__ddiv_rn(1.0, __dmul_rn(sig, 2.5066282746310002416123552393401041626930)),
-                                     exp(__ddiv_rn(-__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(__dmul_rn(2.0, sig), sig))));
-      const int px = (int)round_half_up(__dadd_rn((double)(sc * cc), kp.x)), py = (int)round_half_up(__dadd_rn((double)(sc * rr), kp.y));
-      const double hx = __dmul_rn(gauss, (double)sat_haar_x(S, cols, px, py, (int)(4 * sc)));
-      const double hy = __dmul_rn(gauss, (double)sat_haar_y(S, cols, px, py, (int)(4 * sc)));
-      sx[tid] = hx; sy[tid] = hy; sang[tid] = atan2(hy, hx);
-    }
+  // ---- samples of compute_dominant_angle (surf.h:99-115)
+  if (tid < 109) {
+    const int rr = c_dom.r[tid], cc = c_dom.c[tid];
+    const double gauss = __ldg(gauss_tab + tid);
+    const int px = (int)round_half_up(__dadd_rn((double)(sc * cc), kp.x)), py = (int)round_half_up(__dadd_rn((double)(sc * rr), kp.y));
+    const double hx = __dmul_rn(gauss, (double)sat_haar_x(S, cols, px, py, (int)(4 * sc)));
+    const double hy = __dmul_rn(gauss, (double)sat_haar_y(S, cols, px, py, (int)(4 * sc)));
+    sx[tid] = hx; sy[tid] = hy; sang[tid] = atan2(hy, hx);
   }
   __syncthreads();
   // ---- 45 sliding windows (surf.h:118-150): one thread per window, samples added in index order
@@ -426,18 +454,18 @@ surf_describe_kernel(const int *__restrict__ sat, const SurfKey *__restrict__ ke
     wang[tid] = atan2(vy, vx);
   }
   __syncthreads();
-  if (tid == 0) {
+  if (tid < 64 && (tid & 31) == 0) {          // two threads (one per warp): the rotation and its inverse
     double max_length = 0, best = 0;
     for (int k = 0; k < 45; k++) if (wlen[k] > max_length) { max_length = wlen[k]; best = wang[k]; }
-    s_angle = best;
+    double sn, cs;
+    if (tid == 0) { s_angle = best; sincos(best, &sn, &cs); s_rot[0] = sn; s_rot[1] = cs; }
+    else { sincos(-best, &sn, &cs); s_rot[2] = sn; s_rot[3] = cs; }
   }
   __syncthreads();
   const double angle = s_angle;
   // ---- descriptor (surf.h:176-231): 16 cells x up to 7x7 samples; sample values first, in parallel
   {
-    double sn, cs, isn, ics;
-    sincos(angle, &sn, &cs);
-    sincos(-angle, &isn, &ics);
+    const double sn = s_rot[0], cs = s_rot[1], isn = s_rot[2], ics = s_rot[3];
     for (int s = tid; s < 16 * 49; s += blockDim.x) {
       const int cell = s / 49, k = s - cell * 49;
       const int r = -10 + 5 * (cell / 4), c = -10 + 5 * (cell % 4);
@@ -536,6 +564,12 @@ static int surf_pipeline(b2f_ctx *ctx, const unsigned char *d_rgb, const cudaEve
   if (rc != B2F_OK) return rc;
   int *h_counts = static_cast<int *>(ctx->pinned_aux[2]);
   if (grow) *grow = nullptr;
+  if (!ctx->surf_gauss) {        // first SURF call of the context (the call synchronises `st` before it returns)
+    B2F_CUDA(cudaMalloc(&ctx->surf_gauss, 112 * sizeof(double)));
+    surf_gauss_table_kernel<<<1, 128, 0, st>>>(static_cast<double *>(ctx->surf_gauss));
+    B2F_LAUNCH_CHECK(ctx);
+  }
+  const double *gauss_tab = static_cast<const double *>(ctx->surf_gauss);
 
   auto launch_a = [&](int c) -> int {
     const SurfSlot &s = slot[c & 1];
@@ -627,7 +661,7 @@ static int surf_pipeline(b2f_ctx *ctx, const unsigned char *d_rgb, const cudaEve
     std::vector<size_t> k_off(nf + 1, 0);
     for (int f = 0; f < nf; f++) { std::copy(fkeys[f].begin(), fkeys[f].end(), hk + k_off[f]); k_off[f + 1] = k_off[f] + fkeys[f].size(); }
     B2F_CUDA(cudaMemcpyAsync(s.d_keys, hk, sizeof(SurfKey) * nk, cudaMemcpyHostToDevice, st));
-    surf_describe_kernel<<<(unsigned)nk, 128, 0, st>>>(s.sat, s.d_keys, s.d_rec, rows, cols);
+    surf_describe_kernel<<<(unsigned)nk, 128, 0, st>>>(s.sat, s.d_keys, gauss_tab, s.d_rec, rows, cols);
     B2F_LAUNCH_CHECK(ctx);
     // the records go straight into the caller's array: no host-side gather
     if (grow) {
