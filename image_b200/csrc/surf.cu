@@ -530,7 +530,7 @@ size_t surf_scratch_bytes(int n_frames, const SurfGeom &g, int cand_cap, size_t 
   size_t px = (size_t)n_frames * g.rows * g.cols;
   return align256(px * 4) + align256((size_t)n_frames * g.rows * (size_t)(g.cols + 1) * 4) /*split SAT*/ + align256((size_t)n_frames * (g.rows / SEG_ROWS + 1) * g.cols * 4) /*SAT segment sums*/ +
          align256((size_t)n_frames * g.pyr_per_frame * 8) + align256((size_t)n_frames * cand_cap * sizeof(SurfCand)) +
-         align256(n_frames * 4) + align256(max_keys * sizeof(SurfKey)) + align256(max_keys * 70 * 8) + (1 << 12);
+         align256(n_frames * 4) + align256(max_keys * 70 * 8) + (1 << 12);
 }
 
 static_assert(sizeof(b2f_surf_point) == 70 * sizeof(double), "records are 70 packed doubles");
@@ -539,7 +539,6 @@ struct SurfSlot {   // device scratch of one chunk
   int *sat, *split, *segsum, *counts;
   double *pyr, *d_rec;
   SurfCand *cand;
-  SurfKey *d_keys;
 };
 
 // The frames of a call go through in chunks of C frames, two chunks in flight:
@@ -660,8 +659,9 @@ static int surf_pipeline(b2f_ctx *ctx, const unsigned char *d_rgb, const cudaEve
     SurfKey *hk = static_cast<SurfKey *>(ctx->pinned_aux[c & 1]);
     std::vector<size_t> k_off(nf + 1, 0);
     for (int f = 0; f < nf; f++) { std::copy(fkeys[f].begin(), fkeys[f].end(), hk + k_off[f]); k_off[f + 1] = k_off[f] + fkeys[f].size(); }
-    B2F_CUDA(cudaMemcpyAsync(s.d_keys, hk, sizeof(SurfKey) * nk, cudaMemcpyHostToDevice, st));
-    surf_describe_kernel<<<(unsigned)nk, 128, 0, st>>>(s.sat, s.d_keys, gauss_tab, s.d_rec, rows, cols);
+    // The kernel reads the key points straight from the pinned block (56 B per CTA over the link): a host->device copy here
+    // would queue on the copy engine behind the frame uploads still in flight and hold up everything behind it on `st`.
+    surf_describe_kernel<<<(unsigned)nk, 128, 0, st>>>(s.sat, hk, gauss_tab, s.d_rec, rows, cols);
     B2F_LAUNCH_CHECK(ctx);
     // the records go straight into the caller's array: no host-side gather
     if (grow) {
@@ -730,8 +730,10 @@ static int surf_run(b2f_ctx *ctx, const uint8_t *frames, bool on_device, int n_f
       e_up = ctx->events.data() + NCH;
       for (int c = 0; c < NCH; c++) {
         const int f0 = c * C, nf = std::min(C, n_frames - f0);
-        if (cudaMemcpyAsync(up + frame_bytes * f0, frames + frame_bytes * f0, frame_bytes * nf, cudaMemcpyHostToDevice, ctx->s_in) != cudaSuccess ||
-            cudaEventRecord(e_up[c], ctx->s_in) != cudaSuccess) {
+        bool ok = true;
+        for (int f = f0; f < f0 + nf && ok; f++)      // frame by frame: short copies leave gaps for the result copies of earlier chunks
+          ok = cudaMemcpyAsync(up + frame_bytes * f, frames + frame_bytes * f, frame_bytes, cudaMemcpyHostToDevice, ctx->s_in) == cudaSuccess;
+        if (!ok || cudaEventRecord(e_up[c], ctx->s_in) != cudaSuccess) {
           set_error("surf: upload of chunk %d failed: %s", c, cudaGetErrorString(cudaGetLastError()));
           pipe_drain(ctx);
           return B2F_ECUDA;
@@ -747,7 +749,6 @@ static int surf_run(b2f_ctx *ctx, const uint8_t *frames, bool on_device, int n_f
       s.pyr = ctx->arena.get<double>((size_t)C * g.pyr_per_frame);
       s.cand = ctx->arena.get<SurfCand>((size_t)C * cand_cap);
       s.counts = ctx->arena.get<int>(C);
-      s.d_keys = ctx->arena.get<SurfKey>(slot_keys);
       s.d_rec = ctx->arena.get<double>(slot_keys * 70);
     }
     B2F_ARENA_CHECK(ctx);
