@@ -912,7 +912,7 @@ static int response_exact(b2f_ctx *ctx, float *d_I, int n_frames, int nx, int ny
 int harris_response_device(b2f_ctx *ctx, const void *d_frames, bool u8, int n_frames, int nx, int ny,
                            const b2f_harris_params *p, int exact, float *d_R, cudaStream_t st) {
   if (!exact && harris_fused_supported(nx, ny, p->sigma_d, p->sigma_i, p->gaussian))
-    return harris_fused_launch(ctx, d_frames, u8, n_frames, nx, ny, p, d_R, nullptr, st);
+    return harris_fused_launch(ctx, d_frames, u8, n_frames, nx, ny, p, d_R, nullptr, false, st);
   size_t tot = (size_t)nx * ny * n_frames;
   float *I = ctx->arena.get<float>(tot);
   B2F_ARENA_CHECK(ctx);
@@ -1007,7 +1007,7 @@ int harris_corners_certified(b2f_ctx *ctx, const void *d_frames, bool u8, int n_
     B2F_CUDA(cudaMemsetAsync(ctx->harris_stats, 0, sizeof(PatchStats), st));
   }
   B2F_CUDA(cudaMemsetAsync(eps, 0, sizeof(unsigned) * (size_t)n_frames * ebx * eby, st));
-  int rc = harris_fused_launch(ctx, d_frames, u8, n_frames, nx, ny, p, d_R, eps, st);
+  int rc = harris_fused_launch(ctx, d_frames, u8, n_frames, nx, ny, p, d_R, eps, true, st);
   if (rc != B2F_OK) return rc;
   dim3 grid(ceil_div(nx, TN_TW), ceil_div(ny, TN_TH), n_frames);
   if (radius == 5) nms_tolerant_kernel<5><<<grid, TN_NT, 0, st>>>(d_R, eps, cand, cert, nx, ny, wpr, p->threshold);

@@ -433,7 +433,7 @@ int b2f_harris_response_eps_dev(b2f_ctx *ctx, const void *d_frames, int is_u8, i
   cudaStream_t st;
   { int hrc = stream_handoff(ctx, stream, &st); if (hrc != B2F_OK) return hrc; }
   B2F_CUDA(cudaMemsetAsync(d_eps, 0, sizeof(float) * (size_t)n_frames * ((nx + 7) / 8) * ((ny + 7) / 8), st));
-  return harris_fused_launch(ctx, d_frames, is_u8 != 0, n_frames, nx, ny, p, d_R, reinterpret_cast<unsigned *>(d_eps), st);
+  return harris_fused_launch(ctx, d_frames, is_u8 != 0, n_frames, nx, ny, p, d_R, reinterpret_cast<unsigned *>(d_eps), false, st);
 }
 
 int b2f_harris_cert_stats(b2f_ctx *ctx, unsigned long long *out4) {

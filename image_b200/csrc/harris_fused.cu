@@ -102,9 +102,10 @@ int harris_taps_double(float sigma, double *B) {     // gaussian.cpp:306-329
 }
 
 // Fused response for a batch resident on the device.  d_eps (may be NULL) receives the per-8x8-block error bound
-// (it must be zero filled: blocks are combined with atomicMax).
+// (it must be zero filled: blocks are combined with atomicMax).  corners_only: the plane feeds the certified corner path
+// only, so pixels certainly below the threshold may be stored as -FLT_MAX (harris_trace_cut).
 int harris_fused_launch(b2f_ctx *ctx, const void *d_frames, bool u8, int n_frames, int nx, int ny, const b2f_harris_params *p,
-                        float *d_R, unsigned *d_eps, cudaStream_t st) {
+                        float *d_R, unsigned *d_eps, bool corners_only, cudaStream_t st) {
   HarrisConsts kc;
   memset(&kc, 0, sizeof(kc));
   double Bd[HARRIS_MAX_TAPS], Bi[HARRIS_MAX_TAPS];
@@ -114,6 +115,7 @@ int harris_fused_launch(b2f_ctx *ctx, const void *d_frames, bool u8, int n_frame
   for (int i = 0; i < si; i++) { kc.wic[i] = (float)Bi[i]; kc.wir[i] = gscale * (float)Bi[i]; }
   kc.k = p->k;
   kc.measure = p->measure;
+  kc.tr_cut = corners_only ? harris_trace_cut(p->threshold, p->k, p->measure, u8) : 0.f;
   const int ri = si - 1, grad = p->gradient == 1;
   // vector loads / stores need 4-pixel aligned rows and aligned base pointers; anything else runs every tile generic
   const bool aligned = (nx % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_frames) & 15) == 0) && ((reinterpret_cast<uintptr_t>(d_R) & 7) == 0);

@@ -6,9 +6,10 @@ namespace b2f {
 bool harris_fused_supported(int nx, int ny, float sigma_d, float sigma_i, int gaussian);
 int harris_response_device(b2f_ctx *ctx, const void *d_frames, bool u8, int n_frames, int nx, int ny,
                            const b2f_harris_params *p, int exact, float *d_R, cudaStream_t st);
-// fused kernel (harris_fused.cu); d_eps: optional zero-filled per-8x8-block error bound of R
+// fused kernel (harris_fused.cu); d_eps: optional zero-filled per-8x8-block error bound of R; corners_only: pixels whose
+// reference response is certainly below the threshold may be stored as -FLT_MAX
 int harris_fused_launch(b2f_ctx *ctx, const void *d_frames, bool u8, int n_frames, int nx, int ny, const b2f_harris_params *p,
-                        float *d_R, unsigned *d_eps, cudaStream_t st);
+                        float *d_R, unsigned *d_eps, bool corners_only, cudaStream_t st);
 int harris_taps_double(float sigma, double *B);
 // certified fast path (harris.cu): reference-identical corner lists from the fused kernel + exact patches
 bool harris_certified_supported(int nx, int ny, const b2f_harris_params *p);

@@ -35,6 +35,8 @@ struct HarrisConsts {
   float wic[HARRIS_MAX_TAPS];   // sigma_i taps of the COLUMN pass (unscaled)
   float k;
   int measure;   // 0 Harris, 1 Shi-Tomasi, 2 harmonic mean
+  float tr_cut;  // > 0 (certified corner path, u8 frames, Harris measure, k >= 0): pixels whose trace is below it are stored
+                 // as -FLT_MAX — their reference response is certainly below the threshold (harris_trace_cut)
 };
 
 // Corner measure from the smoothed structure tensor, every float operation rounded separately
@@ -78,6 +80,21 @@ __device__ __forceinline__ float harris_eps(float T, float M, float k) {
   const float kk = fabsf(k);
   const float e = fmaf(2.f + 4.f * kk, fmaf(T, eT, eT * eT), 2.f * (1.f + 3.f * kk) * u * T * T);
   return fmaf(e, 1.25f, 1e-30f);
+}
+
+// Certificate "the reference response of this pixel is below Th" from the fp32 trace t = A + C alone (Harris measure,
+// k >= 0, u8 frames).  The reference computes R = fl(fl(fl(A C) - fl(B B)) - fl(fl(k tr) tr)) from non-negative A, C:
+// both subtrahends are >= 0 and rounding is monotone, so R <= fl(A C) <= ((A + C) / 2)^2 (1 + u).  Its trace differs from
+// the fused one by at most 2 e_T, and e_T <= 2 e_I sqrt(T) + e_I^2 + 64 u T is largest at the largest trace u8 frames can
+// produce (|gradient| <= 127.5: T <= 32512, e_T <= 0.2172).  Hence t < 2 sqrt(Th) - 2 e_T  =>  R_reference < Th; the cut
+// keeps the bound's factor 1.25 on e_T and a relative 1e-6 on the root.  Such a pixel cannot be a corner, and as a
+// neighbour it is below every kept corner (whose response is >= Th), so the non-maximum test may see -FLT_MAX in its
+// place: beside strong edges — where the per-block eps is wide and the response small — this removes the band of
+// undecided candidates the block bound would otherwise send to the exact patches.
+static inline float harris_trace_cut(float Th, float k, int measure, bool u8) {
+  if (!u8 || measure != 0 || !(k >= 0.f) || !(Th > 0.f)) return 0.f;
+  const float cut = 2.f * sqrtf(Th) * (1.f - 1e-6f) - 2.f * 0.2172f * 1.25f;
+  return cut > 0.f ? cut : 0.f;
 }
 
 template <int RD_, int RI_, int TH_, int NT_, int DW_, int CTAS_> struct Fused3Cfg {
@@ -682,6 +699,10 @@ harris_fused3_kernel(const void *__restrict__ frames, float *__restrict__ Rout, 
           if (kc.measure == 0) {                               // Harris: (A*C - B*B) - (k*tr)*tr, each op rounded (harris.cpp:100-103)
             const float2 det = sub2(__fmul2_rn(aa[j], ac[j]), __fmul2_rn(ab[j], ab[j]));
             rr[j] = sub2(det, __fmul2_rn(__fmul2_rn(f2s(kc.k), tr), tr));
+            if (kc.tr_cut > 0.f) {                             // certainly below the threshold (harris_trace_cut)
+              rr[j].x = tr.x < kc.tr_cut ? -3.402823466e+38f : rr[j].x;
+              rr[j].y = tr.y < kc.tr_cut ? -3.402823466e+38f : rr[j].y;
+            }
           } else {
             rr[j] = f2(corner_measure(aa[j].x, ab[j].x, ac[j].x, kc.k, kc.measure), corner_measure(aa[j].y, ab[j].y, ac[j].y, kc.k, kc.measure));
           }

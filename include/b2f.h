@@ -91,7 +91,9 @@ int b2f_harris_response_dev(b2f_ctx *ctx, const void *d_frames, int is_u8, int n
 /* Frames resident in HBM -> reference-identical corner lists, all on the device and asynchronous on `stream`:
  * d_xy[f*cap + i] = y*nx + x (raster order, harris.cpp:250-252), d_strength the reference's R there,
  * d_counts[f] the number of corners (may exceed cap: only cap are stored; -1 = the internal candidate records
- * overflowed, rerun with a larger cap).  d_R (optional, n_frames*nx*ny floats) receives the fp32 response planes.
+ * overflowed, rerun with a larger cap).  d_R (optional, n_frames*nx*ny floats) receives the fp32 response planes of the
+ * certified path, in which pixels whose reference response is certainly below the threshold may hold -FLT_MAX
+ * (b2f_harris_response_dev / _eps_dev return the plain planes).
  * strategy / precision / Nscales of `p` are not applied here (b2f_harris_host does them per frame). */
 int b2f_harris_corners_dev(b2f_ctx *ctx, const void *d_frames, int is_u8, int n_frames, int nx, int ny,
                            const b2f_harris_params *p, int cap, int *d_xy, float *d_strength, int *d_counts,

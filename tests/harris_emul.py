@@ -86,3 +86,11 @@ def eps(T, M, k=0.06):
     kk = F(abs(k))
     e = ((F(2.0) + F(4.0) * kk) * (T * eT + eT * eT) + F(2.0) * (F(1.0) + F(3.0) * kk) * U * T * T).astype(F)
     return (e * F(1.25) + F(1e-30)).astype(F)
+
+
+def trace_cut(Th):
+    """harris_trace_cut of harris_kernels3.cuh (u8 frames, Harris measure, k >= 0), same float operations."""
+    if not Th > 0:
+        return F(0)
+    cut = F(2.0) * np.sqrt(F(Th)).astype(F) * (F(1.0) - F(1e-6)) - F(2.0) * F(0.2172) * F(1.25)
+    return cut if cut > 0 else F(0)

@@ -63,3 +63,39 @@ def test_bound_fails_when_shrunk(oracle):
     eps = np.kron(E.eps(T, np.float32(255.0)), np.ones((8, 8), np.float32)) / 1000.0
     diff = np.abs(Rf[: by * 8, : bx * 8].astype(np.float64) - Ro[: by * 8, : bx * 8].astype(np.float64))
     assert (diff / eps)[16:-16, 16:-16].max() > 1.0
+
+
+@pytest.mark.parametrize("Th", [1.0, 130.0, 5000.0])
+@pytest.mark.parametrize("name", list(_frames().keys()))
+def test_trace_cut_only_removes_pixels_below_the_threshold(oracle, name, Th):
+    """harris_trace_cut: a pixel whose fused (fp32) trace is below the cut has a reference response below the threshold,
+    so the certified path may drop it (it is stored as -FLT_MAX).  Checked against the oracle's R on the adversarial
+    frames; frames with gentle content make the cut bite (most of their pixels fall under it)."""
+    img = _frames()[name]
+    c = 16
+    for grad in (0, 1):
+        _, tr = E.fused_response(img, grad=grad)
+        Ro, _ = oracle.harris_response(img, grad=grad, measure=0)
+        cut = E.trace_cut(Th)
+        assert cut > 0
+        below = (tr < cut)[c:-c, c:-c]
+        assert np.all(Ro[c:-c, c:-c][below] < np.float32(Th)), (name, grad, Th)
+        # the margin of the certificate: the largest reference response among the removed pixels stays well below Th
+        if below.any():
+            assert float(Ro[c:-c, c:-c][below].max()) <= Th * 1.0
+
+
+def test_trace_cut_bites_on_flat_noise_and_is_tight_enough(oracle):
+    """On small-noise content nearly every pixel is certified below Th = 130 by its trace alone; and the cut is not
+    vacuous the other way: no pixel with a reference response >= Th has a trace below 2*sqrt(Th) at all."""
+    rng = np.random.default_rng(5)
+    img = (100 + rng.integers(0, 8, (136, 200))).astype(np.uint8)
+    _, tr = E.fused_response(img)
+    Ro, _ = oracle.harris_response(img, grad=0, measure=0)
+    cut = E.trace_cut(130.0)
+    assert (tr < cut)[16:-16, 16:-16].mean() > 0.99
+    img2 = _frames()["noise_full_range"]
+    _, tr2 = E.fused_response(img2)
+    Ro2, _ = oracle.harris_response(img2, grad=0, measure=0)
+    hot = Ro2[16:-16, 16:-16] >= 130.0
+    assert hot.any() and tr2[16:-16, 16:-16][hot].min() >= 2 * np.sqrt(130.0)
