@@ -45,8 +45,8 @@ def contour_edge_points_batch(frames, cap=None, sigma=0.0, ctx=None):
     f = np.ascontiguousarray(frames, dtype=np.uint8)
     n, Y, X = f.shape
     cap = int(cap or max(1024, X * Y // 2))
-    idx = np.zeros((n, cap), np.int32)
-    o = [np.zeros((n, cap), np.float64) for _ in range(4)]
+    idx = np.empty((n, cap), np.int32)               # only [:counts[i]] of a row is written
+    o = [np.empty((n, cap), np.float64) for _ in range(4)]
     cnt = np.zeros(n, np.int32)
     _lib.check(lib.b2f_contour_edge_points_batch_u8(ctx or _lib.context(), _lib.ptr(f), n, X, Y, float(sigma), cap, _lib.ptr(idx),
                                                     _lib.ptr(o[0]), _lib.ptr(o[1]), _lib.ptr(o[2]), _lib.ptr(o[3]), _lib.ptr(cnt)))

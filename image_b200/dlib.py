@@ -59,7 +59,7 @@ def fhog_batch(frames, cell=8, frp=1, fcp=1, out=None, ctx=None):
     f = np.ascontiguousarray(frames, dtype=np.uint8)
     n, rows, cols, _ = f.shape
     nr, nc = fhog_size(rows, cols, cell, frp, fcp)
-    hog = out if out is not None else np.zeros((n, nr, nc, 31), np.float32)
+    hog = out if out is not None else np.empty((n, nr, nc, 31), np.float32)
     if nr * nc:
         _lib.check(lib.b2f_fhog_batch(ctx or _lib.context(), _lib.ptr(f), n, rows, cols, int(cell), int(frp), int(fcp), _lib.ptr(hog)))
     return hog

@@ -23,13 +23,14 @@ def features_batch(rgb, harris=None, canny=None, fhog=None, corner_cap=65536, ou
     hp = cx = cy = cs = cc = None
     if harris is not None:
         hp = _params(harris)
-        cx = np.zeros((n, corner_cap), np.float32); cy = np.zeros((n, corner_cap), np.float32); cs = np.zeros((n, corner_cap), np.float32)
+        # padded rows: only the first counts[i] entries of row i are written (np.empty: zero-filling 3 x 4 MB per call cost 0.5 ms)
+        cx = np.empty((n, corner_cap), np.float32); cy = np.empty((n, corner_cap), np.float32); cs = np.empty((n, corner_cap), np.float32)
         cc = np.zeros(n, np.int32)
     cp = edges = nz = None
     if canny is not None:
         cp = _lib.CannyParams(float(canny.get("s", 2.0)), float(canny.get("low_thr", 3.0)), float(canny.get("high_thr", 10.0)),
                               int(bool(canny.get("accGrad", False))))
-        edges = out_edges if out_edges is not None else np.zeros((n, rows, cols), np.uint8)
+        edges = out_edges if out_edges is not None else np.empty((n, rows, cols), np.uint8)
         nz = np.zeros(n, np.int32)
     cell = frp = fcp = 0
     hog = None
@@ -37,7 +38,7 @@ def features_batch(rgb, harris=None, canny=None, fhog=None, corner_cap=65536, ou
         cell, frp, fcp = int(fhog.get("cell", 8)), int(fhog.get("frp", 1)), int(fhog.get("fcp", 1))
         nr, nc = C.c_int(0), C.c_int(0)
         _lib.check(lib.b2f_fhog_size(rows, cols, cell, frp, fcp, C.byref(nr), C.byref(nc)))
-        hog = out_hog if out_hog is not None else np.zeros((n, nr.value, nc.value, 31), np.float32)
+        hog = out_hog if out_hog is not None else np.empty((n, nr.value, nc.value, 31), np.float32)
     if grey_in:
         _lib.check(lib.b2f_features_batch_grey(ctx or _lib.context(), _lib.ptr(f), n, cols, rows,
                                                C.byref(hp) if hp is not None else None, int(corner_cap), _lib.ptr(cx), _lib.ptr(cy), _lib.ptr(cs), _lib.ptr(cc),

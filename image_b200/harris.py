@@ -99,7 +99,7 @@ def harris_batch_u8(frames, cap=65536, raw=False, ctx=None, **kw):
     d.update(kw)
     p = _lib.HarrisParams(*[d[k] for k in ("k", "sigma_d", "sigma_i", "threshold", "gaussian", "gradient", "strategy",
                                            "Nselect", "measure", "Nscales", "precision", "cells", "verbose", "exact")])
-    x = np.zeros((n, cap), np.float32); y = np.zeros((n, cap), np.float32); s = np.zeros((n, cap), np.float32)
+    x = np.empty((n, cap), np.float32); y = np.empty((n, cap), np.float32); s = np.empty((n, cap), np.float32)   # only [:counts[i]] of a row is written
     cnt = np.zeros(n, np.int32)
     _lib.check(lib.b2f_harris_batch_u8(ctx or _lib.context(), _lib.ptr(f), n, nx, ny, C.byref(p), int(cap),
                                        _lib.ptr(x), _lib.ptr(y), _lib.ptr(s), _lib.ptr(cnt)))

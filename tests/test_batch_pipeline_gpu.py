@@ -41,8 +41,9 @@ def test_harris_batch_chunked_equals_single_chunk(small_chunks):
     a = harris_batch_u8(f, cap=4096, raw=True, ctx=small_chunks, threshold=10.0)
     b = harris_batch_u8(f, cap=4096, raw=True, threshold=10.0)
     assert np.array_equal(a[3], b[3]) and a[3].sum() > 0
-    for q in range(3):
-        assert np.array_equal(a[q], b[q])
+    for i, m in enumerate(a[3]):          # only the first counts[i] entries of a padded row are written
+        for q in range(3):
+            assert np.array_equal(a[q][i, :m], b[q][i, :m])
 
 
 def test_fhog_batch_chunked_equals_oracle(oracle, small_chunks):
@@ -94,8 +95,10 @@ def test_three_detectors_from_three_threads(oracle):
         t.join()
     assert not errs, errs
     ref_h = harris_batch_u8(grey, cap=8192, raw=True, threshold=10.0)
-    for q in range(4):
-        assert np.array_equal(out["harris"][q], ref_h[q])
+    assert np.array_equal(out["harris"][3], ref_h[3])
+    for i, m in enumerate(ref_h[3]):
+        for q in range(3):
+            assert np.array_equal(out["harris"][q][i, :m], ref_h[q][i, :m])
     e, cnt = oracle.canny(grey[2])
     assert np.array_equal(out["canny"][0][2], e) and int(out["canny"][1][2]) == cnt
     assert np.array_equal(out["fhog"][5], oracle.fhog(rgb[5]))
