@@ -37,12 +37,14 @@ void set_error(const char *fmt, ...);
 struct Arena {
   char *base = nullptr;
   size_t cap = 0, off = 0, need = 0;
+  size_t limit = 0;       // != 0: end of the region the current carver may use (features.cu gives each detector its own)
   bool overflow = false;
-  void reset() { off = 0; need = 0; overflow = false; }
+  void reset() { off = 0; need = 0; limit = 0; overflow = false; }
+  void region(size_t begin, size_t end) { off = begin; limit = end; }
   template <typename T> T *get(size_t n) {
     size_t bytes = (n * sizeof(T) + 255) & ~size_t(255);
     need += bytes;
-    if (off + bytes > cap) { overflow = true; return nullptr; }
+    if (off + bytes > (limit ? limit : cap)) { overflow = true; return nullptr; }
     T *p = reinterpret_cast<T *>(base + off);
     off += bytes;
     return p;

@@ -103,7 +103,7 @@ static int features_batch(b2f_ctx *ctx, const uint8_t *rgb, int channels, int n_
   float *d_s = do_h ? ctx->arena.get<float>(rec) : nullptr;
   int *d_cnt = ctx->arena.get<int>(n_frames), *d_nz = ctx->arena.get<int>(n_frames);
   B2F_ARENA_CHECK(ctx);
-  const size_t mark_h = ctx->arena.off, mark_c = mark_h + scr_h, mark_f = mark_c + scr_c;
+  const size_t mark_h = ctx->arena.off, mark_c = mark_h + scr_h, mark_f = mark_c + scr_c, mark_end = mark_f + align256(f_scr);
   cudaStream_t st = ctx->stream;
   for (cudaStream_t &s : ctx->s_aux)
     if (!s) B2F_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
@@ -146,7 +146,7 @@ static int features_batch(b2f_ctx *ctx, const uint8_t *rgb, int channels, int n_
     // Three detectors side by side: FHOG (needs only the RGB frames) on its own stream, the grey derivation and Harris on
     // the context stream, Canny on a third.  Each result starts its way home as soon as its detector has finished.
     if (rc == B2F_OK && d_hog) {
-      ctx->arena.off = mark_f;
+      ctx->arena.region(mark_f, mark_end);
       if (cudaStreamWaitEvent(s_fhog, e_in, 0) != cudaSuccess) rc = B2F_ECUDA;
       if (rc == B2F_OK) rc = fhog_device_simple(ctx, d_rgb + fin * f0, nf, rows, cols, cell_size, frp, fcp, d_hog + fout * f0, s_fhog);
       if (rc == B2F_OK && (cudaEventRecord(e_hog, s_fhog) != cudaSuccess || cudaStreamWaitEvent(ctx->s_out, e_hog, 0) != cudaSuccess ||
@@ -161,7 +161,7 @@ static int features_batch(b2f_ctx *ctx, const uint8_t *rgb, int channels, int n_
       if (cudaGetLastError() != cudaSuccess) rc = B2F_ECUDA;
     }
     if (rc == B2F_OK && do_c) {
-      ctx->arena.off = mark_c;
+      ctx->arena.region(mark_c, mark_f);
       if (cudaEventRecord(e_grey, st) != cudaSuccess || cudaStreamWaitEvent(s_canny, e_grey, 0) != cudaSuccess) rc = B2F_ECUDA;
       if (rc == B2F_OK) rc = canny_device(ctx, d_grey_c, nf, nx, ny, cp->s, cp->low_thr, cp->high_thr, cp->acc_grad, d_edges + plane * f0, d_nz + f0, s_canny);
       if (rc == B2F_OK && (cudaEventRecord(e_canny, s_canny) != cudaSuccess || cudaStreamWaitEvent(ctx->s_out, e_canny, 0) != cudaSuccess ||
@@ -169,7 +169,7 @@ static int features_batch(b2f_ctx *ctx, const uint8_t *rgb, int channels, int n_
                            cudaMemcpyAsync(p_nz + f0, d_nz + f0, sizeof(int) * nf, cudaMemcpyDeviceToHost, ctx->s_out) != cudaSuccess)) rc = B2F_ECUDA;
     }
     if (rc == B2F_OK && h_runs) {
-      ctx->arena.off = mark_h;
+      ctx->arena.region(mark_h, mark_c);
       if (certified) rc = harris_corners_certified(ctx, d_grey_c, true, nf, nx, ny, hp, corner_cap, d_xy + (size_t)f0 * corner_cap, d_s + (size_t)f0 * corner_cap, nullptr, d_cnt + f0, nullptr, st);
       else {
         float *d_R = ctx->arena.get<float>(plane * nf);

@@ -9,13 +9,19 @@ import torch  # noqa: E402
 from image_b200 import synth, dlib as Dl  # noqa: E402
 from image_b200.features import features_batch  # noqa: E402
 
-B, NY, NX = 16, 2160, 3840
-rgb = synth.batch(synth.frame_rgb, 2000, B, NY, NX, distinct=8)
-np_rgb = torch.from_numpy(rgb).pin_memory().numpy()
-hnr, hnc = Dl.fhog_size(NY, NX, 8, 1, 1)
+if len(sys.argv) > 1 and sys.argv[1] == "8k":          # the stream8k workload: 4 grey 8K frames, Harris + Canny
+    B, NY, NX = 4, 4320, 7680
+    np_rgb = torch.from_numpy(synth.batch(synth.frame_shapes, 4000, B, NY, NX, distinct=4)).pin_memory().numpy()
+    pin_hog = None
+    kw = dict(harris=dict(threshold=130.0), canny=dict(s=2.0, low_thr=3.0, high_thr=10.0, accGrad=True))
+else:
+    B, NY, NX = 16, 2160, 3840
+    rgb = synth.batch(synth.frame_rgb, 2000, B, NY, NX, distinct=8)
+    np_rgb = torch.from_numpy(rgb).pin_memory().numpy()
+    hnr, hnc = Dl.fhog_size(NY, NX, 8, 1, 1)
+    pin_hog = torch.empty((B, hnr, hnc, 31), dtype=torch.float32).pin_memory().numpy()
+    kw = dict(harris=dict(threshold=130.0), canny=dict(s=2.0, low_thr=3.0, high_thr=10.0, accGrad=True), fhog=dict(cell=8))
 pin_edges = torch.empty((B, NY, NX), dtype=torch.uint8).pin_memory().numpy()
-pin_hog = torch.empty((B, hnr, hnc, 31), dtype=torch.float32).pin_memory().numpy()
-kw = dict(harris=dict(threshold=130.0), canny=dict(s=2.0, low_thr=3.0, high_thr=10.0, accGrad=True), fhog=dict(cell=8))
 for edge in ("default",):
     os.environ.pop("B2F_FEAT_TRACE", None)
     for _ in range(3):
