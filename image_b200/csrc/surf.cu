@@ -214,46 +214,60 @@ surf_pyramid_kernel(const int *__restrict__ split, double *__restrict__ pyr, con
   }
 }
 
-// ---- octave 0 (three quarters of all samples): the six maps of a 64 x 128 pixel tile from ONE shared-memory copy of the table.
+// ---- octave 0 (three quarters of all samples): the six maps of a tile from ONE shared-memory copy of the table.
 // The generic kernel above is bound by L2 -> L1 traffic (ncu: L1 hit rate 41 %, ~75 B per sample from L2): a sample's 32
-// corners lie on 10 rows that no neighbouring sample row shares.  Here a CTA stages the tile plus a 20-pixel rim
-// (3 * 13 / 2 + 1, the largest filter of the octave) once, 68 KB in the same even / odd column split, and evaluates all six
-// filter sizes from it: ~6 B per sample from L2, and every corner is a conflict-free LDS at a compile-time offset.
-constexpr int P0_SR = 32, P0_SC = 64;              // samples per tile: rows x columns (step 2 -> 64 x 128 pixels)
-constexpr int P0_RIM = 20;
-constexpr int P0_ROWS = 2 * (P0_SR - 1) + 1 + P0_RIM + (P0_RIM - 1);   // rows r0-20 .. r0+62+19 -> 102
-constexpr int P0_HALFW = 84;                       // 83 even + 83 odd columns (c0-20 .. c0+126+19), padded
-constexpr int P0_PITCH = 2 * P0_HALFW;
-constexpr int P0_SMEM = P0_ROWS * P0_PITCH * 4;    // 68 544 B -> 3 CTAs / SM
-static_assert(P0_ROWS == 102, "tile rows");
+// corners lie on 10 rows that no neighbouring sample row shares.  Here a CTA stages a 64 x 128 pixel tile plus a rim of 1.5
+// times the octave's largest filter once and evaluates all six filter sizes from it: ~6 B (octave 0) / ~37 B (octave 1) per
+// sample from L2.  In shared memory the columns of a row are split by their residue modulo the sampling step (2 or 4), so the
+// 32 lanes of a warp — 32 consecutive samples — read 32 consecutive words: every corner is a conflict-free LDS at a
+// compile-time offset (the filter size is a template parameter).  The template also describes octave 1 (step 4); that
+// instance lost to the generic kernel (see the launch site) and is not launched.
+template <int O> struct PyrTile {
+  static constexpr int LOG = O + 1, STEP = 1 << LOG;            // sampling step 2 / 4 (get_step_size)
+  static constexpr int lobe(int i) { return STEP * (i + 1) + 1; }                     // 3..13 / 5..25
+  static constexpr int LMAX = lobe(S_INT - 1);
+  static constexpr int RIM_LO = ((3 * LMAX / 2 + 1) + STEP - 1) / STEP * STEP;         // rim above / left, a multiple of STEP: 20 / 40
+  static constexpr int RIM_HI = 3 * LMAX / 2;                                          // rim below / right: 19 / 37
+  static constexpr int SR = 64 / STEP, SC = 128 / STEP;                                // samples per tile: 32 x 64 / 16 x 32
+  static constexpr int ROWS = STEP * (SR - 1) + 1 + RIM_LO + RIM_HI;                   // 102 / 138
+  static constexpr int COLS = STEP * (SC - 1) + 1 + RIM_LO + RIM_HI;                   // 166 / 202
+  static constexpr int PW = (COLS + STEP - 1) / STEP + 1;                              // words per residue plane, padded: 84 / 52
+  static constexpr int PITCH = STEP * PW;
+  static constexpr int SMEM = ROWS * PITCH * 4;                                        // 68 544 B (3 CTAs / SM) / 114 816 B (2 CTAs / SM)
+  static constexpr int NG = 256 / SC, RPT = SR / NG;                                   // row groups of the CTA, sample rows per thread
+  // corner (kc, kr) relative to a sample (whose column is a multiple of STEP); & and >> on negative kc give the positive
+  // residue and the floor
+  static constexpr int off(int kc, int kr) { return kr * PITCH + (kc & (STEP - 1)) * PW + (kc >> LOG); }
+};
+static_assert(PyrTile<0>::ROWS == 102 && PyrTile<0>::PW == 84 && PyrTile<0>::SMEM == 68544, "octave 0 tile");
+static_assert(PyrTile<1>::ROWS == 138 && PyrTile<1>::SMEM <= 115 * 1024, "octave 1 tile");
 
-__host__ __device__ constexpr int p0_off(int kc, int kr) {   // corner (kc, kr) relative to a sample; >> on negative kc floors (arithmetic shift)
-  return kr * P0_PITCH + (kc & 1) * P0_HALFW + (kc >> 1);
-}
-template <int DX, int DY, int W, int H>
-__device__ __forceinline__ int p0_box(const int *__restrict__ q) {       // centered_rect + get_sum_of_area: br - bl - tr + tl
+template <int O, int DX, int DY, int W, int H>
+__device__ __forceinline__ int pt_box(const int *__restrict__ q) {       // centered_rect + get_sum_of_area: br - bl - tr + tl
+  using T = PyrTile<O>;
   constexpr int l = DX - W / 2, t = DY - H / 2, r = l + W - 1, b = t + H - 1;
-  return q[p0_off(r, b)] - q[p0_off(l - 1, b)] - q[p0_off(r, t - 1)] + q[p0_off(l - 1, t - 1)];
+  static_assert(l - 1 >= -T::RIM_LO && t - 1 >= -T::RIM_LO && r <= T::RIM_HI && b <= T::RIM_HI, "rim too small for this filter");
+  return q[T::off(r, b)] - q[T::off(l - 1, b)] - q[T::off(r, t - 1)] + q[T::off(l - 1, t - 1)];
 }
-template <int L>
-__device__ __forceinline__ void p0_interval(const int *__restrict__ tile, double *__restrict__ out, const SurfMap &m, int rows, int cols,
+template <int O, int I>
+__device__ __forceinline__ void pt_interval(const int *__restrict__ tile, double *__restrict__ out, const SurfMap &m, int rows, int cols,
                                             int r0s, int c0s) {        // r0s, c0s: the tile's first sample in map units
-  static_assert(3 * L / 2 + 1 <= P0_RIM, "rim too small for this filter");
-  constexpr int OFF = L / 2 + 1;
+  using T = PyrTile<O>;
+  constexpr int L = T::lobe(I), OFF = L / 2 + 1;
   const int rmax = (rows - m.border * m.step + m.step - 1) / m.step, cmax = (cols - m.border * m.step + m.step - 1) / m.step;
-  const int q = threadIdx.x & (P0_SC - 1), jg = threadIdx.x / P0_SC;
+  const int q = threadIdx.x & (T::SC - 1), jg = threadIdx.x / T::SC;
   const int ci = c0s + q;
   if (ci < m.border || ci >= cmax) return;
   const double area_inv = m.area_inv;
 #pragma unroll 2
-  for (int jj = 0; jj < P0_SR / 4; jj++) {
-    const int j = jg * (P0_SR / 4) + jj, ri = r0s + j;
+  for (int jj = 0; jj < T::RPT; jj++) {
+    const int j = jg * T::RPT + jj, ri = r0s + j;
     if (ri < m.border || ri >= rmax) continue;
-    const int *p = tile + (P0_RIM + 2 * j) * P0_PITCH + P0_RIM / 2 + q;
-    double Dxx = __dsub_rn((double)p0_box<0, 0, 3 * L, 2 * L - 1>(p), __dmul_rn((double)p0_box<0, 0, L, 2 * L - 1>(p), 3.0));
-    double Dyy = __dsub_rn((double)p0_box<0, 0, 2 * L - 1, 3 * L>(p), __dmul_rn((double)p0_box<0, 0, 2 * L - 1, L>(p), 3.0));
+    const int *p = tile + (T::RIM_LO + T::STEP * j) * T::PITCH + T::RIM_LO / T::STEP + q;
+    double Dxx = __dsub_rn((double)pt_box<O, 0, 0, 3 * L, 2 * L - 1>(p), __dmul_rn((double)pt_box<O, 0, 0, L, 2 * L - 1>(p), 3.0));
+    double Dyy = __dsub_rn((double)pt_box<O, 0, 0, 2 * L - 1, 3 * L>(p), __dmul_rn((double)pt_box<O, 0, 0, 2 * L - 1, L>(p), 3.0));
     // int32 arithmetic like the reference (value_type sums): bl + tr - tl - br
-    double Dxy = (double)(p0_box<-OFF, OFF, L, L>(p) + p0_box<OFF, -OFF, L, L>(p) - p0_box<-OFF, -OFF, L, L>(p) - p0_box<OFF, OFF, L, L>(p));
+    double Dxy = (double)(pt_box<O, -OFF, OFF, L, L>(p) + pt_box<O, OFF, -OFF, L, L>(p) - pt_box<O, -OFF, -OFF, L, L>(p) - pt_box<O, OFF, OFF, L, L>(p));
     Dxx = __dmul_rn(Dxx, area_inv); Dyy = __dmul_rn(Dyy, area_inv); Dxy = __dmul_rn(Dxy, area_inv);
     const double sign = (__dadd_rn(Dxx, Dyy) < 0) ? -1.0 : 1.0;
     double det = __dsub_rn(__dmul_rn(Dxx, Dyy), __dmul_rn(__dmul_rn(0.81, Dxy), Dxy));
@@ -262,31 +276,34 @@ __device__ __forceinline__ void p0_interval(const int *__restrict__ tile, double
   }
 }
 
-__global__ void __launch_bounds__(256, 3)
-surf_pyramid0_kernel(const int *__restrict__ split, double *__restrict__ pyr, const __grid_constant__ SurfGeom g, int tiles_x) {
-  extern __shared__ __align__(16) int p0_tile[];
+template <int O>
+__global__ void __launch_bounds__(256, O == 0 ? 3 : 2)
+surf_pyramid_tile_kernel(const int *__restrict__ split, double *__restrict__ pyr, const __grid_constant__ SurfGeom g, int tiles_x) {
+  using T = PyrTile<O>;
+  extern __shared__ __align__(16) int pt_tile[];
   const int half = (g.cols + 1) >> 1, pitch = 2 * half;
   const int *S = split + (size_t)blockIdx.z * g.rows * (size_t)pitch;
   double *out = pyr + (size_t)blockIdx.z * g.pyr_per_frame;
   const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
-  const int r0s = ty * P0_SR, c0s = tx * P0_SC;                 // first sample (map units); pixels: 2 * r0s, 2 * c0s
-  const int prow0 = 2 * r0s - P0_RIM, pcol0 = 2 * c0s - P0_RIM;  // pixel of tile word (0, 0); pcol0 is even
-  // ---- stage: tile row = 83 even-column words, then (at P0_HALFW) 83 odd-column words, both runs contiguous in the split table
-  for (int it = threadIdx.x; it < P0_ROWS * P0_PITCH; it += 256) {
-    const int tr = it / P0_PITCH, w = it - tr * P0_PITCH;
-    const int par = w >= P0_HALFW, k = w - par * P0_HALFW;
-    const int R = prow0 + tr, Cc = pcol0 + 2 * k + par;
+  const int r0s = ty * T::SR, c0s = tx * T::SC;                                   // first sample (map units)
+  const int prow0 = T::STEP * r0s - T::RIM_LO, pcol0 = T::STEP * c0s - T::RIM_LO; // pixel of tile word (0, 0); pcol0 is a multiple of STEP
+  // ---- stage: a tile row is STEP runs of PW words, run p holding the columns pcol0 + p, pcol0 + p + STEP, ...
+  for (int it = threadIdx.x; it < T::ROWS * T::PITCH; it += 256) {
+    const int tr = it / T::PITCH, w = it - tr * T::PITCH;
+    const int pl = w / T::PW, k = w - pl * T::PW;
+    const int R = prow0 + tr, Cc = pcol0 + T::STEP * k + pl;
     int v = 0;
-    if (R >= 0 && R < g.rows && Cc >= 0 && Cc < g.cols && k < P0_HALFW - 1) v = __ldg(S + (size_t)R * pitch + par * half + (Cc >> 1));
-    p0_tile[it] = v;
+    if (R >= 0 && R < g.rows && Cc >= 0 && Cc < g.cols && T::STEP * k + pl < T::COLS) v = __ldg(S + (size_t)R * pitch + (Cc & 1) * half + (Cc >> 1));
+    pt_tile[it] = v;
   }
   __syncthreads();
-  p0_interval<3>(p0_tile, out, g.m[0], g.rows, g.cols, r0s, c0s);
-  p0_interval<5>(p0_tile, out, g.m[1], g.rows, g.cols, r0s, c0s);
-  p0_interval<7>(p0_tile, out, g.m[2], g.rows, g.cols, r0s, c0s);
-  p0_interval<9>(p0_tile, out, g.m[3], g.rows, g.cols, r0s, c0s);
-  p0_interval<11>(p0_tile, out, g.m[4], g.rows, g.cols, r0s, c0s);
-  p0_interval<13>(p0_tile, out, g.m[5], g.rows, g.cols, r0s, c0s);
+  const SurfMap *m = g.m + O * S_INT;
+  pt_interval<O, 0>(pt_tile, out, m[0], g.rows, g.cols, r0s, c0s);
+  pt_interval<O, 1>(pt_tile, out, m[1], g.rows, g.cols, r0s, c0s);
+  pt_interval<O, 2>(pt_tile, out, m[2], g.rows, g.cols, r0s, c0s);
+  pt_interval<O, 3>(pt_tile, out, m[3], g.rows, g.cols, r0s, c0s);
+  pt_interval<O, 4>(pt_tile, out, m[4], g.rows, g.cols, r0s, c0s);
+  pt_interval<O, 5>(pt_tile, out, m[5], g.rows, g.cols, r0s, c0s);
 }
 
 // ------------------------------------------------------------------------------------------ interest points
@@ -586,10 +603,13 @@ static int surf_pipeline(b2f_ctx *ctx, const unsigned char *d_rgb, const cudaEve
     B2F_CUDA(cudaMemsetAsync(s.counts, 0, sizeof(int) * nf, st));
     const long long biggest = (long long)g.m[0].nr * g.m[0].nc;
     const int bx = (int)std::min<long long>((biggest + 255) / 256, 4096);
-    {   // octave 0 from shared-memory tiles, octaves 1-3 (a quarter of the samples, filters up to 97 pixels) straight from the table
-      const int tiles_x = ceil_div(g.m[0].nc, P0_SC), tiles_y = ceil_div(g.m[0].nr, P0_SR);
-      B2F_CUDA(cudaFuncSetAttribute(surf_pyramid0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P0_SMEM));
-      if (tiles_x > 0 && tiles_y > 0) surf_pyramid0_kernel<<<dim3(tiles_x * tiles_y, 1, nf), 256, P0_SMEM, st>>>(s.split, s.pyr, g, tiles_x);
+    {   // octave 0 from shared-memory tiles; octaves 1-3 straight from the table (the tiled kernel is instantiated for octave 0
+        // only: for octave 1 — 114 KB per tile for 3072 samples, 2 CTAs / SM — it measured 328 us per 4 frames against
+        // ~220 us for the generic kernel's share)
+      using T = PyrTile<0>;
+      const int tiles_x = ceil_div(g.m[0].nc, T::SC), tiles_y = ceil_div(g.m[0].nr, T::SR);
+      B2F_CUDA(cudaFuncSetAttribute(surf_pyramid_tile_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM));
+      if (tiles_x > 0 && tiles_y > 0) surf_pyramid_tile_kernel<0><<<dim3(tiles_x * tiles_y, 1, nf), 256, T::SMEM, st>>>(s.split, s.pyr, g, tiles_x);
       B2F_LAUNCH_CHECK(ctx);
       surf_pyramid_kernel<<<dim3(std::max(1, bx / 4), S_MAPS - S_INT, nf), 256, 0, st>>>(s.split, s.pyr, g, S_INT);
       B2F_LAUNCH_CHECK(ctx);
