@@ -423,6 +423,8 @@ static constexpr DomOffsets make_dom_offsets() {
   return t;
 }
 __constant__ DomOffsets c_dom = make_dom_offsets();
+// 1.0 / (4 + n): the descriptor's sample weights (IEEE division, the same value __ddiv_rn gives)
+__constant__ double c_inv4[12] = {1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8, 1.0 / 9, 1.0 / 10, 1.0 / 11, 1.0 / 12, 1.0 / 13, 1.0 / 14, 1.0 / 15};
 
 // Their Gaussian weights (sigma 2.5) depend on the offset only: one table per context, built by the device's own exp()
 // with the operation order the descriptor kernel used to run per key point.
@@ -471,12 +473,23 @@ surf_describe_kernel(const int *__restrict__ sat, const SurfKey *__restrict__ ke
     wang[tid] = atan2(vy, vx);
   }
   __syncthreads();
-  if (tid < 64 && (tid & 31) == 0) {          // two threads (one per warp): the rotation and its inverse
-    double max_length = 0, best = 0;
-    for (int k = 0; k < 45; k++) if (wlen[k] > max_length) { max_length = wlen[k]; best = wang[k]; }
-    double sn, cs;
-    if (tid == 0) { s_angle = best; sincos(best, &sn, &cs); s_rot[0] = sn; s_rot[1] = cs; }
-    else { sincos(-best, &sn, &cs); s_rot[2] = sn; s_rot[3] = cs; }
+  if (tid < 64) {     // warps 0 and 1 both find the first window with the strictly largest length (surf.h:137-146; none: angle 0) ...
+    const int lane = tid & 31;
+    double v = wlen[lane];
+    int k = lane;
+    if (lane + 32 < 45 && wlen[lane + 32] > v) { v = wlen[lane + 32]; k = lane + 32; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+      const int ok = __shfl_xor_sync(0xffffffffu, k, o);
+      if (ov > v || (ov == v && ok < k)) { v = ov; k = ok; }
+    }
+    if (lane == 0) {  // ... and one thread of each computes the rotation / its inverse
+      const double best = v > 0 ? wang[k] : 0.0;
+      double sn, cs;
+      if (tid == 0) { s_angle = best; sincos(best, &sn, &cs); s_rot[0] = sn; s_rot[1] = cs; }
+      else { sincos(-best, &sn, &cs); s_rot[2] = sn; s_rot[3] = cs; }
+    }
   }
   __syncthreads();
   const double angle = s_angle;
@@ -493,7 +506,7 @@ surf_describe_kernel(const int *__restrict__ sat, const SurfKey *__restrict__ ke
         const double rx = __dsub_rn(__dmul_rn(cs, qx), __dmul_rn(sn, qy)), ry = __dadd_rn(__dmul_rn(sn, qx), __dmul_rn(cs, qy));
         const int px = (int)round_half_up(__dadd_rn(rx, kp.x)), py = (int)round_half_up(__dadd_rn(ry, kp.y));
         const int ay = abs(r + 2 - y), ax = abs(c + 2 - x);
-        const double weight = __ddiv_rn(1.0, (double)(4 + ay + ax));
+        const double weight = c_inv4[ay + ax];                                         // 1.0 / (4 + ay + ax), surf.h:205
         const double tx = __dmul_rn(weight, (double)sat_haar_x(S, cols, px, py, (int)(2 * sc)));
         const double ty = __dmul_rn(weight, (double)sat_haar_y(S, cols, px, py, (int)(2 * sc)));
         vx = __dsub_rn(__dmul_rn(ics, tx), __dmul_rn(isn, ty));
