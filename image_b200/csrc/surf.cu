@@ -542,10 +542,6 @@ surf_describe_kernel(const int *__restrict__ sat, const SurfKey *__restrict__ ke
 }
 
 // ------------------------------------------------------------------------------------------ host
-struct ip_mirror {            // interest_point ordering: operator< on score (hessian_pyramid.h:32)
-  double x, y, scale, score, lap;
-  bool operator<(const ip_mirror &p) const { return score < p.score; }
-};
 
 static bool rect_inside(int rows, int cols, double cx, double cy, unsigned long size) {
   // get_rect(int_img).contains(centered_rect(center, size, size)) with vector<double> -> point rounding
@@ -657,18 +653,30 @@ static int surf_pipeline(b2f_ctx *ctx, const unsigned char *d_rgb, const cudaEve
       if (h_counts[f0 + f]) B2F_CUDA(cudaMemcpyAsync(hc_all + c_off[f], s.cand + (size_t)f * cand_cap, sizeof(SurfCand) * h_counts[f0 + f], cudaMemcpyDeviceToHost, ctx->s_out));
     B2F_CUDA(cudaStreamSynchronize(ctx->s_out));
     fkeys.assign(nf, {});
+    // The two sorts move 16-byte (key | score, index) records instead of the 48-byte candidates: std::sort's sequence of
+    // comparisons and exchanges depends on the comparison results and the element count only, so the permutation — also
+    // among equal scores, where the reference's unstable sort decides — is the one surf.h:268 produces on interest_points.
+    struct KeyIdx { long long key; int idx; };
+    struct ScoreIdx {
+      double score; int idx;
+      bool operator<(const ScoreIdx &p) const { return score < p.score; }             // interest_point::operator<, hessian_pyramid.h:32
+    };
     auto tail = [&](int f) {
       const int n = h_counts[f0 + f];
-      SurfCand *hc = hc_all + c_off[f];
-      std::sort(hc, hc + n, [](const SurfCand &x, const SurfCand &y) { return x.key < y.key; });   // emission order
-      std::vector<ip_mirror> pts(n);
-      for (int k = 0; k < n; k++) pts[k] = ip_mirror{hc[k].x, hc[k].y, hc[k].scale, hc[k].score, hc[k].lap};
+      const SurfCand *hc = hc_all + c_off[f];
+      std::vector<KeyIdx> order(n);
+      for (int k = 0; k < n; k++) order[k] = KeyIdx{hc[k].key, k};
+      std::sort(order.begin(), order.end(), [](const KeyIdx &x, const KeyIdx &y) { return x.key < y.key; });   // emission order (keys are unique)
+      std::vector<ScoreIdx> pts(n);
+      for (int k = 0; k < n; k++) pts[k] = ScoreIdx{hc[order[k].idx].score, order[k].idx};
       std::sort(pts.rbegin(), pts.rend());                                             // surf.h:268
       const size_t lim = std::min((size_t)max_points, pts.size());
+      fkeys[f].reserve(lim);
       for (size_t k = 0; k < lim; k++) {
-        const unsigned long bsz = (unsigned long)(32 * pts[k].scale);                  // surf.h:275-277
-        if (!rect_inside(rows, cols, pts[k].x, pts[k].y, bsz)) continue;
-        fkeys[f].push_back(SurfKey{pts[k].x, pts[k].y, pts[k].scale, pts[k].score, pts[k].lap, f, 0});
+        const SurfCand &c = hc[pts[k].idx];
+        const unsigned long bsz = (unsigned long)(32 * c.scale);                       // surf.h:275-277
+        if (!rect_inside(rows, cols, c.x, c.y, bsz)) continue;
+        fkeys[f].push_back(SurfKey{c.x, c.y, c.scale, c.score, c.lap, f, 0});
       }
     };
     const int nt = std::max(1, std::min({nf, (int)std::thread::hardware_concurrency(), 16}));
