@@ -577,10 +577,10 @@ struct SurfSlot {   // device scratch of one chunk
 // *need_cap: raised when a frame had more candidates than cand_cap (the call then returns B2F_ECAP and the caller reruns).
 // Results: counts_out[f] key points of frame f, the first min(counts_out[f], cap) of them at points + f*cap when `points` is
 // given; with `grow` (single-frame host form) *grow receives a malloc'ed array of exactly counts_out[0] records instead.
-static int surf_pipeline(b2f_ctx *ctx, const unsigned char *d_rgb, const cudaEvent_t *e_up, const cudaEvent_t *e_a, int n_frames, int C,
+static int surf_pipeline(b2f_ctx *ctx, const unsigned char *d_rgb, const cudaEvent_t *e_up, const cudaEvent_t *e_a, int n_frames, const std::vector<int> &cstart,
                          const SurfGeom &g, long max_points, double thr, int cand_cap, size_t slot_keys, SurfSlot slot[2],
                          b2f_surf_point *points, int cap, int *counts_out, b2f_surf_point **grow, int *need_cap, cudaStream_t st) {
-  const int rows = g.rows, cols = g.cols, NCH = ceil_div(n_frames, C);
+  const int rows = g.rows, cols = g.cols, NCH = (int)cstart.size() - 1;
   const size_t frame_bytes = (size_t)rows * cols * 3;
   const bool trace = getenv("B2F_SURF_TRACE") != nullptr;   // host-side times of the pipeline on stderr
   const auto t_enter = std::chrono::steady_clock::now();
@@ -598,7 +598,7 @@ static int surf_pipeline(b2f_ctx *ctx, const unsigned char *d_rgb, const cudaEve
 
   auto launch_a = [&](int c) -> int {
     const SurfSlot &s = slot[c & 1];
-    const int f0 = c * C, nf = std::min(C, n_frames - f0);
+    const int f0 = cstart[c], nf = cstart[c + 1] - f0;
     if (e_up) B2F_CUDA(cudaStreamWaitEvent(st, e_up[c], 0));
     surf_grey_rowscan<<<dim3(ceil_div(rows, 8), nf), 256, 0, st>>>(d_rgb + frame_bytes * f0, s.sat, rows, cols);
     B2F_LAUNCH_CHECK(ctx);
@@ -633,7 +633,7 @@ static int surf_pipeline(b2f_ctx *ctx, const unsigned char *d_rgb, const cudaEve
   // T(c): fkeys[f] = the key points of frame f0 + f in output order
   auto host_tail = [&](int c, std::vector<std::vector<SurfKey>> &fkeys) -> int {
     const SurfSlot &s = slot[c & 1];
-    const int f0 = c * C, nf = std::min(C, n_frames - f0);
+    const int f0 = cstart[c], nf = cstart[c + 1] - f0;
     B2F_CUDA(cudaEventSynchronize(e_a[c]));
     size_t total_c = 0;
     std::vector<size_t> c_off(nf + 1, 0);
@@ -690,7 +690,7 @@ static int surf_pipeline(b2f_ctx *ctx, const unsigned char *d_rgb, const cudaEve
 
   auto launch_b = [&](int c, const std::vector<std::vector<SurfKey>> &fkeys) -> int {
     const SurfSlot &s = slot[c & 1];
-    const int f0 = c * C, nf = std::min(C, n_frames - f0);
+    const int f0 = cstart[c], nf = cstart[c + 1] - f0;
     size_t nk = 0;
     for (int f = 0; f < nf; f++) { counts_out[f0 + f] = (int)fkeys[f].size(); nk += fkeys[f].size(); }
     if (!nk) return B2F_OK;
@@ -756,7 +756,18 @@ static int surf_run(b2f_ctx *ctx, const uint8_t *frames, bool on_device, int n_f
   B2F_CUDA(cudaSetDevice(ctx->device));
   const size_t frame_bytes = (size_t)rows * cols * 3, in_bytes = frame_bytes * n_frames;
   // chunks of twice the usual input bytes: the host tail of a chunk (one thread per frame) has to fit under the GPU time of the next
-  const int C = frames_per_chunk(ctx, (frame_bytes + 1) / 2, n_frames), NCH = ceil_div(n_frames, C);
+  const int C = frames_per_chunk(ctx, (frame_bytes + 1) / 2, n_frames);
+  // first and last chunk half size: the first upload / GPU stage and the last host tail + descriptor stage overlap with nothing
+  std::vector<int> cstart;
+  {
+    const int edge = (C >= 2 && n_frames >= 2 * C) ? C / 2 : 0;
+    int f = 0;
+    if (edge) { cstart.push_back(0); f = edge; }
+    for (; f < n_frames - edge; f += std::min(C, n_frames - edge - f)) cstart.push_back(f);
+    if (edge) cstart.push_back(n_frames - edge);
+    cstart.push_back(n_frames);
+  }
+  const int NCH = (int)cstart.size() - 1;
   for (int attempt = 0; attempt < 2; attempt++) {
     const size_t slot_keys = (size_t)C * std::min<long long>(max_points, cand_cap);
     const size_t slot_bytes = surf_scratch_bytes(C, g, cand_cap, slot_keys);
@@ -770,7 +781,7 @@ static int surf_run(b2f_ctx *ctx, const uint8_t *frames, bool on_device, int n_f
       B2F_ARENA_CHECK(ctx);
       e_up = ctx->events.data() + NCH;
       for (int c = 0; c < NCH; c++) {
-        const int f0 = c * C, nf = std::min(C, n_frames - f0);
+        const int f0 = cstart[c], nf = cstart[c + 1] - f0;
         bool ok = true;
         for (int f = f0; f < f0 + nf && ok; f++)      // frame by frame: short copies leave gaps for the result copies of earlier chunks
           ok = cudaMemcpyAsync(up + frame_bytes * f, frames + frame_bytes * f, frame_bytes, cudaMemcpyHostToDevice, ctx->s_in) == cudaSuccess;
@@ -794,7 +805,7 @@ static int surf_run(b2f_ctx *ctx, const uint8_t *frames, bool on_device, int n_f
     }
     B2F_ARENA_CHECK(ctx);
     int need = cand_cap;
-    rc = surf_pipeline(ctx, d_in, e_up, e_a, n_frames, C, g, max_points, thr, cand_cap, slot_keys, slot, points, cap, counts, grow, &need, st);
+    rc = surf_pipeline(ctx, d_in, e_up, e_a, n_frames, cstart, g, max_points, thr, cand_cap, slot_keys, slot, points, cap, counts, grow, &need, st);
     if (rc != B2F_OK) {            // nothing of this call may still be in flight when the arena is rewound or the caller reads its arrays
       cudaStreamSynchronize(st);
       pipe_drain(ctx);
