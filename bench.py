@@ -503,8 +503,8 @@ def main():
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     if np.isfinite(float(dt.item())):
         api = "surf_batch (b2f_surf_batch)" if "surf" in dets else \
-              ("features_batch (b2f_features_batch_rgb: one upload of the RGB frames, grey derived on the device; chunked, three streams)" if "fhog" in dets
-               else "features_batch (b2f_features_batch_grey: one upload of the grey frames; chunked, three streams)")
+              ("features_batch (b2f_features_batch_rgb: one upload of the RGB frames, grey derived on the device; chunked; detectors side by side, copies on their own streams)" if "fhog" in dets
+               else "features_batch (b2f_features_batch_grey: one upload of the grey frames; chunked; detectors side by side, copies on their own streams)")
         e2e = {"value": world * B * NX * NY / float(dt.item()) / 1e6, "unit": "Mpixels/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "api": api + ", pinned host buffers"}
     else:
